@@ -1,0 +1,913 @@
+// gpr_api.cu — the C ABI of include/gpr.h over the sm_100a kernels.
+//
+// Seam replaced in the reference (paths relative to /root/reference):
+//   gpu-pruner/src/main.rs:397-437   send PromQL, decode instant vector, dedup by (pod, ns)
+//   gpu-pruner/src/main.rs:494,508   age gate
+// The library never falls back to a CPU path: every entry point that computes needs a CUDA
+// device and reports GPR_E_CUDA otherwise.
+#include "../../include/gpr.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "gpr_kernels.cuh"
+#include "gpr_synth.cuh"
+
+namespace {
+
+constexpr int kLdgWarps = 16;
+constexpr int kLdgUnroll = 8;
+constexpr int kTmaConsumers = 8;
+constexpr uint32_t kTmaMaxChunkBytes = 32768;
+constexpr size_t kTmaSmemBudget = 200 * 1024;
+constexpr int kSlots = 256;      // outstanding async results
+constexpr int kMaxChunkEvents = 64;
+
+std::mutex g_err_mu;
+char g_create_err[512] = "";
+
+// ---- NCCL, loaded on demand so the library itself has no hard dependency on it ----------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool load_nccl(char* err, size_t n) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.ok) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) {
+    snprintf(err, n, "NCCL not loadable: %s", dlerror());
+    return false;
+  }
+#define GPR_SYM(field, name)                                              \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.handle, name)); \
+  if (!g_nccl.field) {                                                    \
+    snprintf(err, n, "NCCL symbol %s missing", name);                     \
+    return false;                                                         \
+  }
+  GPR_SYM(GetUniqueId, "ncclGetUniqueId")
+  GPR_SYM(CommInitRank, "ncclCommInitRank")
+  GPR_SYM(CommDestroy, "ncclCommDestroy")
+  GPR_SYM(AllGather, "ncclAllGather")
+  GPR_SYM(GetErrorString, "ncclGetErrorString")
+#undef GPR_SYM
+  g_nccl.ok = true;
+  return true;
+}
+
+struct Pending {
+  gpr_result* res;
+  int slot;
+};
+
+}  // namespace
+
+struct gpr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_join = nullptr;
+  cudaEvent_t ev_chunk[kMaxChunkEvents] = {};
+  int sm_count = 0;
+  size_t l2_bytes = 0, hbm_bytes = 0;
+  int cc_major = 0, cc_minor = 0;
+  char name[64] = "";
+  int variant = GPR_KERNEL_AUTO;
+  int ldg_ctas_per_sm = 2;
+  int tma_stages_max = 16;
+  size_t chunk_bytes = 8u << 20;
+
+  // capacity for host windows
+  uint32_t max_pods = 0, max_gpus = 0, max_samples = 0;
+  bool cap_power = false;
+  float* d_util_stage = nullptr;
+  float* d_power_stage = nullptr;
+  uint8_t* d_elig_stage = nullptr;
+  int64_t* d_created_stage = nullptr;
+  size_t gate_cap = 0;
+
+  // scratch (grown on demand)
+  uint8_t* d_flags = nullptr;
+  size_t flags_cap = 0;
+  uint32_t* d_bits = nullptr;  // [dbits W | cbits W]
+  size_t bits_cap = 0;
+  uint32_t* d_gather = nullptr;  // [world][2W]
+  size_t gather_cap = 0;
+  float* d_smax = nullptr;
+  size_t smax_cap = 0;
+  unsigned long long* d_counts = nullptr;
+  unsigned int* d_ticket = nullptr;
+  unsigned long long* h_counts = nullptr;  // pinned [kSlots][3]
+  std::vector<Pending> pending;
+
+  void* d_flush = nullptr;
+  size_t flush_bytes = 0;
+
+  // resident window (daemon mode)
+  float* d_res_util = nullptr;
+  float* d_res_power = nullptr;
+  uint32_t res_P = 0, res_G = 0, res_T = 0, res_head = 0;
+  float* d_cols = nullptr;
+  size_t cols_cap = 0;
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+
+  uint64_t launches = 0;
+  char err[512] = "";
+};
+
+namespace {
+
+int fail(gpr_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) {
+    snprintf(c->err, sizeof c->err, "%s", buf);
+  } else {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    snprintf(g_create_err, sizeof g_create_err, "%s", buf);
+  }
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? GPR_E_NOMEM : GPR_E_CUDA,        \
+                  "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+  } while (0)
+
+#define NC(call)                                                                          \
+  do {                                                                                    \
+    ncclResult_t r_ = (call);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      return fail(ctx, GPR_E_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r_));           \
+  } while (0)
+
+template <typename T>
+int grow(gpr_ctx* ctx, T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return GPR_OK;
+  if (*p) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+  }
+  size_t want = need + need / 4 + 64;
+  CU(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
+  *cap = want;
+  return GPR_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// smallest f32 >= thr, so that (m >= thr_f) in f32 equals ((double)m >= thr) for every f32 m
+float threshold_f32(double thr) {
+  float t = (float)thr;
+  if ((double)t < thr) t = nextafterf(t, INFINITY);
+  return t;
+}
+
+bool power_truthy(double thr) { return thr != 0.0 && !std::isnan(thr); }
+
+gpr::TmaLayout tma_layout(const gpr_ctx* ctx, uint32_t T) {
+  gpr::TmaLayout L;
+  const uint32_t row_bytes = T * 4u;
+  L.n_chunks = (row_bytes + kTmaMaxChunkBytes - 1) / kTmaMaxChunkBytes;
+  uint32_t ce = (T + L.n_chunks - 1) / L.n_chunks;
+  ce = (ce + 3u) & ~3u;
+  L.chunk_elems = ce;
+  L.n_chunks = (T + ce - 1) / ce;
+  L.stage_bytes = (ce * 4u + 127u) & ~127u;
+  uint32_t ns = (uint32_t)(kTmaSmemBudget / L.stage_bytes);
+  ns = std::min<uint32_t>(ns, (uint32_t)ctx->tma_stages_max);
+  L.n_stages = std::max<uint32_t>(ns, 2u);
+  return L;
+}
+
+size_t tma_smem_bytes(const gpr::TmaLayout& L) {
+  return (size_t)L.n_stages * L.stage_bytes + (size_t)L.n_stages * 2 * sizeof(uint64_t);
+}
+
+// launch one reduce pass over the rows described by rp
+int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok) {
+  if (rp.total_rows == 0 && !rp.fold_in_kernel) return GPR_OK;
+  int variant = ctx->variant == GPR_KERNEL_AUTO ? GPR_KERNEL_LDG : ctx->variant;
+  if (variant == GPR_KERNEL_TMA && !tma_ok) variant = GPR_KERNEL_LDG;
+  if (variant == GPR_KERNEL_TMA) {
+    const gpr::TmaLayout L = tma_layout(ctx, rp.T);
+    uint32_t grid = (uint32_t)ctx->sm_count;
+    grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, rp.total_rows));
+    gpr::k_reduce_tma<kTmaConsumers>
+        <<<grid, (kTmaConsumers + 1) * 32, tma_smem_bytes(L), ctx->stream>>>(rp, L);
+  } else {
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctx->ldg_ctas_per_sm);
+    const uint32_t need = (rp.total_rows + kLdgWarps - 1) / kLdgWarps;
+    grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, need));
+    gpr::k_reduce_ldg<kLdgWarps, kLdgUnroll><<<grid, kLdgWarps * 32, 0, ctx->stream>>>(rp);
+  }
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return GPR_OK;
+}
+
+int copy_rows_h2d(gpr_ctx* ctx, float* dst, const float* src, size_t n_rows, uint32_t T,
+                  uint64_t ld, cudaStream_t s) {
+  if (n_rows == 0) return GPR_OK;
+  if (ld == T) {
+    CU(cudaMemcpyAsync(dst, src, n_rows * (size_t)T * 4u, cudaMemcpyHostToDevice, s));
+  } else {
+    CU(cudaMemcpy2DAsync(dst, (size_t)T * 4u, src, (size_t)ld * 4u, (size_t)T * 4u, n_rows,
+                         cudaMemcpyHostToDevice, s));
+  }
+  return GPR_OK;
+}
+
+int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resident, bool async) {
+  if (!ctx) return GPR_E_INVALID;
+  if (!win || !res) return fail(ctx, GPR_E_INVALID, "window/result is NULL");
+  if (win->struct_size != sizeof(gpr_window) || res->struct_size != sizeof(gpr_result))
+    return fail(ctx, GPR_E_INVALID, "struct_size mismatch (window %u/%zu result %u/%zu)",
+                win->struct_size, sizeof(gpr_window), res->struct_size, sizeof(gpr_result));
+  CU(cudaSetDevice(ctx->device));
+
+  uint32_t P = win->n_pods, G = win->n_gpus, T = win->n_samples;
+  uint64_t ld = win->row_stride ? win->row_stride : T;
+  const float* util = win->util;
+  const float* power = win->power;
+  int in_kind = win->mem_kind;
+  if (resident) {
+    if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
+    P = ctx->res_P, G = ctx->res_G, T = ctx->res_T, ld = T;
+    util = ctx->d_res_util;
+    power = ctx->d_res_power;
+  }
+  if (in_kind != GPR_MEM_HOST && in_kind != GPR_MEM_DEVICE)
+    return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", in_kind);
+  if (res->out_mem_kind != GPR_MEM_HOST && res->out_mem_kind != GPR_MEM_DEVICE)
+    return fail(ctx, GPR_E_INVALID, "bad out_mem_kind %d", res->out_mem_kind);
+  if (G == 0 || T == 0) return fail(ctx, GPR_E_INVALID, "n_gpus and n_samples must be > 0");
+  if (ld < T) return fail(ctx, GPR_E_INVALID, "row_stride %llu < n_samples %u",
+                          (unsigned long long)ld, T);
+  if (P > 0 && !util) return fail(ctx, GPR_E_INVALID, "util is NULL");
+  if (!res->decision_bits && P > 0) return fail(ctx, GPR_E_INVALID, "decision_bits is NULL");
+  const uint64_t S64 = (uint64_t)P * G;
+  if (S64 > 0x7fffffffull) return fail(ctx, GPR_E_INVALID, "too many series (%llu)",
+                                       (unsigned long long)S64);
+  const uint32_t S = (uint32_t)S64;
+  const uint32_t W = (P + 31u) / 32u;
+  const bool use_power = power != nullptr && power_truthy(win->power_threshold);
+  const bool host_in = !resident && in_kind == GPR_MEM_HOST;
+  const bool gates_host = in_kind == GPR_MEM_HOST;
+  const bool host_out = res->out_mem_kind == GPR_MEM_HOST;
+  const bool comm = ctx->comm != nullptr && ctx->world > 1;
+  if (comm && (P % 32u) != 0)
+    return fail(ctx, GPR_E_INVALID, "with a communicator n_pods must be a multiple of 32 (got %u)", P);
+  if ((int)ctx->pending.size() >= kSlots)
+    return fail(ctx, GPR_E_STATE, "too many outstanding async results; call gpr_sync");
+
+  if (host_in) {
+    if (P > ctx->max_pods || G > ctx->max_gpus || T > ctx->max_samples ||
+        (uint64_t)P * G * T > (uint64_t)ctx->max_pods * ctx->max_gpus * ctx->max_samples)
+      return fail(ctx, GPR_E_CAPACITY, "host window %ux%ux%u exceeds capacity %ux%ux%u", P, G, T,
+                  ctx->max_pods, ctx->max_gpus, ctx->max_samples);
+    if (use_power && !ctx->cap_power)
+      return fail(ctx, GPR_E_CAPACITY, "power plane not reserved (GPR_F_POWER_PLANE)");
+  }
+
+  // ---- scratch ---------------------------------------------------------------------------
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_flags, &ctx->flags_cap, (size_t)2 * S + 16)) != GPR_OK) return rc;
+  if ((rc = grow(ctx, &ctx->d_bits, &ctx->bits_cap, (size_t)2 * W + 2)) != GPR_OK) return rc;
+  if (comm &&
+      (rc = grow(ctx, &ctx->d_gather, &ctx->gather_cap, (size_t)ctx->world * 2 * W + 2)) != GPR_OK)
+    return rc;
+  const bool want_smax = res->series_max != nullptr;
+  if (want_smax && host_out &&
+      (rc = grow(ctx, &ctx->d_smax, &ctx->smax_cap, (size_t)S + 4)) != GPR_OK)
+    return rc;
+
+  // ---- gates -----------------------------------------------------------------------------
+  const uint8_t* d_elig = win->eligible;
+  const int64_t* d_created = win->created_ts;
+  if (gates_host && (win->eligible || win->created_ts)) {
+    if (P > ctx->gate_cap) {
+      if (ctx->d_elig_stage) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(ctx->d_elig_stage));
+        CU(cudaFree(ctx->d_created_stage));
+        ctx->d_elig_stage = nullptr, ctx->d_created_stage = nullptr, ctx->gate_cap = 0;
+      }
+      const size_t cap = (size_t)P + P / 4 + 64;
+      CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_elig_stage), cap));
+      CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_created_stage), cap * sizeof(int64_t)));
+      ctx->gate_cap = cap;
+    }
+    if (win->eligible) {
+      CU(cudaMemcpyAsync(ctx->d_elig_stage, win->eligible, P, cudaMemcpyHostToDevice, ctx->stream));
+      d_elig = ctx->d_elig_stage;
+    }
+    if (win->created_ts) {
+      CU(cudaMemcpyAsync(ctx->d_created_stage, win->created_ts, (size_t)P * sizeof(int64_t),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      d_created = ctx->d_created_stage;
+    }
+  }
+
+  // ---- output targets --------------------------------------------------------------------
+  const bool direct_bits = !host_out && !comm;
+  uint32_t* dbits_dev = direct_bits ? res->decision_bits : ctx->d_bits;
+  uint32_t* cbits_dev = direct_bits ? res->candidate_bits
+                                    : ((res->candidate_bits || comm) ? ctx->d_bits + W : nullptr);
+  float* smax_dev = want_smax ? (host_out ? ctx->d_smax : res->series_max) : nullptr;
+
+  gpr::FoldParams fp;
+  fp.idle_flag = ctx->d_flags;
+  fp.veto_flag = use_power ? ctx->d_flags + S : nullptr;
+  fp.eligible = d_elig;
+  fp.created = d_created;
+  fp.cutoff = win->cutoff_ts;
+  fp.dbits = dbits_dev;
+  fp.cbits = cbits_dev;
+  fp.counts = ctx->d_counts;
+  fp.ticket = ctx->d_ticket;
+  fp.P = P;
+  fp.G = G;
+
+  gpr::ReduceParams rp;
+  memset(&rp, 0, sizeof rp);
+  rp.T = T;
+  rp.thr = threshold_f32(win->power_threshold);
+  rp.fold = fp;
+
+  if (!async) CU(cudaEventRecord(ctx->ev_k0, ctx->stream));
+
+  if (!host_in) {
+    // ---- device-resident window: ONE launch, reduce + ticket fold -------------------------
+    rp.ld = ld;
+    rp.seg[0] = gpr::Segment{util, ctx->d_flags, smax_dev, S, 0u};
+    rp.seg[1] = gpr::Segment{power, ctx->d_flags + S, nullptr, use_power ? S : 0u, 1u};
+    rp.total_rows = S + (use_power ? S : 0u);
+    rp.fold_in_kernel = 1;
+    const bool tma_ok = (T % 4u) == 0 && (ld % 4u) == 0 && aligned16(util) &&
+                        (!use_power || aligned16(power));
+    if (P > 0 && (rc = launch_reduce(ctx, rp, tma_ok)) != GPR_OK) return rc;
+  } else {
+    // ---- host window: pod chunks, H2D on the copy stream overlapped with the reduce --------
+    CU(cudaEventRecord(ctx->ev_join, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));
+    const size_t pod_bytes = (size_t)G * T * 4u * (use_power ? 2u : 1u);
+    uint32_t chunk_pods = (uint32_t)std::max<size_t>(1, ctx->chunk_bytes / std::max<size_t>(pod_bytes, 1));
+    uint32_t n_chunks = P ? (P + chunk_pods - 1) / chunk_pods : 0;
+    rp.ld = T;  // staging is dense
+    rp.fold_in_kernel = 0;
+    const bool tma_ok = (T % 4u) == 0;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t p0 = c * chunk_pods, p1 = std::min(P, p0 + chunk_pods);
+      const size_t row0 = (size_t)p0 * G, n_rows = (size_t)(p1 - p0) * G;
+      float* du = ctx->d_util_stage + row0 * T;
+      if ((rc = copy_rows_h2d(ctx, du, util + row0 * ld, n_rows, T, ld, ctx->copy_stream)) != GPR_OK)
+        return rc;
+      float* dp = nullptr;
+      if (use_power) {
+        dp = ctx->d_power_stage + row0 * T;
+        if ((rc = copy_rows_h2d(ctx, dp, power + row0 * ld, n_rows, T, ld, ctx->copy_stream)) != GPR_OK)
+          return rc;
+      }
+      cudaEvent_t ev = ctx->ev_chunk[c % kMaxChunkEvents];
+      CU(cudaEventRecord(ev, ctx->copy_stream));
+      CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
+      rp.seg[0] = gpr::Segment{du, ctx->d_flags + row0, smax_dev ? smax_dev + row0 : nullptr,
+                               (uint32_t)n_rows, 0u};
+      rp.seg[1] = gpr::Segment{dp, ctx->d_flags + S + row0, nullptr,
+                               use_power ? (uint32_t)n_rows : 0u, 1u};
+      rp.total_rows = (uint32_t)n_rows * (use_power ? 2u : 1u);
+      if ((rc = launch_reduce(ctx, rp, tma_ok)) != GPR_OK) return rc;
+    }
+    CU(cudaMemsetAsync(ctx->d_counts, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    if (W > 0) {
+      const uint32_t warps_per_cta = 8;
+      uint32_t grid = std::min<uint32_t>((W + warps_per_cta - 1) / warps_per_cta,
+                                         (uint32_t)ctx->sm_count * 4u);
+      gpr::k_fold<<<grid, warps_per_cta * 32, 0, ctx->stream>>>(fp);
+      ctx->launches++;
+      CU(cudaGetLastError());
+    }
+  }
+  if (P == 0) CU(cudaMemsetAsync(ctx->d_counts, 0, 3 * sizeof(unsigned long long), ctx->stream));
+
+  // ---- the one collective: allgather of the packed bitmap over NVLink ----------------------
+  if (comm && W > 0) {
+    NC(g_nccl.AllGather(ctx->d_bits, ctx->d_gather, (size_t)2 * W, ncclUint32, ctx->comm,
+                        ctx->stream));
+  }
+  if (!async) CU(cudaEventRecord(ctx->ev_k1, ctx->stream));
+
+  // ---- deliver -----------------------------------------------------------------------------
+  const cudaMemcpyKind out_kind = host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (W > 0) {
+    if (comm) {
+      CU(cudaMemcpy2DAsync(res->decision_bits, (size_t)W * 4u, ctx->d_gather, (size_t)2 * W * 4u,
+                           (size_t)W * 4u, ctx->world, out_kind, ctx->stream));
+      if (res->candidate_bits)
+        CU(cudaMemcpy2DAsync(res->candidate_bits, (size_t)W * 4u, ctx->d_gather + W,
+                             (size_t)2 * W * 4u, (size_t)W * 4u, ctx->world, out_kind, ctx->stream));
+    } else if (host_out) {
+      CU(cudaMemcpyAsync(res->decision_bits, ctx->d_bits, (size_t)W * 4u, out_kind, ctx->stream));
+      if (res->candidate_bits)
+        CU(cudaMemcpyAsync(res->candidate_bits, ctx->d_bits + W, (size_t)W * 4u, out_kind,
+                           ctx->stream));
+    }
+  }
+  if (want_smax && host_out && S > 0)
+    CU(cudaMemcpyAsync(res->series_max, ctx->d_smax, (size_t)S * 4u, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  const int slot = (int)ctx->pending.size();
+  CU(cudaMemcpyAsync(ctx->h_counts + (size_t)slot * 3, ctx->d_counts, 3 * sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->pending.push_back(Pending{res, slot});
+  res->kernel_ms = 0.0;
+  return GPR_OK;
+}
+
+int sync_impl(gpr_ctx* ctx) {
+  CU(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->pending.clear();
+    return fail(ctx, GPR_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+  }
+  for (const Pending& p : ctx->pending) {
+    const unsigned long long* c = ctx->h_counts + (size_t)p.slot * 3;
+    p.res->n_series = c[0];
+    p.res->n_candidates = c[1];
+    p.res->n_decisions = c[2];
+  }
+  ctx->pending.clear();
+  return GPR_OK;
+}
+
+__global__ void k_append(float* __restrict__ dst, const float* __restrict__ src, uint32_t n_rows,
+                         uint32_t T, uint32_t head, uint32_t n_new, uint64_t ld_src) {
+  for (uint32_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    float* out = dst + (size_t)r * T;
+    const float* in = src + (size_t)r * ld_src;
+    for (uint32_t j = threadIdx.x; j < n_new; j += blockDim.x) {
+      uint32_t t = head + j;
+      if (t >= T) t -= T;
+      out[t] = in[j];
+    }
+  }
+}
+
+}  // namespace
+
+// ===========================================================================================
+// extern "C"
+// ===========================================================================================
+#define GPR_TRY try {
+#define GPR_CATCH(ctxp)                                                     \
+  }                                                                         \
+  catch (const std::bad_alloc&) {                                           \
+    return fail(ctxp, GPR_E_NOMEM, "host allocation failed");               \
+  }                                                                         \
+  catch (...) {                                                             \
+    return fail(ctxp, GPR_E_INVALID, "unexpected C++ exception");           \
+  }
+
+extern "C" {
+
+int gpr_version(void) {
+  return GPR_VERSION_MAJOR * 10000 + GPR_VERSION_MINOR * 100 + GPR_VERSION_PATCH;
+}
+
+const char* gpr_last_error(const gpr_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+void gpr_destroy(gpr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+  void* dev[] = {ctx->d_util_stage, ctx->d_power_stage, ctx->d_elig_stage, ctx->d_created_stage,
+                 ctx->d_flags,      ctx->d_bits,        ctx->d_gather,     ctx->d_smax,
+                 ctx->d_counts,     ctx->d_ticket,      ctx->d_flush,      ctx->d_res_util,
+                 ctx->d_res_power,  ctx->d_cols};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  cudaEvent_t evs[] = {ctx->ev_k0, ctx->ev_k1, ctx->ev_t0, ctx->ev_t1, ctx->ev_join};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
+  gpr_ctx* ctx = nullptr;  // errors before allocation go to the global slot
+  GPR_TRY
+  if (!cfg || !out) return fail(nullptr, GPR_E_INVALID, "config/out is NULL");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(gpr_config))
+    return fail(nullptr, GPR_E_INVALID, "gpr_config.struct_size %u != %zu", cfg->struct_size,
+                sizeof(gpr_config));
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, GPR_E_CUDA, "no CUDA device (%s); this engine has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (cfg->device < 0 || cfg->device >= n_dev)
+    return fail(nullptr, GPR_E_INVALID, "device %d out of range [0,%d)", cfg->device, n_dev);
+  gpr_ctx* c = new gpr_ctx();
+  c->device = cfg->device;
+  // from here on failures are reported through the global slot too, then the ctx is freed
+  auto bail = [&](int code) {
+    {
+      std::lock_guard<std::mutex> lk(g_err_mu);
+      snprintf(g_create_err, sizeof g_create_err, "%s", c->err);
+    }
+    gpr_destroy(c);
+    return code;
+  };
+  ctx = c;
+  auto body = [&]() -> int {
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    c->hbm_bytes = prop.totalGlobalMem;
+    c->cc_major = prop.major, c->cc_minor = prop.minor;
+    snprintf(c->name, sizeof c->name, "%s", prop.name);
+    if (prop.major < 10)
+      return fail(c, GPR_E_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a",
+                  prop.name, prop.major, prop.minor);
+    if (cfg->stream) {
+      c->stream = static_cast<cudaStream_t>(cfg->stream);
+    } else {
+      CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->own_stream = true;
+    }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev_k0));
+    CU(cudaEventCreate(&c->ev_k1));
+    CU(cudaEventCreate(&c->ev_t0));
+    CU(cudaEventCreate(&c->ev_t1));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (cudaEvent_t& ev : c->ev_chunk) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_counts), 3 * sizeof(unsigned long long)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_ticket), sizeof(unsigned int)));
+    CU(cudaMemset(c->d_counts, 0, 3 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+    CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
+                      (size_t)kSlots * 3 * sizeof(unsigned long long)));
+    c->pending.reserve(kSlots);
+
+    c->variant = cfg->kernel_variant;
+    if (const char* k = getenv("GPR_KERNEL")) {
+      if (!strcmp(k, "ldg")) c->variant = GPR_KERNEL_LDG;
+      else if (!strcmp(k, "tma")) c->variant = GPR_KERNEL_TMA;
+    }
+    if (c->variant < GPR_KERNEL_AUTO || c->variant > GPR_KERNEL_TMA)
+      return fail(c, GPR_E_INVALID, "bad kernel_variant %d", c->variant);
+    c->ldg_ctas_per_sm = std::max(1, env_int("GPR_LDG_CTAS", 2));
+    c->tma_stages_max = std::max(2, env_int("GPR_TMA_STAGES", 16));
+    c->chunk_bytes = (size_t)std::max(1, env_int("GPR_CHUNK_MB", 8)) << 20;
+    CU(cudaFuncSetAttribute(gpr::k_reduce_tma<kTmaConsumers>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaSmemBudget + 4096)));
+
+    c->max_pods = cfg->max_pods, c->max_gpus = cfg->max_gpus, c->max_samples = cfg->max_samples;
+    c->cap_power = (cfg->flags & GPR_F_POWER_PLANE) != 0;
+    const size_t cells = (size_t)cfg->max_pods * cfg->max_gpus * cfg->max_samples;
+    if (cells) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&c->d_util_stage), cells * sizeof(float) + 256));
+      if (c->cap_power)
+        CU(cudaMalloc(reinterpret_cast<void**>(&c->d_power_stage), cells * sizeof(float) + 256));
+    }
+    return GPR_OK;
+  };
+  int rc = body();
+  if (rc != GPR_OK) return bail(rc);
+  *out = c;
+  return GPR_OK;
+  GPR_CATCH(nullptr)
+}
+
+int gpr_decide_async(gpr_ctx* ctx, const gpr_window* win, gpr_result* res) {
+  GPR_TRY
+  return decide_impl(ctx, win, res, false, true);
+  GPR_CATCH(ctx)
+}
+
+int gpr_sync(gpr_ctx* ctx) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  return sync_impl(ctx);
+  GPR_CATCH(ctx)
+}
+
+static int decide_blocking(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resident) {
+  int rc = decide_impl(ctx, win, res, resident, false);
+  if (rc != GPR_OK) {
+    if (ctx) {
+      cudaStreamSynchronize(ctx->stream);
+      ctx->pending.clear();
+    }
+    return rc;
+  }
+  rc = sync_impl(ctx);
+  if (rc != GPR_OK) return rc;
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1));
+  res->kernel_ms = ms;
+  return GPR_OK;
+}
+
+int gpr_decide(gpr_ctx* ctx, const gpr_window* win, gpr_result* res) {
+  GPR_TRY
+  return decide_blocking(ctx, win, res, false);
+  GPR_CATCH(ctx)
+}
+
+int gpr_decide_resident(gpr_ctx* ctx, const gpr_window* win, gpr_result* res) {
+  GPR_TRY
+  return decide_blocking(ctx, win, res, true);
+  GPR_CATCH(ctx)
+}
+
+// ---- resident window -----------------------------------------------------------------------
+int gpr_resident_init(gpr_ctx* ctx, uint32_t P, uint32_t G, uint32_t T, uint32_t flags) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (P == 0 || G == 0 || T == 0) return fail(ctx, GPR_E_INVALID, "empty resident window");
+  if ((uint64_t)P * G > 0x7fffffffull) return fail(ctx, GPR_E_INVALID, "too many series");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_res_util) CU(cudaFree(ctx->d_res_util));
+  if (ctx->d_res_power) CU(cudaFree(ctx->d_res_power));
+  ctx->d_res_util = ctx->d_res_power = nullptr;
+  const size_t bytes = (size_t)P * G * T * sizeof(float);
+  CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_res_util), bytes));
+  // 0xFFFFFFFF is a NaN: every step starts out "no sample"
+  CU(cudaMemsetAsync(ctx->d_res_util, 0xFF, bytes, ctx->stream));
+  if (flags & GPR_F_POWER_PLANE) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_res_power), bytes));
+    CU(cudaMemsetAsync(ctx->d_res_power, 0xFF, bytes, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->res_P = P, ctx->res_G = G, ctx->res_T = T, ctx->res_head = 0;
+  return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
+int gpr_append(gpr_ctx* ctx, const float* util_cols, const float* power_cols, uint32_t n_new,
+               uint64_t row_stride, int32_t mem_kind) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
+  if (n_new == 0) return GPR_OK;
+  if (!util_cols) return fail(ctx, GPR_E_INVALID, "util_cols is NULL");
+  if (mem_kind != GPR_MEM_HOST && mem_kind != GPR_MEM_DEVICE)
+    return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", mem_kind);
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t T = ctx->res_T;
+  const size_t rows = (size_t)ctx->res_P * ctx->res_G;
+  uint64_t ld = row_stride ? row_stride : n_new;
+  if (ld < n_new) return fail(ctx, GPR_E_INVALID, "row_stride < n_new");
+  // only the newest T columns can survive in a ring of T
+  uint32_t skip = n_new > T ? n_new - T : 0;
+  const uint32_t n_eff = n_new - skip;
+  const float* planes_in[2] = {util_cols, ctx->d_res_power ? power_cols : nullptr};
+  float* planes_out[2] = {ctx->d_res_util, ctx->d_res_power};
+  for (int pl = 0; pl < 2; ++pl) {
+    if (!planes_in[pl]) continue;
+    const float* src = planes_in[pl] + skip;
+    uint64_t ld_dev = ld;
+    if (mem_kind == GPR_MEM_HOST) {
+      int rc = grow(ctx, &ctx->d_cols, &ctx->cols_cap, rows * n_eff + 4);
+      if (rc != GPR_OK) return rc;
+      CU(cudaMemcpy2DAsync(ctx->d_cols, (size_t)n_eff * 4u, src, (size_t)ld * 4u,
+                           (size_t)n_eff * 4u, rows, cudaMemcpyHostToDevice, ctx->stream));
+      src = ctx->d_cols;
+      ld_dev = n_eff;
+    }
+    const uint32_t grid = (uint32_t)std::min<size_t>(rows, (size_t)ctx->sm_count * 16);
+    k_append<<<grid, 128, 0, ctx->stream>>>(planes_out[pl], src, (uint32_t)rows, T,
+                                            (ctx->res_head + skip) % T, n_eff, ld_dev);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  ctx->res_head = (uint32_t)(((uint64_t)ctx->res_head + n_new) % T);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
+int gpr_resident_planes(gpr_ctx* ctx, float** util, float** power, uint64_t* row_stride) {
+  if (!ctx) return GPR_E_INVALID;
+  if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window");
+  if (util) *util = ctx->d_res_util;
+  if (power) *power = ctx->d_res_power;
+  if (row_stride) *row_stride = ctx->res_T;
+  return GPR_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------
+int gpr_comm_unique_id(void* id128) {
+  gpr_ctx* ctx = nullptr;
+  GPR_TRY
+  if (!id128) return fail(nullptr, GPR_E_INVALID, "id buffer is NULL");
+  char err[256];
+  if (!load_nccl(err, sizeof err)) return fail(nullptr, GPR_E_NCCL, "%s", err);
+  static_assert(sizeof(ncclUniqueId) == GPR_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return GPR_OK;
+  GPR_CATCH(nullptr)
+}
+
+int gpr_comm_init(gpr_ctx* ctx, const void* id128, int rank, int world) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (!id128 || world < 1 || rank < 0 || rank >= world)
+    return fail(ctx, GPR_E_INVALID, "bad communicator arguments (rank %d world %d)", rank, world);
+  if (ctx->comm) return fail(ctx, GPR_E_STATE, "communicator already attached");
+  char err[256];
+  if (!load_nccl(err, sizeof err)) return fail(ctx, GPR_E_NCCL, "%s", err);
+  CU(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NC(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+  ctx->rank = rank, ctx->world = world;
+  return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
+int gpr_comm_destroy(gpr_ctx* ctx) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (ctx->comm) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    NC(g_nccl.CommDestroy(ctx->comm));
+    ctx->comm = nullptr;
+  }
+  ctx->rank = 0, ctx->world = 1;
+  return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
+// ---- memory helpers -----------------------------------------------------------------------------
+int gpr_host_alloc(gpr_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMallocHost(out, bytes ? bytes : 1));
+  return GPR_OK;
+}
+int gpr_host_free(gpr_ctx* ctx, void* p) {
+  if (!ctx) return GPR_E_INVALID;
+  if (p) CU(cudaFreeHost(p));
+  return GPR_OK;
+}
+int gpr_device_alloc(gpr_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMalloc(out, bytes ? bytes : 1));
+  return GPR_OK;
+}
+int gpr_device_free(gpr_ctx* ctx, void* p) {
+  if (!ctx) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  if (p) CU(cudaFree(p));
+  return GPR_OK;
+}
+int gpr_memcpy(gpr_ctx* ctx, void* dst, const void* src, size_t bytes, int32_t dst_kind,
+               int32_t src_kind) {
+  if (!ctx) return GPR_E_INVALID;
+  if (bytes == 0) return GPR_OK;
+  if (!dst || !src) return fail(ctx, GPR_E_INVALID, "NULL pointer in gpr_memcpy");
+  CU(cudaSetDevice(ctx->device));
+  cudaMemcpyKind k = dst_kind == GPR_MEM_DEVICE
+                         ? (src_kind == GPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                         : (src_kind == GPR_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+  CU(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+// ---- measurement support --------------------------------------------------------------------------
+int gpr_timer_begin(gpr_ctx* ctx) {
+  if (!ctx) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev_t0, ctx->stream));
+  return GPR_OK;
+}
+int gpr_timer_end(gpr_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev_t1));
+  float f = 0.f;
+  CU(cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+  *ms = f;
+  return GPR_OK;
+}
+int gpr_flush_l2(gpr_ctx* ctx) {
+  if (!ctx) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->d_flush) {
+    ctx->flush_bytes = std::max<size_t>(ctx->l2_bytes * 2, (size_t)256 << 20);
+    CU(cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+  }
+  CU(cudaMemsetAsync(ctx->d_flush, 0x5a, ctx->flush_bytes, ctx->stream));
+  return GPR_OK;
+}
+int gpr_launch_count(const gpr_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return GPR_E_INVALID;
+  *n = ctx->launches;
+  return GPR_OK;
+}
+int gpr_get_device_info(gpr_ctx* ctx, gpr_device_info* info) {
+  if (!ctx || !info) return GPR_E_INVALID;
+  if (info->struct_size != sizeof(gpr_device_info))
+    return fail(ctx, GPR_E_INVALID, "gpr_device_info.struct_size mismatch");
+  info->sm_count = ctx->sm_count;
+  info->cc_major = ctx->cc_major, info->cc_minor = ctx->cc_minor;
+  info->l2_bytes = ctx->l2_bytes, info->hbm_bytes = ctx->hbm_bytes;
+  memcpy(info->name, ctx->name, sizeof info->name);
+  return GPR_OK;
+}
+
+// ---- synthetic windows -----------------------------------------------------------------------------
+int gpr_synth_fill(gpr_ctx* ctx, uint64_t seed, int32_t plane, float* dst, uint64_t pod_offset,
+                   uint32_t n_pods, uint32_t n_gpus, uint32_t n_samples, uint64_t row_stride) {
+  if (!ctx) return GPR_E_INVALID;
+  if (!dst || n_gpus == 0 || n_samples == 0 || (plane != 0 && plane != 1))
+    return fail(ctx, GPR_E_INVALID, "bad gpr_synth_fill arguments");
+  const uint64_t rows = (uint64_t)n_pods * n_gpus;
+  if (rows == 0) return GPR_OK;
+  if (rows > 0x7fffffffull) return fail(ctx, GPR_E_INVALID, "too many series");
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t ld = row_stride ? row_stride : n_samples;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(rows, (uint64_t)ctx->sm_count * 32);
+  gpr::k_synth_fill<<<grid, 256, 0, ctx->stream>>>(dst, seed, plane, pod_offset * n_gpus,
+                                                   (uint32_t)rows, n_samples, ld);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+int gpr_synth_eligible(gpr_ctx* ctx, uint64_t seed, uint8_t* dst, uint64_t pod_offset,
+                       uint32_t n_pods) {
+  if (!ctx) return GPR_E_INVALID;
+  if (!dst) return fail(ctx, GPR_E_INVALID, "dst is NULL");
+  if (n_pods == 0) return GPR_OK;
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t grid = std::min<uint32_t>((n_pods + 255u) / 256u, (uint32_t)ctx->sm_count * 8u);
+  gpr::k_synth_eligible<<<grid, 256, 0, ctx->stream>>>(dst, seed, pod_offset, n_pods);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,430 @@
+// gpr_kernels.cuh — sm_100a kernels of the idle-decision engine.
+//
+// The arithmetic replaced here is the PromQL expression of the reference,
+// /root/reference/gpu-pruner/src/query.promql.j2:1-44, plus the Rust-side ANY-GPU dedup
+// (gpu-pruner/src/main.rs:416-437) and age gate (main.rs:473-510):
+//
+//   smax(p,g)   = max_over_time(util[p,g,:])         NaN = missing step, NaN iff none present
+//   idle_s(p,g) = smax(p,g) == 0                     (query.promql.j2:35)
+//   veto(p)     = any g: max_over_time(power[p,g,:]) >= T       (query.promql.j2:36-44)
+//   candidate   = (any g: idle_s) && !veto           (main.rs:416-437)
+//   decision    = candidate && eligible && !(created >= cutoff)  (main.rs:473-510)
+//
+// Two phases:
+//   reduce : one pass over the f32 tensor(s) — 100 % of the algorithmic bytes — producing one
+//            flag byte per series row.  Two interchangeable implementations:
+//              k_reduce_ldg  128-bit ld.global.nc streaming loads, warp per row
+//              k_reduce_tma  cp.async.bulk (TMA, SASS UBLKCP) rows into an mbarrier-guarded
+//                            shared-memory ring; one producer lane, consumer warps reduce
+//   fold   : flags -> per-pod verdict -> packed uint32 bitmaps + counts (touches S bytes, <0.1 %).
+//            Either the last CTA of the reduce grid (ticket) or a standalone kernel.
+//
+// HBM-bound streaming max: ~1 FMNMX per 4 bytes, no tensor cores, no reuse.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpr {
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+struct Segment {
+  const float* base;   // first row of this segment (device)
+  uint8_t* flag;       // one byte per row: util -> idle_s, power -> veto_s
+  float* smax;         // optional per-row window max (util segment only)
+  uint32_t n_rows;
+  uint32_t is_power;   // 0: flag = (max == 0)   1: flag = (max >= thr)
+};
+
+struct FoldParams {
+  const uint8_t* idle_flag;   // [P*G]
+  const uint8_t* veto_flag;   // [P*G] or nullptr
+  const uint8_t* eligible;    // [P] or nullptr
+  const int64_t* created;     // [P] or nullptr
+  int64_t cutoff;
+  uint32_t* dbits;            // [ceil(P/32)]
+  uint32_t* cbits;            // [ceil(P/32)] or nullptr
+  unsigned long long* counts; // [3] n_series, n_candidates, n_decisions (overwritten)
+  unsigned int* ticket;       // self-resetting arrival counter (ticket mode)
+  uint32_t P, G;
+};
+
+struct ReduceParams {
+  Segment seg[2];
+  uint64_t ld;        // elements between rows
+  uint32_t T;
+  uint32_t total_rows;
+  float thr;          // smallest f32 >= (double) power threshold
+  int fold_in_kernel; // 1: last CTA folds (single-launch path)
+  FoldParams fold;
+};
+
+__device__ __forceinline__ float nan_f() { return __int_as_float(0x7fffffff); }
+
+// PTX max.f32: if exactly one operand is NaN the other is returned; NaN only if both are.
+// Folding from NaN therefore reproduces Prometheus' max_over_time on the present samples.
+// Built without -use_fast_math / -ftz so denormals are compared, not flushed (K7).
+__device__ __forceinline__ float fold4(float m, const float4& v) {
+  return fmaxf(fmaxf(fmaxf(m, v.x), fmaxf(v.y, v.z)), v.w);
+}
+
+__device__ __forceinline__ float warp_max(float m) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m;
+}
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (every byte is used once)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// fold: flags -> verdict bits.  One lane per pod, one warp per bitmap word.
+// ------------------------------------------------------------------------------------------
+template <int BATCH>
+__device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin, uint32_t w_end,
+                                           uint32_t w_step, int lane, unsigned long long& n_series,
+                                           unsigned long long& n_cand, unsigned long long& n_dec) {
+  const uint32_t G = f.G;
+  for (uint32_t w0 = w_begin; w0 < w_end; w0 += w_step * BATCH) {
+    uint32_t idle_cnt[BATCH];
+    uint32_t veto[BATCH];
+    uint32_t elig[BATCH];
+    // issue every load of the batch before consuming any (latency-bound phase)
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const uint32_t w = w0 + b * w_step;
+      const uint32_t pod = w * 32u + lane;
+      idle_cnt[b] = 0, veto[b] = 0, elig[b] = 0;
+      if (w < w_end && pod < f.P) {
+        const size_t r = (size_t)pod * G;
+        if (G == 4) {
+          const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(f.idle_flag + r));
+          idle_cnt[b] = __popc(v & 0x01010101u);
+          if (f.veto_flag) veto[b] = __ldcg(reinterpret_cast<const uint32_t*>(f.veto_flag + r)) != 0;
+        } else if (G == 8) {
+          const uint2 v = __ldcg(reinterpret_cast<const uint2*>(f.idle_flag + r));
+          idle_cnt[b] = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u);
+          if (f.veto_flag) {
+            const uint2 q = __ldcg(reinterpret_cast<const uint2*>(f.veto_flag + r));
+            veto[b] = (q.x | q.y) != 0;
+          }
+        } else {
+          for (uint32_t g = 0; g < G; ++g) {
+            idle_cnt[b] += __ldcg(f.idle_flag + r + g) & 1u;
+            if (f.veto_flag) veto[b] |= __ldcg(f.veto_flag + r + g);
+          }
+        }
+        uint32_t e = 1;
+        if (f.eligible) e = f.eligible[pod] != 0;
+        if (f.created && f.created[pod] >= f.cutoff) e = 0;
+        elig[b] = e;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const uint32_t w = w0 + b * w_step;
+      if (w >= w_end) break;  // warp-uniform
+      const bool cand = idle_cnt[b] > 0 && !veto[b];
+      const bool dec = cand && elig[b];
+      const uint32_t cw = __ballot_sync(0xffffffffu, cand);
+      const uint32_t dw = __ballot_sync(0xffffffffu, dec);
+      uint32_t ns = cand ? idle_cnt[b] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+      if (lane == 0) {
+        f.dbits[w] = dw;
+        if (f.cbits) f.cbits[w] = cw;
+        n_series += ns;
+        n_cand += __popc(cw);
+        n_dec += __popc(dw);
+      }
+    }
+  }
+}
+
+// block-level sum of the three counters into fold.counts (call from all threads)
+__device__ __forceinline__ void block_counts(unsigned long long* sh3, unsigned long long a,
+                                             unsigned long long b, unsigned long long c, int lane) {
+  if (lane == 0 && (a | b | c)) {
+    atomicAdd(&sh3[0], a);
+    atomicAdd(&sh3[1], b);
+    atomicAdd(&sh3[2], c);
+  }
+}
+
+// Ticket fold at the end of a reduce grid: every CTA publishes its flags, the last one to
+// arrive packs the whole bitmap.  The ticket resets itself so the buffer is reusable by the
+// next launch on the stream without a memset.
+__device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
+  __shared__ unsigned int s_last;
+  __shared__ unsigned long long s_cnt[3];
+  __threadfence();  // this thread's flag stores are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+    const unsigned int t = atomicAdd(f.ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const uint32_t n_words = (f.P + 31u) / 32u;
+  unsigned long long a = 0, b = 0, c = 0;
+  fold_words<8>(f, warp, n_words, n_warps, lane, a, b, c);
+  block_counts(s_cnt, a, b, c, lane);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    f.counts[0] = s_cnt[0];
+    f.counts[1] = s_cnt[1];
+    f.counts[2] = s_cnt[2];
+    *f.ticket = 0u;
+  }
+}
+
+// Standalone fold (chunked host-window path): counts must be zeroed by the caller.
+__global__ void __launch_bounds__(256) k_fold(FoldParams f) {
+  __shared__ unsigned long long s_cnt[3];
+  if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const uint32_t n_words = (f.P + 31u) / 32u;
+  unsigned long long a = 0, b = 0, c = 0;
+  fold_words<1>(f, gw, n_words, gridDim.x * warps_per_cta, lane, a, b, c);
+  block_counts(s_cnt, a, b, c, lane);
+  __syncthreads();
+  if (threadIdx.x == 0 && (s_cnt[0] | s_cnt[1] | s_cnt[2])) {
+    atomicAdd(&f.counts[0], s_cnt[0]);
+    atomicAdd(&f.counts[1], s_cnt[1]);
+    atomicAdd(&f.counts[2], s_cnt[2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared row bookkeeping
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* row_ptr(const ReduceParams& p, uint32_t r, uint32_t& seg,
+                                                uint32_t& local) {
+  seg = r >= p.seg[0].n_rows ? 1u : 0u;
+  local = r - (seg ? p.seg[0].n_rows : 0u);
+  return p.seg[seg].base + (size_t)local * p.ld;
+}
+
+__device__ __forceinline__ void publish_row(const ReduceParams& p, uint32_t seg, uint32_t local,
+                                            float m) {
+  const Segment& s = p.seg[seg];
+  // util: `== 0` (NaN fails, -0.0 passes); power: `>= T` (NaN fails)
+  const bool flag = s.is_power ? (m >= p.thr) : (m == 0.0f);
+  s.flag[local] = flag ? 1 : 0;
+  if (s.smax) s.smax[local] = m;
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce, variant 1: vectorised streaming loads
+// ------------------------------------------------------------------------------------------
+// One warp per series row; rows of a CTA's contiguous range are handed out through a
+// shared-memory counter so the SM stays busy until its range is exhausted.  Any base
+// alignment / T / stride is accepted: a scalar head peels to 16-byte alignment, the body is
+// float4, a scalar tail finishes the row.
+template <int U>
+__device__ __forceinline__ float row_max_ldg(const float* __restrict__ row, uint32_t T, int lane) {
+  float m = nan_f();
+  const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+  uint32_t head = (uint32_t)(((16u - (a & 15u)) & 15u) >> 2);
+  if (head > T) head = T;
+  if ((uint32_t)lane < head) m = __ldg(row + lane);
+  const float4* __restrict__ v = reinterpret_cast<const float4*>(row + head);
+  const uint32_t nv = (T - head) >> 2;
+  uint32_t i = lane;
+  // full batches: U independent 16-byte loads per lane in flight
+  for (; i + 32u * (U - 1) < nv; i += 32u * U) {
+    float4 x[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) x[j] = ldg_stream(v + i + 32u * j);
+#pragma unroll
+    for (int j = 0; j < U; ++j) m = fold4(m, x[j]);
+  }
+  // one predicated batch for the remainder
+  if (i < nv) {
+    float4 x[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint32_t k = i + 32u * j;
+      x[j] = make_float4(nan_f(), nan_f(), nan_f(), nan_f());
+      if (k < nv) x[j] = ldg_stream(v + k);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) m = fold4(m, x[j]);
+  }
+  const uint32_t done = head + nv * 4u;
+  if (done + lane < T) m = fmaxf(m, __ldg(row + done + lane));
+  return warp_max(m);
+}
+
+template <int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32) k_reduce_ldg(ReduceParams p) {
+  __shared__ unsigned int s_next;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t r0 = (uint32_t)(((uint64_t)p.total_rows * blockIdx.x) / gridDim.x);
+  const uint32_t r1 = (uint32_t)(((uint64_t)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
+  if (threadIdx.x == 0) s_next = r0 + WARPS;
+  __syncthreads();
+  uint32_t r = r0 + warp;
+  while (r < r1) {
+    uint32_t seg, local;
+    const float* row = row_ptr(p, r, seg, local);
+    const float m = row_max_ldg<U>(row, p.T, lane);
+    if (lane == 0) {
+      publish_row(p, seg, local, m);
+      r = atomicAdd(&s_next, 1u);
+    }
+    r = __shfl_sync(0xffffffffu, r, 0);
+  }
+  if (p.fold_in_kernel) fold_by_last_cta(p.fold);
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce, variant 2: TMA bulk copies into a shared-memory ring
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier.
+// The data is read exactly once: L2 evict_first keeps it from displacing anything useful.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+struct TmaLayout {
+  uint32_t n_stages;
+  uint32_t stage_bytes;   // capacity of one stage (multiple of 128)
+  uint32_t chunk_elems;   // elements copied per chunk (multiple of 4); row = n_chunks chunks
+  uint32_t n_chunks;
+};
+
+// Requirements (checked on the host): every row base 16-byte aligned, T % 4 == 0.
+// Warp 0 lane 0 = producer; warps 1..NC = consumers.  Item q = (row k, chunk c) lives in stage
+// q % n_stages; full[stage] flips when the bytes have landed, empty[stage] when the consumer
+// warp has finished reading.  Row k belongs to consumer warp k % NC, which carries the
+// running max across the row's chunks.
+template <int NC>
+__global__ void __launch_bounds__((NC + 1) * 32) k_reduce_tma(ReduceParams p, TmaLayout L) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)L.n_stages * L.stage_bytes);
+  uint64_t* empty = full + L.n_stages;
+
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t r0 = (uint32_t)(((uint64_t)p.total_rows * blockIdx.x) / gridDim.x);
+  const uint32_t r1 = (uint32_t)(((uint64_t)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t n_rows = r1 - r0;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < L.n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol = l2_evict_first_policy();
+      uint32_t q = 0;
+      for (uint32_t k = 0; k < n_rows; ++k) {
+        uint32_t seg, local;
+        const float* row = row_ptr(p, r0 + k, seg, local);
+        for (uint32_t c = 0; c < L.n_chunks; ++c, ++q) {
+          const uint32_t st = q % L.n_stages;
+          const uint32_t it = q / L.n_stages;
+          mbar_wait(&empty[st], (it & 1u) ^ 1u);  // passes immediately on the first lap
+          const uint32_t e0 = c * L.chunk_elems;
+          const uint32_t ne = min(L.chunk_elems, p.T - e0);
+          mbar_expect_tx(&full[st], ne * 4u);
+          tma_load_1d(smem + (size_t)st * L.stage_bytes, row + e0, ne * 4u, &full[st], pol);
+        }
+      }
+    }
+  } else {
+    const uint32_t cw = warp - 1;
+    for (uint32_t k = cw; k < n_rows; k += NC) {
+      float m = nan_f();
+      for (uint32_t c = 0; c < L.n_chunks; ++c) {
+        const uint32_t q = k * L.n_chunks + c;
+        const uint32_t st = q % L.n_stages;
+        const uint32_t it = q / L.n_stages;
+        mbar_wait(&full[st], it & 1u);
+        const float4* v = reinterpret_cast<const float4*>(smem + (size_t)st * L.stage_bytes);
+        const uint32_t e0 = c * L.chunk_elems;
+        const uint32_t nv = min(L.chunk_elems, p.T - e0) >> 2;
+        float m0 = nan_f(), m1 = nan_f();
+        uint32_t i = lane;
+        for (; i + 32u < nv; i += 64u) {
+          const float4 a = v[i], b = v[i + 32u];
+          m0 = fold4(m0, a);
+          m1 = fold4(m1, b);
+        }
+        if (i < nv) m0 = fold4(m0, v[i]);
+        m = fmaxf(m, fmaxf(m0, m1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+      }
+      m = warp_max(m);
+      if (lane == 0) {
+        uint32_t seg, local;
+        (void)row_ptr(p, r0 + k, seg, local);
+        publish_row(p, seg, local, m);
+      }
+    }
+  }
+  if (p.fold_in_kernel) fold_by_last_cta(p.fold);
+}
+
+}  // namespace gpr

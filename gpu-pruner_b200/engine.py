@@ -1,0 +1,280 @@
+"""Thin object wrapper over the C ABI (include/gpr.h) for Python callers, tests and bench.py.
+
+The product is libgpr.so; this file only marshals arguments.  It mirrors the seam of the
+reference at ``/root/reference/gpu-pruner/src/main.rs:397-437`` ("run the aggregation, get
+back the candidate set"): :meth:`IdleEngine.decide` takes the window matrix and returns the
+packed decision bitmap plus the ``QueryResponse``-style counts (``lib.rs:131-134``).
+
+There is no CPU fallback anywhere in this module: if libgpr.so or a CUDA device is missing the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import ffi
+
+_KERNELS = {"auto": ffi.GPR_KERNEL_AUTO, "ldg": ffi.GPR_KERNEL_LDG, "tma": ffi.GPR_KERNEL_TMA}
+
+
+class GprError(RuntimeError):
+    """Non-zero status from libgpr.so (the Rust wrapper would turn this into ``anyhow!``,
+    feeding the failure counter at main.rs:310-321)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ffi.ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+        self.message = message
+
+
+@dataclass
+class Decision:
+    n_pods: int
+    decision_bits: np.ndarray            # uint32[ceil(P/32)] (x world with a communicator)
+    candidate_bits: Optional[np.ndarray]
+    series_max: Optional[np.ndarray]     # float32[P, G]
+    n_series: int                        # QueryResponse.num_pods (series, pre-dedup; main.rs:418)
+    n_candidates: int
+    n_decisions: int
+    kernel_ms: float
+
+    def pods(self, bits: Optional[np.ndarray] = None) -> np.ndarray:
+        """Indices of set bits (the idle-pod set), ascending."""
+        w = self.decision_bits if bits is None else bits
+        flat = np.unpackbits(np.ascontiguousarray(w, dtype="<u4").view(np.uint8), bitorder="little")
+        return np.flatnonzero(flat)
+
+
+def _ptr(x) -> Optional[int]:
+    """numpy array / torch tensor / int address / None -> address."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(f"cannot take the address of {type(x)!r}")
+
+
+class IdleEngine:
+    """One context = one GPU.  Not re-entrant (one call at a time), thread-agnostic."""
+
+    def __init__(self, device: int = 0, max_pods: int = 0, max_gpus: int = 0, max_samples: int = 0,
+                 power_plane: bool = False, kernel: str = "auto", stream: Optional[int] = None):
+        self._lib = ffi.load()
+        cfg = ffi.gpr_config()
+        cfg.struct_size = C.sizeof(ffi.gpr_config)
+        cfg.device = device
+        cfg.max_pods, cfg.max_gpus, cfg.max_samples = max_pods, max_gpus, max_samples
+        cfg.flags = ffi.GPR_F_POWER_PLANE if power_plane else 0
+        cfg.kernel_variant = _KERNELS[kernel]
+        cfg.stream = stream
+        h = C.c_void_p()
+        rc = self._lib.gpr_create(C.byref(cfg), C.byref(h))
+        if rc != ffi.GPR_OK:
+            raise GprError(rc, (self._lib.gpr_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self._keep = []  # result structs / arrays referenced by outstanding async calls
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != ffi.GPR_OK:
+            raise GprError(rc, (self._lib.gpr_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- hot path ---------------------------------------------------------------------------
+    def _window(self, util, power, eligible, created_ts, cutoff_ts, P, G, T, row_stride,
+                power_threshold, mem_kind) -> ffi.gpr_window:
+        w = ffi.gpr_window()
+        w.struct_size = C.sizeof(ffi.gpr_window)
+        w.mem_kind = mem_kind
+        w.util, w.power = _ptr(util), _ptr(power)
+        w.eligible, w.created_ts = _ptr(eligible), _ptr(created_ts)
+        w.cutoff_ts = int(cutoff_ts)
+        w.n_pods, w.n_gpus, w.n_samples = P, G, T
+        w.row_stride = row_stride
+        w.power_threshold = float(power_threshold) if power_threshold is not None else 0.0
+        return w
+
+    def decide(self, util: np.ndarray, power: Optional[np.ndarray] = None,
+               eligible: Optional[np.ndarray] = None, created_ts: Optional[np.ndarray] = None,
+               cutoff_ts: int = 0, power_threshold: Optional[float] = 0.0,
+               want_candidates: bool = True, want_series_max: bool = False,
+               world: int = 1) -> Decision:
+        """Blocking decision over a HOST window ``util[P, G, T]`` (float32, NaN = no sample)."""
+        util = np.ascontiguousarray(util, dtype=np.float32)
+        if util.ndim != 3:
+            raise ValueError("util must be [pods, gpus, samples]")
+        P, G, T = util.shape
+        if power is not None:
+            power = np.ascontiguousarray(power, dtype=np.float32)
+            if power.shape != util.shape:
+                raise ValueError("power must have util's shape")
+        if eligible is not None:
+            eligible = np.ascontiguousarray(eligible, dtype=np.uint8)
+        if created_ts is not None:
+            created_ts = np.ascontiguousarray(created_ts, dtype=np.int64)
+        w = self._window(util, power, eligible, created_ts, cutoff_ts, P, G, T, 0,
+                         power_threshold, ffi.GPR_MEM_HOST)
+        W = (P + 31) // 32 * world
+        dbits = np.zeros(max(W, 1), dtype=np.uint32)
+        cbits = np.zeros(max(W, 1), dtype=np.uint32) if want_candidates else None
+        smax = np.zeros((P, G), dtype=np.float32) if want_series_max else None
+        r = ffi.gpr_result()
+        r.struct_size = C.sizeof(ffi.gpr_result)
+        r.out_mem_kind = ffi.GPR_MEM_HOST
+        r.decision_bits, r.candidate_bits, r.series_max = _ptr(dbits), _ptr(cbits), _ptr(smax)
+        self._check(self._lib.gpr_decide(self._h, C.byref(w), C.byref(r)))
+        return Decision(P, dbits[:W], None if cbits is None else cbits[:W], smax, r.n_series,
+                        r.n_candidates, r.n_decisions, r.kernel_ms)
+
+    def decide_ptr(self, util, P: int, G: int, T: int, decision_bits, *, power=None, eligible=None,
+                   created_ts=None, cutoff_ts: int = 0, power_threshold: Optional[float] = 0.0,
+                   candidate_bits=None, series_max=None, row_stride: int = 0,
+                   in_kind: int = ffi.GPR_MEM_DEVICE, out_kind: int = ffi.GPR_MEM_DEVICE,
+                   blocking: bool = True, resident: bool = False) -> ffi.gpr_result:
+        """Raw-pointer form (device tensors, pinned host buffers).  With ``blocking=False`` the
+        call only enqueues; counters in the returned struct are valid after :meth:`sync`."""
+        w = self._window(util, power, eligible, created_ts, cutoff_ts, P, G, T, row_stride,
+                         power_threshold, in_kind)
+        r = ffi.gpr_result()
+        r.struct_size = C.sizeof(ffi.gpr_result)
+        r.out_mem_kind = out_kind
+        r.decision_bits, r.candidate_bits, r.series_max = (_ptr(decision_bits), _ptr(candidate_bits),
+                                                           _ptr(series_max))
+        if resident:
+            self._check(self._lib.gpr_decide_resident(self._h, C.byref(w), C.byref(r)))
+        elif blocking:
+            self._check(self._lib.gpr_decide(self._h, C.byref(w), C.byref(r)))
+        else:
+            self._keep.append((w, r))
+            self._check(self._lib.gpr_decide_async(self._h, C.byref(w), C.byref(r)))
+        return r
+
+    def sync(self):
+        self._check(self._lib.gpr_sync(self._h))
+        self._keep.clear()
+
+    # ---- resident window (daemon mode) --------------------------------------------------------
+    def resident_init(self, P: int, G: int, T: int, power_plane: bool = False):
+        self._check(self._lib.gpr_resident_init(self._h, P, G, T,
+                                                ffi.GPR_F_POWER_PLANE if power_plane else 0))
+
+    def append(self, util_cols, power_cols=None, n_new: Optional[int] = None, row_stride: int = 0,
+               mem_kind: int = ffi.GPR_MEM_HOST):
+        if isinstance(util_cols, np.ndarray):
+            util_cols = np.ascontiguousarray(util_cols, dtype=np.float32)
+            n_new = util_cols.shape[-1]
+            if power_cols is not None:
+                power_cols = np.ascontiguousarray(power_cols, dtype=np.float32)
+        self._check(self._lib.gpr_append(self._h, _ptr(util_cols), _ptr(power_cols), n_new,
+                                         row_stride, mem_kind))
+        self._keep_cols = (util_cols, power_cols)
+
+    def resident_planes(self):
+        u, p, ld = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self._lib.gpr_resident_planes(self._h, C.byref(u), C.byref(p), C.byref(ld)))
+        return u.value, p.value, ld.value
+
+    # ---- multi-GPU ------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(ffi.GPR_UNIQUE_ID_BYTES)
+        rc = self._lib.gpr_comm_unique_id(buf)
+        if rc != ffi.GPR_OK:
+            raise GprError(rc, (self._lib.gpr_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, ffi.GPR_UNIQUE_ID_BYTES)
+        self._check(self._lib.gpr_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._check(self._lib.gpr_comm_destroy(self._h))
+
+    # ---- memory / measurement helpers -------------------------------------------------------------
+    def host_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.gpr_host_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def host_free(self, ptr: int):
+        self._check(self._lib.gpr_host_free(self._h, ptr))
+
+    def host_array(self, shape, dtype) -> np.ndarray:
+        """numpy view over freshly allocated PINNED host memory (freed with the engine)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = self.host_alloc(max(n, 1))
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.gpr_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        self._check(self._lib.gpr_device_free(self._h, ptr))
+
+    def memcpy(self, dst, src, nbytes: int, dst_kind: int, src_kind: int):
+        self._check(self._lib.gpr_memcpy(self._h, _ptr(dst), _ptr(src), nbytes, dst_kind, src_kind))
+
+    def timer_begin(self):
+        self._check(self._lib.gpr_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        self._check(self._lib.gpr_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._check(self._lib.gpr_flush_l2(self._h))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.gpr_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def device_info(self) -> dict:
+        info = ffi.gpr_device_info()
+        info.struct_size = C.sizeof(ffi.gpr_device_info)
+        self._check(self._lib.gpr_get_device_info(self._h, C.byref(info)))
+        return {"name": info.name.decode(errors="replace"), "sm_count": info.sm_count,
+                "cc": (info.cc_major, info.cc_minor), "l2_bytes": info.l2_bytes,
+                "hbm_bytes": info.hbm_bytes}
+
+    def synth_fill(self, seed: int, plane: int, dst, pod_offset: int, P: int, G: int, T: int,
+                   row_stride: int = 0):
+        self._check(self._lib.gpr_synth_fill(self._h, seed, plane, _ptr(dst), pod_offset, P, G, T,
+                                             row_stride))
+
+    def synth_eligible(self, seed: int, dst, pod_offset: int, P: int):
+        self._check(self._lib.gpr_synth_eligible(self._h, seed, _ptr(dst), pod_offset, P))

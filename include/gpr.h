@@ -1,0 +1,231 @@
+/*
+ * gpr.h — C ABI of the B200 idle-decision engine (libgpr.so).
+ *
+ * This is the drop-in boundary for gpu-pruner's one data-parallel path: the per-pod
+ * windowed aggregation of DCGM GPU-utilisation samples into an idle/active verdict.
+ * In the reference that arithmetic is a PromQL expression evaluated by a remote
+ * Prometheus server; the seam this ABI replaces is, in the reference tree,
+ *
+ *     gpu-pruner/src/main.rs:397      client.query(query).get().await        (send PromQL)
+ *     gpu-pruner/src/main.rs:405-409  response.data().into_vector()          (decode result)
+ *     gpu-pruner/src/main.rs:416-437  HashSet<(pod, namespace)> dedup        (ANY-GPU fold)
+ *     gpu-pruner/src/main.rs:494,508  create_time >= now - lookback => skip  (age gate)
+ *
+ * i.e. "obtain window matrix -> gpr_decide() -> expand set bits to PodMetricData".
+ * Everything after main.rs:444 (Kubernetes lookups, owner walk, scale patches) is
+ * unchanged host logic.
+ *
+ * Conventions:
+ *   - every entry point returns int: 0 = GPR_OK, negative = GPR_E_*; the message for the
+ *     last failure on a context is gpr_last_error(ctx) (gpr_last_error(NULL) for a failed
+ *     gpr_create).  Nothing aborts, exits or throws across this boundary, so the caller's
+ *     failure accounting (main.rs:310-321, QUERY_FAILURES) keeps working.
+ *   - the caller owns every in/out buffer; the library owns only what is behind gpr_ctx*.
+ *   - a context is NOT re-entrant (one call at a time, matching the single caller at
+ *     main.rs:297) but it is thread-agnostic: every entry point selects its device itself
+ *     and keeps no thread-local state, because tokio may migrate the caller between ticks.
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *
+ * There is no CPU fallback: without a CUDA device gpr_create fails with GPR_E_CUDA.
+ */
+#ifndef GPR_H_
+#define GPR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GPR_API __attribute__((visibility("default")))
+#else
+#define GPR_API
+#endif
+
+#define GPR_VERSION_MAJOR 0
+#define GPR_VERSION_MINOR 1
+#define GPR_VERSION_PATCH 0
+
+/* ---- status codes ------------------------------------------------------------------- */
+enum {
+  GPR_OK = 0,
+  GPR_E_INVALID = -1,   /* bad argument / shape / struct_size                           */
+  GPR_E_CUDA = -2,      /* CUDA runtime or driver error (message has the CUDA string)    */
+  GPR_E_NOMEM = -3,     /* allocation failed (host or device)                            */
+  GPR_E_CAPACITY = -4,  /* window larger than the capacity given at gpr_create           */
+  GPR_E_STATE = -5,     /* call not valid in this state (e.g. resident window not set)   */
+  GPR_E_NCCL = -6,      /* NCCL error or NCCL library not loadable                       */
+  GPR_E_UNSUPPORTED = -7
+};
+
+/* ---- where a buffer lives ------------------------------------------------------------ */
+enum {
+  GPR_MEM_HOST = 0,   /* host memory (pinned via gpr_host_alloc for full PCIe speed)     */
+  GPR_MEM_DEVICE = 1  /* device memory on the context's GPU                              */
+};
+
+/* ---- kernel selection (both variants are always built) ------- */
+enum {
+  GPR_KERNEL_AUTO = 0,
+  GPR_KERNEL_LDG = 1,  /* 128-bit ld.global.nc streaming loads, warp per series          */
+  GPR_KERNEL_TMA = 2   /* cp.async.bulk (TMA) rows into an mbarrier-guarded smem ring     */
+};
+
+/* ---- gpr_config.flags ---------------------------------------------------------------- */
+#define GPR_F_POWER_PLANE 0x1u /* reserve staging for the power plane (host windows)      */
+
+typedef struct gpr_ctx gpr_ctx;
+
+/* Creation-time configuration.  Set struct_size = sizeof(gpr_config).                    */
+typedef struct gpr_config {
+  uint32_t struct_size;
+  int32_t device;          /* CUDA device ordinal                                        */
+  uint32_t max_pods;       /* capacity for HOST windows (staging in HBM); 0 = none        */
+  uint32_t max_gpus;
+  uint32_t max_samples;
+  uint32_t flags;          /* GPR_F_*                                                    */
+  int32_t kernel_variant;  /* GPR_KERNEL_*                                               */
+  int32_t reserved0;
+  void *stream;            /* optional caller-owned cudaStream_t all work is ordered on;
+                              NULL = the context creates its own non-blocking stream      */
+} gpr_config;
+
+/*
+ * One window = the range-vector result laid out densely.
+ *
+ *   util[p][g][t]   f32, t fastest; NaN = "no sample" (stale / absent / scrape gap).
+ *                   Restates DCGM_FI_DEV_GPU_UTIL{pod != ""}[Nm]   (query.promql.j2:16-20)
+ *   power[p][g][t]  f32 or NULL.  Restates DCGM_FI_DEV_POWER_USAGE{...}[Nm]
+ *                   (query.promql.j2:39-42).  Used only if power_threshold is "truthy".
+ *   row_stride      elements between consecutive (p,g) rows; 0 means n_samples.
+ *   power_threshold watts; the veto clause exists iff power != NULL and the threshold is
+ *                   neither 0.0 nor NaN (Jinja truthiness of `args.power_threshold`,
+ *                   query.promql.j2:36).  veto(p) = any g: max_t power[p][g][:] >= threshold.
+ *   eligible[p]     u8 or NULL: 0 = pod fails the Pending / missing-timestamp gates
+ *                   (main.rs:473-492).  NULL = all eligible.
+ *   created_ts[p]   i64 or NULL: pod creation time in caller-chosen ticks; the pod is skipped
+ *                   iff created_ts[p] >= cutoff_ts   (main.rs:494,508-510, cutoff = now -
+ *                   (duration*60 + grace_period)).  INT64_MAX = "no creationTimestamp".
+ */
+typedef struct gpr_window {
+  uint32_t struct_size;
+  int32_t mem_kind;        /* GPR_MEM_*: applies to util, power, eligible, created_ts     */
+  const float *util;
+  const float *power;
+  const uint8_t *eligible;
+  const int64_t *created_ts;
+  int64_t cutoff_ts;
+  uint32_t n_pods;
+  uint32_t n_gpus;
+  uint32_t n_samples;
+  uint32_t reserved0;
+  uint64_t row_stride;
+  double power_threshold;
+} gpr_window;
+
+/*
+ * Result.  Bitmaps are packed little-endian within a word: pod p is bit (p & 31) of word
+ * (p >> 5); padding bits above n_pods are zero.  With a communicator attached
+ * (gpr_comm_init) the bitmaps cover all ranks: world * ceil(n_pods/32) words, rank-major,
+ * and n_pods must be a multiple of 32 and identical on every rank.
+ *
+ *   decision_bits   required.  candidate(p) && eligible(p)         (after main.rs:473-510)
+ *   candidate_bits  optional.  (any g: max_t util == 0) && !veto(p) (what Prometheus + the
+ *                   dedup at main.rs:416-437 return)
+ *   series_max      optional, n_pods * n_gpus f32: window max per series, NaN if no sample
+ *                   (the reference's reported `value` is this / 100; lib.rs:184,
+ *                   query.promql.j2:20).
+ *   out_mem_kind    where the three buffers above live.
+ *   n_series        number of idle series in non-vetoed pods = QueryResponse.num_pods
+ *                   (main.rs:418; a series count despite the name).
+ *   n_candidates / n_decisions   popcounts of the two bitmaps (this rank's pods).
+ *   kernel_ms       device time of the decision kernel(s) for this call (CUDA events);
+ *                   0 from the _async entry point.
+ */
+typedef struct gpr_result {
+  uint32_t struct_size;
+  int32_t out_mem_kind;
+  uint32_t *decision_bits;
+  uint32_t *candidate_bits;
+  float *series_max;
+  uint64_t n_series;
+  uint64_t n_candidates;
+  uint64_t n_decisions;
+  double kernel_ms;
+} gpr_result;
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+GPR_API int gpr_version(void); /* major*10000 + minor*100 + patch */
+GPR_API int gpr_create(const gpr_config *cfg, gpr_ctx **out);
+GPR_API void gpr_destroy(gpr_ctx *ctx);
+GPR_API const char *gpr_last_error(const gpr_ctx *ctx);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* Blocking: on return the result buffers and counters are complete.                      */
+GPR_API int gpr_decide(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
+/* Enqueue only (device or pinned-host buffers); counters are filled by gpr_sync().       */
+GPR_API int gpr_decide_async(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
+GPR_API int gpr_sync(gpr_ctx *ctx);
+
+/* ---- resident window for daemon mode (--daemon-mode / --check-interval, main.rs:286-330)
+ * The window lives in HBM as a ring over the time axis; each tick appends the columns that
+ * arrived since the previous tick and rescans.  max is order-independent so ring order is
+ * irrelevant to the verdict.                                                              */
+GPR_API int gpr_resident_init(gpr_ctx *ctx, uint32_t n_pods, uint32_t n_gpus, uint32_t n_samples,
+                      uint32_t flags /* GPR_F_POWER_PLANE */);
+/* new columns laid out [p][g][n_new] (row_stride 0 = n_new); power_cols may be NULL.      */
+GPR_API int gpr_append(gpr_ctx *ctx, const float *util_cols, const float *power_cols, uint32_t n_new,
+               uint64_t row_stride, int32_t mem_kind);
+/* win->util / win->power are ignored (resident planes are used); gates come from win.     */
+GPR_API int gpr_decide_resident(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
+/* device pointers of the resident planes (for generators / inspection); power may be NULL */
+GPR_API int gpr_resident_planes(gpr_ctx *ctx, float **util, float **power, uint64_t *row_stride);
+
+/* ---- multi-GPU: one process per GPU, pods sharded by rank, one allgather of the bitmap - */
+#define GPR_UNIQUE_ID_BYTES 128
+GPR_API int gpr_comm_unique_id(void *id128);                       /* rank 0; ship to the others */
+GPR_API int gpr_comm_init(gpr_ctx *ctx, const void *id128, int rank, int world);
+GPR_API int gpr_comm_destroy(gpr_ctx *ctx);
+
+/* ---- memory helpers ------------------------------------------------------------------ */
+GPR_API int gpr_host_alloc(gpr_ctx *ctx, size_t bytes, void **out); /* pinned host memory         */
+GPR_API int gpr_host_free(gpr_ctx *ctx, void *p);
+GPR_API int gpr_device_alloc(gpr_ctx *ctx, size_t bytes, void **out);
+GPR_API int gpr_device_free(gpr_ctx *ctx, void *p);
+GPR_API int gpr_memcpy(gpr_ctx *ctx, void *dst, const void *src, size_t bytes,
+               int32_t dst_kind, int32_t src_kind);          /* blocking                   */
+
+/* ---- measurement support ------------------------------------------------------------- */
+/* CUDA events on the context's stream: begin; ...enqueue...; end -> elapsed ms.           */
+GPR_API int gpr_timer_begin(gpr_ctx *ctx);
+GPR_API int gpr_timer_end(gpr_ctx *ctx, double *ms);
+/* writes > L2-size bytes so the next launch starts with a cold L2                          */
+GPR_API int gpr_flush_l2(gpr_ctx *ctx);
+/* number of kernels this context has launched since creation                               */
+GPR_API int gpr_launch_count(const gpr_ctx *ctx, uint64_t *n);
+/* device facts: sm_count, l2 bytes, total HBM bytes, cc major/minor                        */
+typedef struct gpr_device_info {
+  uint32_t struct_size;
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+  uint64_t l2_bytes;
+  uint64_t hbm_bytes;
+  char name[64];
+} gpr_device_info;
+GPR_API int gpr_get_device_info(gpr_ctx *ctx, gpr_device_info *info);
+
+/* ---- synthetic DCGM windows; counter-based so any implementation can
+ * regenerate any cell.  plane: 0 = util, 1 = power.  Fills rows for pods
+ * [pod_offset, pod_offset + n_pods) of a seeded (.., n_gpus, n_samples) universe into dst
+ * (device memory, row_stride 0 = n_samples).  elig/created are optional device outputs.    */
+GPR_API int gpr_synth_fill(gpr_ctx *ctx, uint64_t seed, int32_t plane, float *dst, uint64_t pod_offset,
+                   uint32_t n_pods, uint32_t n_gpus, uint32_t n_samples, uint64_t row_stride);
+GPR_API int gpr_synth_eligible(gpr_ctx *ctx, uint64_t seed, uint8_t *dst, uint64_t pod_offset,
+                       uint32_t n_pods);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPR_H_ */
