@@ -6,5 +6,7 @@ of the reference controller lives under ``host/``.
 """
 from . import ffi
 from .engine import Decision, GprError, IdleEngine
+from . import sharding
+from .sharding import Shard, shard_pods
 
-__all__ = ["ffi", "Decision", "GprError", "IdleEngine"]
+__all__ = ["ffi", "Decision", "GprError", "IdleEngine", "Shard", "shard_pods"]

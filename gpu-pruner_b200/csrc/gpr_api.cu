@@ -28,9 +28,7 @@ namespace {
 
 constexpr int kLdgWarps = 16;
 constexpr int kLdgUnroll = 8;
-constexpr int kTmaConsumers = 8;
-constexpr uint32_t kTmaMaxChunkBytes = 32768;
-constexpr size_t kTmaSmemBudget = 200 * 1024;
+constexpr size_t kTmaSmemBudget = 208 * 1024;
 constexpr int kSlots = 256;      // outstanding async results
 constexpr int kMaxChunkEvents = 64;
 
@@ -100,7 +98,9 @@ struct gpr_ctx {
   char name[64] = "";
   int variant = GPR_KERNEL_AUTO;
   int ldg_ctas_per_sm = 2;
-  int tma_stages_max = 16;
+  int tma_depth_max = 3;
+  int tma_warps = 8;
+  int tma_chunk_bytes = 8192;
   size_t chunk_bytes = 8u << 20;
 
   // capacity for host windows
@@ -207,23 +207,30 @@ float threshold_f32(double thr) {
 
 bool power_truthy(double thr) { return thr != 0.0 && !std::isnan(thr); }
 
-gpr::TmaLayout tma_layout(const gpr_ctx* ctx, uint32_t T) {
+gpr::TmaLayout tma_layout(const gpr_ctx* ctx, uint32_t T, int nw) {
   gpr::TmaLayout L;
   const uint32_t row_bytes = T * 4u;
-  L.n_chunks = (row_bytes + kTmaMaxChunkBytes - 1) / kTmaMaxChunkBytes;
+  const uint32_t max_chunk = (uint32_t)ctx->tma_chunk_bytes;
+  L.n_chunks = (row_bytes + max_chunk - 1) / max_chunk;
   uint32_t ce = (T + L.n_chunks - 1) / L.n_chunks;
   ce = (ce + 3u) & ~3u;
   L.chunk_elems = ce;
   L.n_chunks = (T + ce - 1) / ce;
   L.stage_bytes = (ce * 4u + 127u) & ~127u;
-  uint32_t ns = (uint32_t)(kTmaSmemBudget / L.stage_bytes);
-  ns = std::min<uint32_t>(ns, (uint32_t)ctx->tma_stages_max);
-  L.n_stages = std::max<uint32_t>(ns, 2u);
+  uint32_t d = (uint32_t)((kTmaSmemBudget - 1024) / ((size_t)L.stage_bytes * nw));
+  d = std::min<uint32_t>(d, (uint32_t)ctx->tma_depth_max);
+  L.depth = std::max<uint32_t>(d, 1u);
   return L;
 }
 
-size_t tma_smem_bytes(const gpr::TmaLayout& L) {
-  return (size_t)L.n_stages * L.stage_bytes + (size_t)L.n_stages * 2 * sizeof(uint64_t);
+size_t tma_smem_bytes(const gpr::TmaLayout& L, int nw) {
+  return (size_t)nw * L.depth * L.stage_bytes + (size_t)nw * L.depth * sizeof(uint64_t);
+}
+
+template <int NW>
+void launch_tma(gpr_ctx* ctx, const gpr::ReduceParams& rp, uint32_t grid) {
+  const gpr::TmaLayout L = tma_layout(ctx, rp.T, NW);
+  gpr::k_reduce_tma<NW><<<grid, NW * 32, tma_smem_bytes(L, NW), ctx->stream>>>(rp, L);
 }
 
 // launch one reduce pass over the rows described by rp
@@ -232,11 +239,12 @@ int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok) {
   int variant = ctx->variant == GPR_KERNEL_AUTO ? GPR_KERNEL_LDG : ctx->variant;
   if (variant == GPR_KERNEL_TMA && !tma_ok) variant = GPR_KERNEL_LDG;
   if (variant == GPR_KERNEL_TMA) {
-    const gpr::TmaLayout L = tma_layout(ctx, rp.T);
+    const int nw = ctx->tma_warps;
     uint32_t grid = (uint32_t)ctx->sm_count;
-    grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, rp.total_rows));
-    gpr::k_reduce_tma<kTmaConsumers>
-        <<<grid, (kTmaConsumers + 1) * 32, tma_smem_bytes(L), ctx->stream>>>(rp, L);
+    grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, (rp.total_rows + nw - 1) / nw));
+    if (nw == 4) launch_tma<4>(ctx, rp, grid);
+    else if (nw == 16) launch_tma<16>(ctx, rp, grid);
+    else launch_tma<8>(ctx, rp, grid);
   } else {
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->ldg_ctas_per_sm);
     const uint32_t need = (rp.total_rows + kLdgWarps - 1) / kLdgWarps;
@@ -610,10 +618,17 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     if (c->variant < GPR_KERNEL_AUTO || c->variant > GPR_KERNEL_TMA)
       return fail(c, GPR_E_INVALID, "bad kernel_variant %d", c->variant);
     c->ldg_ctas_per_sm = std::max(1, env_int("GPR_LDG_CTAS", 2));
-    c->tma_stages_max = std::max(2, env_int("GPR_TMA_STAGES", 16));
+    c->tma_depth_max = std::max(1, env_int("GPR_TMA_DEPTH", 3));
+    c->tma_warps = env_int("GPR_TMA_WARPS", 8);
+    if (c->tma_warps != 4 && c->tma_warps != 8 && c->tma_warps != 16) c->tma_warps = 8;
+    c->tma_chunk_bytes = std::min(65536, std::max(512, env_int("GPR_TMA_CHUNK", 8192))) & ~15;
     c->chunk_bytes = (size_t)std::max(1, env_int("GPR_CHUNK_MB", 8)) << 20;
-    CU(cudaFuncSetAttribute(gpr::k_reduce_tma<kTmaConsumers>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaSmemBudget + 4096)));
+    CU(cudaFuncSetAttribute(gpr::k_reduce_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kTmaSmemBudget));
+    CU(cudaFuncSetAttribute(gpr::k_reduce_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kTmaSmemBudget));
+    CU(cudaFuncSetAttribute(gpr::k_reduce_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kTmaSmemBudget));
 
     c->max_pods = cfg->max_pods, c->max_gpus = cfg->max_gpus, c->max_samples = cfg->max_samples;
     c->cap_power = (cfg->flags & GPR_F_POWER_PLANE) != 0;

@@ -14,8 +14,8 @@
 //   reduce : one pass over the f32 tensor(s) — 100 % of the algorithmic bytes — producing one
 //            flag byte per series row.  Two interchangeable implementations:
 //              k_reduce_ldg  128-bit ld.global.nc streaming loads, warp per row
-//              k_reduce_tma  cp.async.bulk (TMA, SASS UBLKCP) rows into an mbarrier-guarded
-//                            shared-memory ring; one producer lane, consumer warps reduce
+//              k_reduce_tma  cp.async.bulk (TMA, SASS UBLKCP) row chunks into warp-private,
+//                            mbarrier-guarded shared-memory rings
 //   fold   : flags -> per-pod verdict -> packed uint32 bitmaps + counts (touches S bytes, <0.1 %).
 //            Either the last CTA of the reduce grid (ticket) or a standalone kernel.
 //
@@ -342,86 +342,86 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 }
 
 struct TmaLayout {
-  uint32_t n_stages;
+  uint32_t depth;         // stages per warp
   uint32_t stage_bytes;   // capacity of one stage (multiple of 128)
-  uint32_t chunk_elems;   // elements copied per chunk (multiple of 4); row = n_chunks chunks
+  uint32_t chunk_elems;   // elements copied per chunk (multiple of 4); a row = n_chunks chunks
   uint32_t n_chunks;
 };
 
 // Requirements (checked on the host): every row base 16-byte aligned, T % 4 == 0.
-// Warp 0 lane 0 = producer; warps 1..NC = consumers.  Item q = (row k, chunk c) lives in stage
-// q % n_stages; full[stage] flips when the bytes have landed, empty[stage] when the consumer
-// warp has finished reading.  Row k belongs to consumer warp k % NC, which carries the
-// running max across the row's chunks.
-template <int NC>
-__global__ void __launch_bounds__((NC + 1) * 32) k_reduce_tma(ReduceParams p, TmaLayout L) {
+//
+// Every warp runs its own TMA pipeline: a private ring of `depth` stages, each with one
+// mbarrier.  Lane 0 issues a 1-D bulk copy (row chunk -> stage) with the byte count expected on
+// the stage's barrier; the warp waits for the bytes, folds the chunk out of shared memory with
+// conflict-free 128-bit LDS, and — once every lane has finished reading — lane 0 immediately
+// re-arms the same stage with the chunk `depth` items ahead.  No producer warp, no empty
+// barriers, no cross-warp synchronisation: a stage is only ever touched by its owner warp, so
+// the mbarrier phase parity cannot alias, and NW * depth * chunk bytes stay in flight per SM
+// without holding a single register.
+// Rows r0 + w, r0 + w + NW, ... of the CTA's contiguous range belong to warp w.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_reduce_tma(ReduceParams p, TmaLayout L) {
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)L.n_stages * L.stage_bytes);
-  uint64_t* empty = full + L.n_stages;
-
   const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t w = threadIdx.x >> 5;
+  const uint32_t D = L.depth;
+  unsigned char* stage0 = smem + (size_t)w * D * L.stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NW * D * L.stage_bytes) + w * D;
+
   const uint32_t r0 = (uint32_t)(((uint64_t)p.total_rows * blockIdx.x) / gridDim.x);
   const uint32_t r1 = (uint32_t)(((uint64_t)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
   const uint32_t n_rows = r1 - r0;
+  const uint32_t my_rows = n_rows > w ? (n_rows - w + NW - 1) / NW : 0u;
+  const uint32_t n_items = my_rows * L.n_chunks;
 
-  if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < L.n_stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
+  if (lane == 0) {
+    for (uint32_t s = 0; s < D; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  __syncwarp();
+  const uint64_t pol = l2_evict_first_policy();
 
-  if (warp == 0) {
+  // producer cursor (tracked by every lane, acted on by lane 0)
+  uint32_t pi = 0, pc = 0, pst = 0, issued = 0;
+  auto issue = [&]() {
+    uint32_t seg, local;
+    const float* row = row_ptr(p, r0 + w + NW * pi, seg, local);
+    const uint32_t e0 = pc * L.chunk_elems;
+    const uint32_t bytes = min(L.chunk_elems, p.T - e0) * 4u;
     if (lane == 0) {
-      const uint64_t pol = l2_evict_first_policy();
-      uint32_t q = 0;
-      for (uint32_t k = 0; k < n_rows; ++k) {
-        uint32_t seg, local;
-        const float* row = row_ptr(p, r0 + k, seg, local);
-        for (uint32_t c = 0; c < L.n_chunks; ++c, ++q) {
-          const uint32_t st = q % L.n_stages;
-          const uint32_t it = q / L.n_stages;
-          mbar_wait(&empty[st], (it & 1u) ^ 1u);  // passes immediately on the first lap
-          const uint32_t e0 = c * L.chunk_elems;
-          const uint32_t ne = min(L.chunk_elems, p.T - e0);
-          mbar_expect_tx(&full[st], ne * 4u);
-          tma_load_1d(smem + (size_t)st * L.stage_bytes, row + e0, ne * 4u, &full[st], pol);
-        }
-      }
+      mbar_expect_tx(&full[pst], bytes);
+      tma_load_1d(stage0 + (size_t)pst * L.stage_bytes, row + e0, bytes, &full[pst], pol);
     }
-  } else {
-    const uint32_t cw = warp - 1;
-    for (uint32_t k = cw; k < n_rows; k += NC) {
-      float m = nan_f();
-      for (uint32_t c = 0; c < L.n_chunks; ++c) {
-        const uint32_t q = k * L.n_chunks + c;
-        const uint32_t st = q % L.n_stages;
-        const uint32_t it = q / L.n_stages;
-        mbar_wait(&full[st], it & 1u);
-        const float4* v = reinterpret_cast<const float4*>(smem + (size_t)st * L.stage_bytes);
-        const uint32_t e0 = c * L.chunk_elems;
-        const uint32_t nv = min(L.chunk_elems, p.T - e0) >> 2;
-        float m0 = nan_f(), m1 = nan_f();
-        uint32_t i = lane;
-        for (; i + 32u < nv; i += 64u) {
-          const float4 a = v[i], b = v[i + 32u];
-          m0 = fold4(m0, a);
-          m1 = fold4(m1, b);
-        }
-        if (i < nv) m0 = fold4(m0, v[i]);
-        m = fmaxf(m, fmaxf(m0, m1));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+    if (++pc == L.n_chunks) pc = 0, ++pi;
+    if (++pst == D) pst = 0;
+    ++issued;
+  };
+  while (issued < D && issued < n_items) issue();
+
+  uint32_t cs = 0, cph = 0;
+  for (uint32_t i = 0; i < my_rows; ++i) {
+    float m0 = nan_f(), m1 = nan_f();
+    for (uint32_t c = 0; c < L.n_chunks; ++c) {
+      mbar_wait(&full[cs], cph);
+      const float4* v = reinterpret_cast<const float4*>(stage0 + (size_t)cs * L.stage_bytes);
+      const uint32_t nv = min(L.chunk_elems, p.T - c * L.chunk_elems) >> 2;
+      uint32_t k = lane;
+#pragma unroll 4
+      for (; k + 32u < nv; k += 64u) {
+        const float4 a = v[k], b = v[k + 32u];
+        m0 = fold4(m0, a);
+        m1 = fold4(m1, b);
       }
-      m = warp_max(m);
-      if (lane == 0) {
-        uint32_t seg, local;
-        (void)row_ptr(p, r0 + k, seg, local);
-        publish_row(p, seg, local, m);
-      }
+      if (k < nv) m0 = fold4(m0, v[k]);
+      __syncwarp();  // every lane has its data in registers: the stage may be overwritten
+      if (issued < n_items) issue();
+      if (++cs == D) cs = 0, cph ^= 1u;
+    }
+    const float m = warp_max(fmaxf(m0, m1));
+    if (lane == 0) {
+      uint32_t seg, local;
+      (void)row_ptr(p, r0 + w + NW * i, seg, local);
+      publish_row(p, seg, local, m);
     }
   }
   if (p.fold_in_kernel) fold_by_last_cta(p.fold);

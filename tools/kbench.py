@@ -1,0 +1,62 @@
+"""Developer micro-benchmark: device-resident windows, back-to-back async decides, CUDA events.
+Not the judged benchmark (that is bench.py); used to compare kernel variants and tunables."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import gpu_pruner_b200 as g  # noqa: E402
+
+
+def run(variant, P, G, T, iters, rot, power=False):
+    eng = g.IdleEngine(device=0, kernel=variant)
+    wins = []
+    for i in range(rot):
+        u = torch.empty((P, G, T), dtype=torch.float32, device="cuda:0")
+        eng.synth_fill(0x5EED0002 + i, 0, u, 0, P, G, T)
+        w = None
+        if power:
+            w = torch.empty((P, G, T), dtype=torch.float32, device="cuda:0")
+            eng.synth_fill(0x5EED0002 + i, 1, w, 0, P, G, T)
+        wins.append((u, w))
+    db = torch.zeros((P + 31) // 32, dtype=torch.int32, device="cuda:0")
+    for i in range(5):
+        eng.decide_ptr(wins[i % rot][0], P, G, T, db, power=wins[i % rot][1], power_threshold=150.0 if power else 0.0,
+                       blocking=False)
+    eng.sync()
+    best = 1e9
+    tot = 0.0
+    reps = 3
+    for _ in range(reps):
+        eng.timer_begin()
+        for i in range(iters):
+            eng.decide_ptr(wins[i % rot][0], P, G, T, db, power=wins[i % rot][1],
+                           power_threshold=150.0 if power else 0.0, blocking=False)
+        ms = eng.timer_end()
+        eng.sync()
+        best = min(best, ms / iters)
+        tot += ms / iters
+    nbytes = 4.0 * P * G * T * (2 if power else 1)
+    print(f"{variant:4s} P={P} G={G} T={T} power={int(power)} rot={rot}: best {best*1e3:8.2f} us/step  "
+          f"avg {tot/reps*1e3:8.2f} us  -> {nbytes/best/1e6:8.1f} GB/s (best)  "
+          f"{P/best/1e3:8.2f} Mdecisions/s", flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c2,c3")
+    ap.add_argument("--variants", default="ldg,tma")
+    ap.add_argument("--iters", type=int, default=100)
+    a = ap.parse_args()
+    shapes = {"c2": (10000, 4, 1800, 6), "c3": (100000, 8, 3600, 2), "c4": (250000, 4, 1800, 2),
+              "c5s": (312500, 4, 7200, 1)}
+    for c in a.configs.split(","):
+        P, G, T, rot = shapes[c]
+        for v in a.variants.split(","):
+            run(v, P, G, T, a.iters if c == "c2" else max(10, a.iters // 5), rot)
+    if "c2" in a.configs:
+        for v in a.variants.split(","):
+            run(v, 10000, 4, 1800, a.iters, 4, power=True)
