@@ -99,7 +99,7 @@ struct gpr_ctx {
   int variant = GPR_KERNEL_AUTO;
   int ldg_ctas_per_sm = 2;
   int tma_depth_max = 3;
-  int tma_warps = 8;
+  int tma_warps = 16;
   int tma_chunk_bytes = 8192;
   size_t chunk_bytes = 8u << 20;
 
@@ -113,8 +113,17 @@ struct gpr_ctx {
   size_t gate_cap = 0;
 
   // scratch (grown on demand)
-  uint8_t* d_flags = nullptr;
-  size_t flags_cap = 0;
+  // Two scratch sets used alternately by successive single-launch decisions so that a launch may
+  // start (programmatic dependent launch) while its predecessor is still folding.
+  uint32_t* d_masks[2] = {nullptr, nullptr};  // each [idle P | veto P], all-zero between uses
+  size_t masks_cap[2] = {0, 0};
+  bool masks_dirty = false;     // a failed call may have left bits behind
+  unsigned int* d_tickets = nullptr;          // [2]
+  unsigned long long* d_done = nullptr;       // [2] completed in-kernel folds per scratch set
+  unsigned long long uses[2] = {0, 0};        // in-kernel-fold launches issued per scratch set
+  unsigned parity = 0;
+  bool pdl_enabled = true;      // GPR_PDL=0 disables programmatic dependent launch
+  bool last_was_reduce = false; // the newest op on the stream is a self-folding reduce kernel
   uint32_t* d_bits = nullptr;  // [dbits W | cbits W]
   size_t bits_cap = 0;
   uint32_t* d_gather = nullptr;  // [world][2W]
@@ -122,7 +131,6 @@ struct gpr_ctx {
   float* d_smax = nullptr;
   size_t smax_cap = 0;
   unsigned long long* d_counts = nullptr;
-  unsigned int* d_ticket = nullptr;
   unsigned long long* h_counts = nullptr;  // pinned [kSlots][3]
   std::vector<Pending> pending;
 
@@ -227,31 +235,51 @@ size_t tma_smem_bytes(const gpr::TmaLayout& L, int nw) {
   return (size_t)nw * L.depth * L.stage_bytes + (size_t)nw * L.depth * sizeof(uint64_t);
 }
 
+// One launch helper for both variants; `pdl` adds the programmatic-stream-serialization
+// attribute so the kernel may begin while the previous reduce kernel on the stream drains.
+template <typename Kernel, typename... Args>
+cudaError_t launch_ex(Kernel k, uint32_t grid, uint32_t block, size_t smem, cudaStream_t st, bool pdl,
+                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, args...);
+}
+
 template <int NW>
-void launch_tma(gpr_ctx* ctx, const gpr::ReduceParams& rp, uint32_t grid) {
+cudaError_t launch_tma(gpr_ctx* ctx, const gpr::ReduceParams& rp, uint32_t grid, bool pdl) {
   const gpr::TmaLayout L = tma_layout(ctx, rp.T, NW);
-  gpr::k_reduce_tma<NW><<<grid, NW * 32, tma_smem_bytes(L, NW), ctx->stream>>>(rp, L);
+  return launch_ex(gpr::k_reduce_tma<NW>, grid, NW * 32, tma_smem_bytes(L, NW), ctx->stream, pdl, rp, L);
 }
 
 // launch one reduce pass over the rows described by rp
-int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok) {
+int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok, bool pdl) {
   if (rp.total_rows == 0 && !rp.fold_in_kernel) return GPR_OK;
-  int variant = ctx->variant == GPR_KERNEL_AUTO ? GPR_KERNEL_LDG : ctx->variant;
+  // AUTO = the TMA pipeline (measured winner on B200 at C2 and C3, profiles/README.md); rows that are
+  // not 16-byte aligned or have T % 4 != 0 cannot be bulk-copied and take the LDG kernel
+  int variant = ctx->variant == GPR_KERNEL_AUTO ? GPR_KERNEL_TMA : ctx->variant;
   if (variant == GPR_KERNEL_TMA && !tma_ok) variant = GPR_KERNEL_LDG;
+  cudaError_t e;
   if (variant == GPR_KERNEL_TMA) {
     const int nw = ctx->tma_warps;
     uint32_t grid = (uint32_t)ctx->sm_count;
     grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, (rp.total_rows + nw - 1) / nw));
-    if (nw == 4) launch_tma<4>(ctx, rp, grid);
-    else if (nw == 16) launch_tma<16>(ctx, rp, grid);
-    else launch_tma<8>(ctx, rp, grid);
+    if (nw == 4) e = launch_tma<4>(ctx, rp, grid, pdl);
+    else if (nw == 16) e = launch_tma<16>(ctx, rp, grid, pdl);
+    else if (nw == 32) e = launch_tma<32>(ctx, rp, grid, pdl);
+    else e = launch_tma<8>(ctx, rp, grid, pdl);
   } else {
     uint32_t grid = (uint32_t)(ctx->sm_count * ctx->ldg_ctas_per_sm);
     const uint32_t need = (rp.total_rows + kLdgWarps - 1) / kLdgWarps;
     grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, need));
-    gpr::k_reduce_ldg<kLdgWarps, kLdgUnroll><<<grid, kLdgWarps * 32, 0, ctx->stream>>>(rp);
+    e = launch_ex(gpr::k_reduce_ldg<kLdgWarps, kLdgUnroll>, grid, kLdgWarps * 32, 0, ctx->stream, pdl, rp);
   }
   ctx->launches++;
+  CU(e);
   CU(cudaGetLastError());
   return GPR_OK;
 }
@@ -292,6 +320,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   if (res->out_mem_kind != GPR_MEM_HOST && res->out_mem_kind != GPR_MEM_DEVICE)
     return fail(ctx, GPR_E_INVALID, "bad out_mem_kind %d", res->out_mem_kind);
   if (G == 0 || T == 0) return fail(ctx, GPR_E_INVALID, "n_gpus and n_samples must be > 0");
+  if (G > 32) return fail(ctx, GPR_E_UNSUPPORTED, "n_gpus %u > 32 GPUs per pod is not supported", G);
   if (ld < T) return fail(ctx, GPR_E_INVALID, "row_stride %llu < n_samples %u",
                           (unsigned long long)ld, T);
   if (P > 0 && !util) return fail(ctx, GPR_E_INVALID, "util is NULL");
@@ -322,7 +351,18 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
 
   // ---- scratch ---------------------------------------------------------------------------
   int rc;
-  if ((rc = grow(ctx, &ctx->d_flags, &ctx->flags_cap, (size_t)2 * S + 16)) != GPR_OK) return rc;
+  const unsigned sset = ctx->parity;  // scratch set of this call; successive calls alternate
+  ctx->parity ^= 1u;
+  for (int k = 0; k < 2; ++k) {
+    const size_t cap_before = ctx->masks_cap[k];
+    if ((rc = grow(ctx, &ctx->d_masks[k], &ctx->masks_cap[k], (size_t)2 * P + 16)) != GPR_OK) return rc;
+    if (ctx->masks_cap[k] != cap_before || ctx->masks_dirty) {
+      CU(cudaMemsetAsync(ctx->d_masks[k], 0, ctx->masks_cap[k] * sizeof(uint32_t), ctx->stream));
+      ctx->last_was_reduce = false;
+    }
+  }
+  ctx->masks_dirty = false;
+  uint32_t* const masks = ctx->d_masks[sset];
   if ((rc = grow(ctx, &ctx->d_bits, &ctx->bits_cap, (size_t)2 * W + 2)) != GPR_OK) return rc;
   if (comm &&
       (rc = grow(ctx, &ctx->d_gather, &ctx->gather_cap, (size_t)ctx->world * 2 * W + 2)) != GPR_OK)
@@ -348,6 +388,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_created_stage), cap * sizeof(int64_t)));
       ctx->gate_cap = cap;
     }
+    ctx->last_was_reduce = false;
     if (win->eligible) {
       CU(cudaMemcpyAsync(ctx->d_elig_stage, win->eligible, P, cudaMemcpyHostToDevice, ctx->stream));
       d_elig = ctx->d_elig_stage;
@@ -367,38 +408,57 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   float* smax_dev = want_smax ? (host_out ? ctx->d_smax : res->series_max) : nullptr;
 
   gpr::FoldParams fp;
-  fp.idle_flag = ctx->d_flags;
-  fp.veto_flag = use_power ? ctx->d_flags + S : nullptr;
+  fp.idle_mask = masks;
+  fp.veto_mask = use_power ? masks + P : nullptr;
   fp.eligible = d_elig;
   fp.created = d_created;
   fp.cutoff = win->cutoff_ts;
   fp.dbits = dbits_dev;
   fp.cbits = cbits_dev;
-  fp.counts = ctx->d_counts;
-  fp.ticket = ctx->d_ticket;
+  // single-launch path: the last CTA stores the three counters straight into this call's
+  // pinned (device-mapped, UVA) host slot, so no copy operation separates back-to-back steps
+  const int slot = (int)ctx->pending.size();
+  unsigned long long* h_slot = ctx->h_counts + (size_t)slot * 3;
+  fp.counts = host_in ? ctx->d_counts : h_slot;
+  fp.ticket = ctx->d_tickets + sset;
+  fp.done = ctx->d_done + sset;
+  fp.need = host_in ? 0ull : ctx->uses[sset];
   fp.P = P;
   fp.G = G;
 
   gpr::ReduceParams rp;
   memset(&rp, 0, sizeof rp);
   rp.T = T;
+  rp.G = G;
   rp.thr = threshold_f32(win->power_threshold);
   rp.fold = fp;
 
-  if (!async) CU(cudaEventRecord(ctx->ev_k0, ctx->stream));
+  if (!async) {
+    CU(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    ctx->last_was_reduce = false;
+  }
 
   if (!host_in) {
     // ---- device-resident window: ONE launch, reduce + ticket fold -------------------------
     rp.ld = ld;
-    rp.seg[0] = gpr::Segment{util, ctx->d_flags, smax_dev, S, 0u};
-    rp.seg[1] = gpr::Segment{power, ctx->d_flags + S, nullptr, use_power ? S : 0u, 1u};
+    rp.seg[0] = gpr::Segment{util, masks, smax_dev, S, 0u};
+    rp.seg[1] = gpr::Segment{power, masks + P, nullptr, use_power ? S : 0u, 1u};
     rp.total_rows = S + (use_power ? S : 0u);
     rp.fold_in_kernel = 1;
     const bool tma_ok = (T % 4u) == 0 && (ld % 4u) == 0 && aligned16(util) &&
                         (!use_power || aligned16(power));
-    if (P > 0 && (rc = launch_reduce(ctx, rp, tma_ok)) != GPR_OK) return rc;
+    if (P > 0) {
+      // Overlap with the previous decision only when that is provably safe: our own stream (no
+      // foreign producer kernels), the newest op on it is a self-folding reduce kernel, and this
+      // launch writes nothing before its fold except into its own scratch set.
+      const bool pdl = ctx->pdl_enabled && ctx->own_stream && ctx->last_was_reduce && !want_smax;
+      if ((rc = launch_reduce(ctx, rp, tma_ok, pdl)) != GPR_OK) return rc;
+      ctx->uses[sset]++;
+      ctx->last_was_reduce = true;
+    }
   } else {
     // ---- host window: pod chunks, H2D on the copy stream overlapped with the reduce --------
+    ctx->last_was_reduce = false;
     CU(cudaEventRecord(ctx->ev_join, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));
     const size_t pod_bytes = (size_t)G * T * 4u * (use_power ? 2u : 1u);
@@ -422,12 +482,12 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       cudaEvent_t ev = ctx->ev_chunk[c % kMaxChunkEvents];
       CU(cudaEventRecord(ev, ctx->copy_stream));
       CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
-      rp.seg[0] = gpr::Segment{du, ctx->d_flags + row0, smax_dev ? smax_dev + row0 : nullptr,
+      rp.seg[0] = gpr::Segment{du, masks + p0, smax_dev ? smax_dev + row0 : nullptr,
                                (uint32_t)n_rows, 0u};
-      rp.seg[1] = gpr::Segment{dp, ctx->d_flags + S + row0, nullptr,
+      rp.seg[1] = gpr::Segment{dp, masks + P + p0, nullptr,
                                use_power ? (uint32_t)n_rows : 0u, 1u};
       rp.total_rows = (uint32_t)n_rows * (use_power ? 2u : 1u);
-      if ((rc = launch_reduce(ctx, rp, tma_ok)) != GPR_OK) return rc;
+      if ((rc = launch_reduce(ctx, rp, tma_ok, false)) != GPR_OK) return rc;
     }
     CU(cudaMemsetAsync(ctx->d_counts, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (W > 0) {
@@ -439,9 +499,10 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       CU(cudaGetLastError());
     }
   }
-  if (P == 0) CU(cudaMemsetAsync(ctx->d_counts, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  if (P == 0 && !host_in) h_slot[0] = h_slot[1] = h_slot[2] = 0;  // slot is not in flight
 
   // ---- the one collective: allgather of the packed bitmap over NVLink ----------------------
+  if (comm || host_out || !async) ctx->last_was_reduce = false;  // something follows the kernel
   if (comm && W > 0) {
     NC(g_nccl.AllGather(ctx->d_bits, ctx->d_gather, (size_t)2 * W, ncclUint32, ctx->comm,
                         ctx->stream));
@@ -467,9 +528,9 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   if (want_smax && host_out && S > 0)
     CU(cudaMemcpyAsync(res->series_max, ctx->d_smax, (size_t)S * 4u, cudaMemcpyDeviceToHost,
                        ctx->stream));
-  const int slot = (int)ctx->pending.size();
-  CU(cudaMemcpyAsync(ctx->h_counts + (size_t)slot * 3, ctx->d_counts, 3 * sizeof(unsigned long long),
-                     cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_in)
+    CU(cudaMemcpyAsync(h_slot, ctx->d_counts, 3 * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, ctx->stream));
   ctx->pending.push_back(Pending{res, slot});
   res->kernel_ms = 0.0;
   return GPR_OK;
@@ -480,6 +541,7 @@ int sync_impl(gpr_ctx* ctx) {
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     ctx->pending.clear();
+    ctx->masks_dirty = true;
     return fail(ctx, GPR_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
   }
   for (const Pending& p : ctx->pending) {
@@ -534,9 +596,9 @@ void gpr_destroy(gpr_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   void* dev[] = {ctx->d_util_stage, ctx->d_power_stage, ctx->d_elig_stage, ctx->d_created_stage,
-                 ctx->d_flags,      ctx->d_bits,        ctx->d_gather,     ctx->d_smax,
-                 ctx->d_counts,     ctx->d_ticket,      ctx->d_flush,      ctx->d_res_util,
-                 ctx->d_res_power,  ctx->d_cols};
+                 ctx->d_masks[0],   ctx->d_masks[1],    ctx->d_bits,       ctx->d_gather,
+                 ctx->d_smax,       ctx->d_counts,      ctx->d_tickets,    ctx->d_done,
+                 ctx->d_flush,      ctx->d_res_util,    ctx->d_res_power,  ctx->d_cols};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -585,7 +647,7 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     c->l2_bytes = (size_t)prop.l2CacheSize;
     c->hbm_bytes = prop.totalGlobalMem;
     c->cc_major = prop.major, c->cc_minor = prop.minor;
-    snprintf(c->name, sizeof c->name, "%s", prop.name);
+    memcpy(c->name, prop.name, sizeof c->name - 1);
     if (prop.major < 10)
       return fail(c, GPR_E_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a",
                   prop.name, prop.major, prop.minor);
@@ -603,9 +665,12 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (cudaEvent_t& ev : c->ev_chunk) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaMalloc(reinterpret_cast<void**>(&c->d_counts), 3 * sizeof(unsigned long long)));
-    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_ticket), sizeof(unsigned int)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_tickets), 2 * sizeof(unsigned int)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_done), 2 * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_counts, 0, 3 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+    CU(cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned int)));
+    CU(cudaMemset(c->d_done, 0, 2 * sizeof(unsigned long long)));
+    c->pdl_enabled = env_int("GPR_PDL", 1) != 0;
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
                       (size_t)kSlots * 3 * sizeof(unsigned long long)));
     c->pending.reserve(kSlots);
@@ -619,8 +684,9 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
       return fail(c, GPR_E_INVALID, "bad kernel_variant %d", c->variant);
     c->ldg_ctas_per_sm = std::max(1, env_int("GPR_LDG_CTAS", 2));
     c->tma_depth_max = std::max(1, env_int("GPR_TMA_DEPTH", 3));
-    c->tma_warps = env_int("GPR_TMA_WARPS", 8);
-    if (c->tma_warps != 4 && c->tma_warps != 8 && c->tma_warps != 16) c->tma_warps = 8;
+    c->tma_warps = env_int("GPR_TMA_WARPS", 16);
+    if (c->tma_warps != 4 && c->tma_warps != 8 && c->tma_warps != 16 && c->tma_warps != 32)
+      c->tma_warps = 16;
     c->tma_chunk_bytes = std::min(65536, std::max(512, env_int("GPR_TMA_CHUNK", 8192))) & ~15;
     c->chunk_bytes = (size_t)std::max(1, env_int("GPR_CHUNK_MB", 8)) << 20;
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -628,6 +694,8 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kTmaSmemBudget));
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kTmaSmemBudget));
+    CU(cudaFuncSetAttribute(gpr::k_reduce_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kTmaSmemBudget));
 
     c->max_pods = cfg->max_pods, c->max_gpus = cfg->max_gpus, c->max_samples = cfg->max_samples;
@@ -649,7 +717,9 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
 
 int gpr_decide_async(gpr_ctx* ctx, const gpr_window* win, gpr_result* res) {
   GPR_TRY
-  return decide_impl(ctx, win, res, false, true);
+  const int rc = decide_impl(ctx, win, res, false, true);
+  if (rc != GPR_OK && ctx) ctx->masks_dirty = true;
+  return rc;
   GPR_CATCH(ctx)
 }
 
@@ -666,6 +736,7 @@ static int decide_blocking(gpr_ctx* ctx, const gpr_window* win, gpr_result* res,
     if (ctx) {
       cudaStreamSynchronize(ctx->stream);
       ctx->pending.clear();
+      ctx->masks_dirty = true;
     }
     return rc;
   }
@@ -721,6 +792,7 @@ int gpr_append(gpr_ctx* ctx, const float* util_cols, const float* power_cols, ui
   if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
   if (n_new == 0) return GPR_OK;
   if (!util_cols) return fail(ctx, GPR_E_INVALID, "util_cols is NULL");
+  ctx->last_was_reduce = false;
   if (mem_kind != GPR_MEM_HOST && mem_kind != GPR_MEM_DEVICE)
     return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", mem_kind);
   CU(cudaSetDevice(ctx->device));
@@ -841,6 +913,7 @@ int gpr_memcpy(gpr_ctx* ctx, void* dst, const void* src, size_t bytes, int32_t d
   if (!ctx) return GPR_E_INVALID;
   if (bytes == 0) return GPR_OK;
   if (!dst || !src) return fail(ctx, GPR_E_INVALID, "NULL pointer in gpr_memcpy");
+  ctx->last_was_reduce = false;
   CU(cudaSetDevice(ctx->device));
   cudaMemcpyKind k = dst_kind == GPR_MEM_DEVICE
                          ? (src_kind == GPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
@@ -853,12 +926,14 @@ int gpr_memcpy(gpr_ctx* ctx, void* dst, const void* src, size_t bytes, int32_t d
 // ---- measurement support --------------------------------------------------------------------------
 int gpr_timer_begin(gpr_ctx* ctx) {
   if (!ctx) return GPR_E_INVALID;
+  ctx->last_was_reduce = false;
   CU(cudaSetDevice(ctx->device));
   CU(cudaEventRecord(ctx->ev_t0, ctx->stream));
   return GPR_OK;
 }
 int gpr_timer_end(gpr_ctx* ctx, double* ms) {
   if (!ctx || !ms) return GPR_E_INVALID;
+  ctx->last_was_reduce = false;
   CU(cudaSetDevice(ctx->device));
   CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
   CU(cudaEventSynchronize(ctx->ev_t1));
@@ -869,6 +944,7 @@ int gpr_timer_end(gpr_ctx* ctx, double* ms) {
 }
 int gpr_flush_l2(gpr_ctx* ctx) {
   if (!ctx) return GPR_E_INVALID;
+  ctx->last_was_reduce = false;
   CU(cudaSetDevice(ctx->device));
   if (!ctx->d_flush) {
     ctx->flush_bytes = std::max<size_t>(ctx->l2_bytes * 2, (size_t)256 << 20);
@@ -901,6 +977,7 @@ int gpr_synth_fill(gpr_ctx* ctx, uint64_t seed, int32_t plane, float* dst, uint6
     return fail(ctx, GPR_E_INVALID, "bad gpr_synth_fill arguments");
   const uint64_t rows = (uint64_t)n_pods * n_gpus;
   if (rows == 0) return GPR_OK;
+  ctx->last_was_reduce = false;
   if (rows > 0x7fffffffull) return fail(ctx, GPR_E_INVALID, "too many series");
   CU(cudaSetDevice(ctx->device));
   const uint64_t ld = row_stride ? row_stride : n_samples;
@@ -917,6 +994,7 @@ int gpr_synth_eligible(gpr_ctx* ctx, uint64_t seed, uint8_t* dst, uint64_t pod_o
   if (!ctx) return GPR_E_INVALID;
   if (!dst) return fail(ctx, GPR_E_INVALID, "dst is NULL");
   if (n_pods == 0) return GPR_OK;
+  ctx->last_was_reduce = false;
   CU(cudaSetDevice(ctx->device));
   const uint32_t grid = std::min<uint32_t>((n_pods + 255u) / 256u, (uint32_t)ctx->sm_count * 8u);
   gpr::k_synth_eligible<<<grid, 256, 0, ctx->stream>>>(dst, seed, pod_offset, n_pods);
@@ -926,3 +1004,13 @@ int gpr_synth_eligible(gpr_ctx* ctx, uint64_t seed, uint8_t* dst, uint64_t pod_o
 }
 
 }  // extern "C"
+
+#ifdef GPR_TIMELINE
+extern "C" GPR_API int gpr_debug_timeline(gpr_ctx* ctx, unsigned long long* out, int n_ctas) {
+  if (!ctx || !out) return GPR_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyFromSymbol(out, gpr::g_timeline, sizeof(unsigned long long) * 4 * (size_t)n_ctas));
+  return GPR_OK;
+}
+#endif

@@ -32,15 +32,18 @@ namespace gpr {
 // ------------------------------------------------------------------------------------------
 struct Segment {
   const float* base;   // first row of this segment (device)
-  uint8_t* flag;       // one byte per row: util -> idle_s, power -> veto_s
+  uint32_t* mask;      // per-pod bitmask, bit g set when series (pod, g) is flagged:
+                       //   util plane -> idle_s = (max == 0), power plane -> veto_s = (max >= thr)
+                       // indexed by (first_pod + local_row / G); zero between calls (the fold
+                       // clears every word it reads)
   float* smax;         // optional per-row window max (util segment only)
   uint32_t n_rows;
-  uint32_t is_power;   // 0: flag = (max == 0)   1: flag = (max >= thr)
+  uint32_t is_power;
 };
 
 struct FoldParams {
-  const uint8_t* idle_flag;   // [P*G]
-  const uint8_t* veto_flag;   // [P*G] or nullptr
+  uint32_t* idle_mask;        // [P]   read, then cleared
+  uint32_t* veto_mask;        // [P] or nullptr
   const uint8_t* eligible;    // [P] or nullptr
   const int64_t* created;     // [P] or nullptr
   int64_t cutoff;
@@ -48,6 +51,8 @@ struct FoldParams {
   uint32_t* cbits;            // [ceil(P/32)] or nullptr
   unsigned long long* counts; // [3] n_series, n_candidates, n_decisions (overwritten)
   unsigned int* ticket;       // self-resetting arrival counter (ticket mode)
+  unsigned long long* done;   // completed in-kernel folds on this scratch set (monotonic)
+  unsigned long long need;    // folds that must have completed before this launch may publish
   uint32_t P, G;
 };
 
@@ -55,11 +60,55 @@ struct ReduceParams {
   Segment seg[2];
   uint64_t ld;        // elements between rows
   uint32_t T;
+  uint32_t G;         // rows per pod
   uint32_t total_rows;
   float thr;          // smallest f32 >= (double) power threshold
   int fold_in_kernel; // 1: last CTA folds (single-launch path)
   FoldParams fold;
 };
+
+#ifdef GPR_TIMELINE
+// developer-only: per-CTA (smid, t_start, t_stream_end, t_exit) in ns, see tools/timeline.py
+__device__ unsigned long long g_timeline[4 * 4096];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_mark(int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < 4096) {
+    if (slot == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      g_timeline[4 * blockIdx.x] = smid;
+    }
+    g_timeline[4 * blockIdx.x + 1 + slot] = gtime();
+  }
+}
+#define TL_MARK(slot) tl_mark(slot)
+#else
+#define TL_MARK(slot)
+#endif
+
+// ---- programmatic dependent launch (back-to-back decisions on the context's own stream) -------
+// A reduce kernel lets its successor start while it drains (launch_dependents at entry).  The
+// successor streams its input and publishes into the OTHER scratch set; before its first publish
+// it checks that the launch two back (same scratch set) has finished (`done` counter), and before
+// it writes outputs it waits for its predecessor's completion (griddepcontrol.wait).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grids() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __device__ __forceinline__ float nan_f() { return __int_as_float(0x7fffffff); }
 
@@ -88,57 +137,43 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 // ------------------------------------------------------------------------------------------
 // fold: flags -> verdict bits.  One lane per pod, one warp per bitmap word.
 // ------------------------------------------------------------------------------------------
+// Loads of a batch are unconditional (addresses clamped) and nothing consumes them until the
+// whole batch is in flight: the fold is a pure latency chain, so a dependent use inside the load
+// loop would serialise BATCH round trips to L2 (measured: 14 us instead of 1 us at P = 10,000).
 template <int BATCH>
 __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin, uint32_t w_end,
                                            uint32_t w_step, int lane, unsigned long long& n_series,
                                            unsigned long long& n_cand, unsigned long long& n_dec) {
-  const uint32_t G = f.G;
+  const uint32_t last_pod = f.P - 1u;  // callers guarantee P > 0
   for (uint32_t w0 = w_begin; w0 < w_end; w0 += w_step * BATCH) {
-    uint32_t idle_cnt[BATCH];
-    uint32_t veto[BATCH];
-    uint32_t elig[BATCH];
-    // issue every load of the batch before consuming any (latency-bound phase)
+    uint32_t idle[BATCH], veto[BATCH];
+    uint8_t elig[BATCH];
+    long long created[BATCH];
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) {
-      const uint32_t w = w0 + b * w_step;
-      const uint32_t pod = w * 32u + lane;
-      idle_cnt[b] = 0, veto[b] = 0, elig[b] = 0;
-      if (w < w_end && pod < f.P) {
-        const size_t r = (size_t)pod * G;
-        if (G == 4) {
-          const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(f.idle_flag + r));
-          idle_cnt[b] = __popc(v & 0x01010101u);
-          if (f.veto_flag) veto[b] = __ldcg(reinterpret_cast<const uint32_t*>(f.veto_flag + r)) != 0;
-        } else if (G == 8) {
-          const uint2 v = __ldcg(reinterpret_cast<const uint2*>(f.idle_flag + r));
-          idle_cnt[b] = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u);
-          if (f.veto_flag) {
-            const uint2 q = __ldcg(reinterpret_cast<const uint2*>(f.veto_flag + r));
-            veto[b] = (q.x | q.y) != 0;
-          }
-        } else {
-          for (uint32_t g = 0; g < G; ++g) {
-            idle_cnt[b] += __ldcg(f.idle_flag + r + g) & 1u;
-            if (f.veto_flag) veto[b] |= __ldcg(f.veto_flag + r + g);
-          }
-        }
-        uint32_t e = 1;
-        if (f.eligible) e = f.eligible[pod] != 0;
-        if (f.created && f.created[pod] >= f.cutoff) e = 0;
-        elig[b] = e;
-      }
+      const uint32_t pod = min((w0 + b * w_step) * 32u + lane, last_pod);
+      idle[b] = __ldcg(f.idle_mask + pod);
+      veto[b] = f.veto_mask ? __ldcg(f.veto_mask + pod) : 0u;
+      elig[b] = f.eligible ? f.eligible[pod] : (uint8_t)1;
+      created[b] = f.created ? f.created[pod] : (long long)0x8000000000000000ll;
     }
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) {
       const uint32_t w = w0 + b * w_step;
       if (w >= w_end) break;  // warp-uniform
-      const bool cand = idle_cnt[b] > 0 && !veto[b];
-      const bool dec = cand && elig[b];
+      const uint32_t pod = w * 32u + lane;
+      const bool valid = pod < f.P;
+      const bool cand = valid && idle[b] != 0u && veto[b] == 0u;
+      const bool dec = cand && elig[b] != 0 && !(f.created && created[b] >= f.cutoff);
       const uint32_t cw = __ballot_sync(0xffffffffu, cand);
       const uint32_t dw = __ballot_sync(0xffffffffu, dec);
-      uint32_t ns = cand ? idle_cnt[b] : 0;
+      uint32_t ns = cand ? __popc(idle[b]) : 0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+      if (valid) {  // leave the scratch zeroed for the next call
+        if (idle[b]) f.idle_mask[pod] = 0u;
+        if (veto[b]) f.veto_mask[pod] = 0u;
+      }
       if (lane == 0) {
         f.dbits[w] = dw;
         if (f.cbits) f.cbits[w] = cw;
@@ -166,7 +201,7 @@ __device__ __forceinline__ void block_counts(unsigned long long* sh3, unsigned l
 __device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
   __shared__ unsigned int s_last;
   __shared__ unsigned long long s_cnt[3];
-  __threadfence();  // this thread's flag stores are visible device-wide
+  __threadfence();  // this thread's mask updates are visible device-wide
   __syncthreads();
   if (threadIdx.x == 0) {
     s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
@@ -175,6 +210,8 @@ __device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
   }
   __syncthreads();
   if (!s_last) return;
+  // outputs may still be owned by the previous launch on the stream until it has completed
+  pdl_wait_prior_grids();
   __threadfence();
   const int lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -182,12 +219,14 @@ __device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
   unsigned long long a = 0, b = 0, c = 0;
   fold_words<8>(f, warp, n_words, n_warps, lane, a, b, c);
   block_counts(s_cnt, a, b, c, lane);
+  __threadfence();  // mask clears and outputs before the completion signal
   __syncthreads();
   if (threadIdx.x == 0) {
     f.counts[0] = s_cnt[0];
     f.counts[1] = s_cnt[1];
     f.counts[2] = s_cnt[2];
     *f.ticket = 0u;
+    st_release_u64(f.done, f.need + 1ull);
   }
 }
 
@@ -221,12 +260,23 @@ __device__ __forceinline__ const float* row_ptr(const ReduceParams& p, uint32_t 
   return p.seg[seg].base + (size_t)local * p.ld;
 }
 
+// before a warp's first publish: the launch that last used this scratch set must be finished
+__device__ __forceinline__ void wait_scratch_free(const FoldParams& f) {
+  while (ld_acquire_u64(f.done) < f.need) __nanosleep(64);
+}
+
+// rows owned by this CTA under the strided assignment row = blockIdx.x + j * gridDim.x
+__device__ __forceinline__ uint32_t cta_row_count(uint32_t total_rows) {
+  return total_rows > blockIdx.x ? (total_rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+}
+
 __device__ __forceinline__ void publish_row(const ReduceParams& p, uint32_t seg, uint32_t local,
                                             float m) {
   const Segment& s = p.seg[seg];
   // util: `== 0` (NaN fails, -0.0 passes); power: `>= T` (NaN fails)
   const bool flag = s.is_power ? (m >= p.thr) : (m == 0.0f);
-  s.flag[local] = flag ? 1 : 0;
+  // fire-and-forget RED at L2; unflagged rows write nothing at all
+  if (flag) atomicOr(s.mask + local / p.G, 1u << (local % p.G));
   if (s.smax) s.smax[local] = m;
 }
 
@@ -277,22 +327,33 @@ __global__ void __launch_bounds__(WARPS * 32) k_reduce_ldg(ReduceParams p) {
   __shared__ unsigned int s_next;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t r0 = (uint32_t)(((uint64_t)p.total_rows * blockIdx.x) / gridDim.x);
-  const uint32_t r1 = (uint32_t)(((uint64_t)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
-  if (threadIdx.x == 0) s_next = r0 + WARPS;
+  // CTA b owns rows b, b + grid, b + 2*grid, ...: at any instant the whole chip streams one
+  // narrow, advancing band of the tensor (sequential DRAM pages, few live TLB entries) and every
+  // CTA's share differs by at most one row.
+  TL_MARK(0);
+  pdl_launch_dependents();
+  const uint32_t n_mine = cta_row_count(p.total_rows);
+  if (threadIdx.x == 0) s_next = WARPS;
   __syncthreads();
-  uint32_t r = r0 + warp;
-  while (r < r1) {
+  uint32_t j = warp;
+  bool scratch_ok = false;
+  while (j < n_mine) {
     uint32_t seg, local;
-    const float* row = row_ptr(p, r, seg, local);
+    const float* row = row_ptr(p, blockIdx.x + j * gridDim.x, seg, local);
     const float m = row_max_ldg<U>(row, p.T, lane);
     if (lane == 0) {
+      if (!scratch_ok) wait_scratch_free(p.fold), scratch_ok = true;
       publish_row(p, seg, local, m);
-      r = atomicAdd(&s_next, 1u);
+      j = atomicAdd(&s_next, 1u);
     }
-    r = __shfl_sync(0xffffffffu, r, 0);
+    j = __shfl_sync(0xffffffffu, j, 0);
   }
+#ifdef GPR_TIMELINE
+  __syncthreads();
+  TL_MARK(1);
+#endif
   if (p.fold_in_kernel) fold_by_last_cta(p.fold);
+  TL_MARK(2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -358,7 +419,7 @@ struct TmaLayout {
 // barriers, no cross-warp synchronisation: a stage is only ever touched by its owner warp, so
 // the mbarrier phase parity cannot alias, and NW * depth * chunk bytes stay in flight per SM
 // without holding a single register.
-// Rows r0 + w, r0 + w + NW, ... of the CTA's contiguous range belong to warp w.
+// The CTA owns rows b, b + grid, ... (see k_reduce_ldg); its j-th row belongs to warp j % NW.
 template <int NW>
 __global__ void __launch_bounds__(NW * 32) k_reduce_tma(ReduceParams p, TmaLayout L) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -368,10 +429,10 @@ __global__ void __launch_bounds__(NW * 32) k_reduce_tma(ReduceParams p, TmaLayou
   unsigned char* stage0 = smem + (size_t)w * D * L.stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NW * D * L.stage_bytes) + w * D;
 
-  const uint32_t r0 = (uint32_t)(((uint64_t)p.total_rows * blockIdx.x) / gridDim.x);
-  const uint32_t r1 = (uint32_t)(((uint64_t)p.total_rows * (blockIdx.x + 1)) / gridDim.x);
-  const uint32_t n_rows = r1 - r0;
+  pdl_launch_dependents();
+  const uint32_t n_rows = cta_row_count(p.total_rows);
   const uint32_t my_rows = n_rows > w ? (n_rows - w + NW - 1) / NW : 0u;
+  bool scratch_ok = false;
   const uint32_t n_items = my_rows * L.n_chunks;
 
   if (lane == 0) {
@@ -385,7 +446,7 @@ __global__ void __launch_bounds__(NW * 32) k_reduce_tma(ReduceParams p, TmaLayou
   uint32_t pi = 0, pc = 0, pst = 0, issued = 0;
   auto issue = [&]() {
     uint32_t seg, local;
-    const float* row = row_ptr(p, r0 + w + NW * pi, seg, local);
+    const float* row = row_ptr(p, blockIdx.x + (w + NW * pi) * gridDim.x, seg, local);
     const uint32_t e0 = pc * L.chunk_elems;
     const uint32_t bytes = min(L.chunk_elems, p.T - e0) * 4u;
     if (lane == 0) {
@@ -420,7 +481,8 @@ __global__ void __launch_bounds__(NW * 32) k_reduce_tma(ReduceParams p, TmaLayou
     const float m = warp_max(fmaxf(m0, m1));
     if (lane == 0) {
       uint32_t seg, local;
-      (void)row_ptr(p, r0 + w + NW * i, seg, local);
+      (void)row_ptr(p, blockIdx.x + (w + NW * i) * gridDim.x, seg, local);
+      if (!scratch_ok) wait_scratch_free(p.fold), scratch_ok = true;
       publish_row(p, seg, local, m);
     }
   }

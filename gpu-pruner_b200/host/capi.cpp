@@ -1,0 +1,208 @@
+// capi.cpp — a small extern "C" surface over the host library so the test-suite (pytest + ctypes)
+// can exercise the pure host logic — CLI parsing, PromQL rendering, matrix ingest, owner walk,
+// scale requests — without a GPU.  Strings are returned in a caller-provided buffer as JSON.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cli.hpp"
+#include "controller.hpp"
+#include "ingest.hpp"
+#include "json.hpp"
+#include "kube.hpp"
+#include "promql.hpp"
+
+#define GPH_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+int put(const std::string& s, char* out, int cap) {
+  if ((int)s.size() + 1 > cap) return -(int)(s.size() + 1);
+  memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+std::vector<std::string> split_args(const char* nul_separated, int n) {
+  std::vector<std::string> v;
+  const char* p = nul_separated;
+  for (int i = 0; i < n; ++i) {
+    v.emplace_back(p);
+    p += v.back().size() + 1;
+  }
+  return v;
+}
+gph::Json cli_json(const gph::Cli& c) {
+  using gph::Json;
+  Json j = Json::object();
+  j.set("duration", (int64_t)c.duration);
+  j.set("daemon_mode", c.daemon_mode);
+  j.set("enabled_resources", c.enabled_resources);
+  j.set("check_interval", (int64_t)c.check_interval);
+  j.set("namespace", c.ns ? Json(*c.ns) : Json());
+  j.set("grace_period", (int64_t)c.grace_period);
+  j.set("model_name", c.model_name ? Json(*c.model_name) : Json());
+  j.set("power_threshold", c.power_threshold ? Json(*c.power_threshold) : Json());
+  j.set("honor_labels", c.honor_labels);
+  j.set("run_mode", gph::to_string(c.run_mode));
+  j.set("prometheus_url", c.prometheus_url);
+  j.set("prometheus_token", c.prometheus_token ? Json(*c.prometheus_token) : Json());
+  j.set("prometheus_tls_mode", gph::to_string(c.prometheus_tls_mode));
+  j.set("prometheus_tls_cert", c.prometheus_tls_cert ? Json(*c.prometheus_tls_cert) : Json());
+  j.set("log_format", gph::to_string(c.log_format));
+  return j;
+}
+}  // namespace
+
+// args: n NUL-terminated strings back to back.  JSON out: {"ok":bool,"exit_code":n,"message":s,"cli":{...}}
+GPH_API int gph_parse_cli(const char* args, int n, char* out, int cap) {
+  gph::ParseOutcome po = gph::parse_cli(split_args(args, n));
+  gph::Json j = gph::Json::object();
+  j.set("ok", po.ok);
+  j.set("exit_code", po.exit_code);
+  j.set("message", po.message);
+  j.set("cli", cli_json(po.cli));
+  return put(j.dump(), out, cap);
+}
+
+GPH_API int gph_render_query(const char* args, int n, char* out, int cap) {
+  gph::ParseOutcome po = gph::parse_cli(split_args(args, n));
+  if (!po.ok) return put(po.message, out, cap) >= 0 ? -1 : -2;
+  return put(gph::render_query(po.cli), out, cap);
+}
+
+GPH_API int gph_render_selectors(const char* args, int n, char* out, int cap) {
+  gph::ParseOutcome po = gph::parse_cli(split_args(args, n));
+  if (!po.ok) return -1;
+  gph::Selectors s = gph::render_selectors(po.cli);
+  gph::Json j = gph::Json::object();
+  j.set("prof", s.prof), j.set("util", s.util), j.set("power", s.power);
+  return put(j.dump(), out, cap);
+}
+
+GPH_API int gph_enabled_resources(const char* letters) { return gph::get_enabled_resources(letters); }
+
+GPH_API int gph_format_float(double v, char* out, int cap) { return put(gph::format_float(v), out, cap); }
+
+// ingest: JSON texts in, tensor out.  Returns 0 or negative; dims written to dims[3] = P,G,T.
+// util_out/power_out may be NULL to query dimensions + the pod table (JSON) first.
+GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char* power_json,
+                       long long duration_min, long long step, long long t_end, unsigned* dims,
+                       float* util_out, float* power_out, char* pods_json, int cap) {
+  try {
+    gph::Json u = gph::Json::parse(util_json), pf, pw;
+    const gph::Json *ppf = nullptr, *ppw = nullptr;
+    if (prof_json) pf = gph::Json::parse(prof_json), ppf = &pf;
+    if (power_json) pw = gph::Json::parse(power_json), ppw = &pw;
+    gph::IngestOptions o;
+    o.duration_min = duration_min, o.step = step, o.t_end = t_end;
+    gph::Window w = gph::ingest_matrix(u, ppf, ppw, o);
+    dims[0] = w.P, dims[1] = w.G, dims[2] = w.T;
+    if (util_out) memcpy(util_out, w.util.data(), w.util.size() * sizeof(float));
+    if (power_out && !w.power.empty()) memcpy(power_out, w.power.data(), w.power.size() * sizeof(float));
+    gph::Json pods = gph::Json::array();
+    for (const gph::PodEntry& pe : w.pods) {
+      gph::Json p = gph::Json::object();
+      p.set("name", pe.name), p.set("namespace", pe.ns);
+      gph::Json slots = gph::Json::array();
+      for (const gph::GpuSlot& s : pe.slots) {
+        gph::Json sj = gph::Json::object();
+        sj.set("Hostname", s.hostname), sj.set("container", s.container), sj.set("gpu", s.gpu);
+        sj.set("modelName", s.model), sj.set("node_type", s.node_type), sj.set("from_prof", s.from_prof);
+        slots.push(sj);
+      }
+      p.set("slots", slots);
+      p.set("power_slots", (int64_t)pe.power_slots);
+      pods.push(p);
+    }
+    gph::Json meta = gph::Json::object();
+    meta.set("pods", pods);
+    meta.set("t_end", (int64_t)w.t_end), meta.set("step", (int64_t)w.step);
+    meta.set("series_in", (int64_t)w.stats.series_in), meta.set("series_skipped", (int64_t)w.stats.series_skipped);
+    meta.set("samples_out_of_window", (int64_t)w.stats.samples_out_of_window);
+    meta.set("duplicates_merged", (int64_t)w.stats.duplicates_merged);
+    meta.set("tiny_values_clamped", (int64_t)w.stats.tiny_values_clamped);
+    return pods_json ? (put(meta.dump(), pods_json, cap) >= 0 ? 0 : -3) : 0;
+  } catch (const std::exception& e) {
+    if (pods_json) put(std::string("{\"error\":\"") + gph::json_escape(e.what()) + "\"}", pods_json, cap);
+    return -1;
+  }
+}
+
+// owner walk over a fixture directory: pod_meta_json = the pod's .metadata.  JSON out:
+// {"kind":..,"name":..,"namespace":..,"uid":..,"apiVersion":..,"calls":n} or {"error":..}
+GPH_API int gph_find_root(const char* fixture_dir, const char* pod_meta_json, char* out, int cap) {
+  try {
+    gph::FixtureKubeApi api(fixture_dir);
+    gph::RootResult r = gph::find_root_object(api, gph::Json::parse(pod_meta_json));
+    gph::Json j = gph::Json::object();
+    if (r.root) {
+      j.set("kind", r.root->kind_name()), j.set("name", r.root->name());
+      j.set("namespace", r.root->ns() ? gph::Json(*r.root->ns()) : gph::Json());
+      j.set("uid", r.root->uid() ? gph::Json(*r.root->uid()) : gph::Json());
+      j.set("apiVersion", r.root->api_version());
+      j.set("resourceVersion", r.root->resource_version() ? gph::Json(*r.root->resource_version()) : gph::Json());
+      j.set("resource_kind", (int64_t)r.root->resource_kind());
+    } else {
+      j.set("error", r.error);
+    }
+    j.set("calls", (int64_t)api.calls);
+    return put(j.dump(), out, cap);
+  } catch (const std::exception& e) {
+    return put(std::string("{\"error\":\"") + gph::json_escape(e.what()) + "\"}", out, cap);
+  }
+}
+
+static bool kind_from(const std::string& k, gph::Kind* out) {
+  if (k == "Deployment") *out = gph::Kind::Deployment;
+  else if (k == "ReplicaSet") *out = gph::Kind::ReplicaSet;
+  else if (k == "StatefulSet") *out = gph::Kind::StatefulSet;
+  else if (k == "InferenceService") *out = gph::Kind::InferenceService;
+  else if (k == "Notebook") *out = gph::Kind::Notebook;
+  else return false;
+  return true;
+}
+
+// requests that ScaleKind::scale would send, with a fixed clock / uuid for reproducible tests
+GPH_API int gph_scale_requests(const char* kind, const char* object_json, long long now_ns,
+                               const char* uuid, const char* pod_name_env, char* out, int cap) {
+  try {
+    gph::Kind k;
+    if (!kind_from(kind, &k)) return -1;
+    gph::ScaleKind sk{k, gph::Json::parse(object_json)};
+    gph::Clock c;
+    c.now_ns = [now_ns] { return (int64_t)now_ns; };
+    std::string u = uuid;
+    c.uuid_simple = [u] { return u; };
+    gph::Json arr = gph::Json::array();
+    for (const gph::Request& rq : gph::scale_requests(sk, c, pod_name_env ? pod_name_env : "")) {
+      gph::Json j = gph::Json::object();
+      j.set("method", rq.method), j.set("path", rq.path), j.set("contentType", rq.content_type);
+      j.set("body", rq.body);
+      arr.push(j);
+    }
+    return put(arr.dump(), out, cap);
+  } catch (const std::exception&) {
+    return -2;
+  }
+}
+
+// ScaleKind Eq / Hash (lib.rs:45-82): 1 if equal, 0 if not; hashes written to h[2]
+GPH_API int gph_scalekind_eq(const char* kind_a, const char* obj_a, const char* kind_b, const char* obj_b,
+                             unsigned long long* h) {
+  try {
+    gph::Kind ka, kb;
+    if (!kind_from(kind_a, &ka) || !kind_from(kind_b, &kb)) return -1;
+    gph::ScaleKind a{ka, gph::Json::parse(obj_a)}, b{kb, gph::Json::parse(obj_b)};
+    if (h) h[0] = a.hash(), h[1] = b.hash();
+    return a == b ? 1 : 0;
+  } catch (const std::exception&) {
+    return -2;
+  }
+}
+
+GPH_API int gph_rfc3339(long long ns, char* out, int cap) { return put(gph::rfc3339(ns), out, cap); }
+GPH_API long long gph_parse_rfc3339(const char* s) {
+  try {
+    return gph::parse_rfc3339(s);
+  } catch (const std::exception&) {
+    return -1;
+  }
+}

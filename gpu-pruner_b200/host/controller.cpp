@@ -1,0 +1,340 @@
+#include "controller.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <stdexcept>
+#include <sys/stat.h>
+#include <thread>
+#include <unordered_map>
+
+namespace gph {
+
+// ---- logging (main.rs:157-243: default | json | pretty) --------------------------------------------
+void Logger::log(const char* level, const std::string& msg,
+                 const std::vector<std::pair<std::string, std::string>>& fields) const {
+  const auto now = std::chrono::system_clock::now();
+  const int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(now.time_since_epoch()).count();
+  const std::string ts = rfc3339(ns / 1000 * 1000);
+  if (fmt_ == LogFormat::Json) {
+    Json f = Json::object();
+    f.set("message", msg);
+    for (auto& kv : fields) f.set(kv.first, kv.second);
+    Json j = Json::object();
+    j.set("timestamp", ts);
+    j.set("level", level);
+    j.set("fields", f);
+    j.set("target", "gpu_pruner");
+    fprintf(out_, "%s\n", j.dump().c_str());
+  } else if (fmt_ == LogFormat::Pretty) {
+    fprintf(out_, "  %s %s gpu_pruner: %s\n", ts.c_str(), level, msg.c_str());
+    for (auto& kv : fields) fprintf(out_, "    %s: %s\n", kv.first.c_str(), kv.second.c_str());
+  } else {
+    std::string extra;
+    for (auto& kv : fields) extra += " " + kv.first + "=" + kv.second;
+    fprintf(out_, "%s %5s gpu_pruner: %s%s\n", ts.c_str(), level, msg.c_str(), extra.c_str());
+  }
+  fflush(out_);
+}
+void Logger::counter(const char* level, const std::string& name, uint64_t v, const std::string& msg) const {
+  log(level, msg, {{name, std::to_string(v)}});
+}
+
+// ---- window sources ----------------------------------------------------------------------------------
+namespace {
+
+bool file_exists(const std::string& p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0;
+}
+
+// file://DIR with util.json [prof.json] [power.json] [query.json = {"end": ts, "step": s}]
+class FileSource : public WindowSource {
+ public:
+  explicit FileSource(std::string dir) : dir_(std::move(dir)) {}
+  Window fetch(const Cli& args) override {
+    const std::string up = dir_ + "/util.json";
+    if (!file_exists(up)) throw std::runtime_error("Failed to run query! " + up + " not found");
+    Json util = Json::parse_file(up);
+    Json prof, power, meta;
+    const Json *pprof = nullptr, *ppower = nullptr;
+    if (file_exists(dir_ + "/prof.json")) prof = Json::parse_file(dir_ + "/prof.json"), pprof = &prof;
+    const bool want_power = args.power_threshold && *args.power_threshold != 0.0;
+    if (want_power && file_exists(dir_ + "/power.json"))
+      power = Json::parse_file(dir_ + "/power.json"), ppower = &power;
+    IngestOptions opt;
+    opt.duration_min = args.duration;
+    if (file_exists(dir_ + "/query.json")) {
+      meta = Json::parse_file(dir_ + "/query.json");
+      opt.t_end = (int64_t)meta["end"].as_number(0);
+      opt.step = (int64_t)meta["step"].as_number(0);
+    }
+    return ingest_matrix(util, pprof, ppower, opt);
+  }
+
+ private:
+  std::string dir_;
+};
+
+class UnsupportedSource : public WindowSource {
+ public:
+  explicit UnsupportedSource(std::string url) : url_(std::move(url)) {}
+  Window fetch(const Cli&) override {
+    throw std::runtime_error("Failed to run query! HTTP transport to " + url_ +
+                             " is not part of this build (no network); use file://DIR");
+  }
+
+ private:
+  std::string url_;
+};
+
+}  // namespace
+
+std::unique_ptr<WindowSource> make_window_source(const std::string& url) {
+  if (url.rfind("file://", 0) == 0) return std::make_unique<FileSource>(url.substr(7));
+  return std::make_unique<UnsupportedSource>(url);
+}
+
+// ---- controller -----------------------------------------------------------------------------------------
+Controller::Controller(const Cli& args, KubeApi* kube, Logger log, Clock clock)
+    : args_(args), kube_(kube), log_(log), clock_(std::move(clock)),
+      enabled_(get_enabled_resources(args.enabled_resources)) {}
+
+Controller::~Controller() {
+  if (ctx_) gpr_destroy(ctx_);
+}
+
+bool Controller::ensure_engine(const Window& w) {
+  const uint64_t cells = (uint64_t)w.P * w.G * w.T;
+  const bool need_power = !w.power.empty();
+  if (ctx_ && cells <= cap_cells_ && (!need_power || cap_power_)) return true;
+  if (ctx_) gpr_destroy(ctx_), ctx_ = nullptr;
+  gpr_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.struct_size = sizeof cfg;
+  cfg.device = args_.gpu_device;
+  // head-room so that a growing cluster does not re-create the context every tick
+  cfg.max_pods = std::max<uint32_t>(64, w.P + w.P / 4);
+  cfg.max_gpus = std::max<uint32_t>(1, w.G);
+  cfg.max_samples = std::max<uint32_t>(1, w.T);
+  cfg.flags = need_power ? GPR_F_POWER_PLANE : 0;
+  const int rc = gpr_create(&cfg, &ctx_);
+  if (rc != GPR_OK) {
+    engine_error_ = std::string("idle engine unavailable (") + std::to_string(rc) + "): " + gpr_last_error(nullptr);
+    ctx_ = nullptr;
+    return false;
+  }
+  cap_cells_ = (uint64_t)cfg.max_pods * cfg.max_gpus * cfg.max_samples;
+  cap_power_ = need_power;
+  return true;
+}
+
+TickResult Controller::run_query_and_scale(const Window& w) {
+  TickResult out;
+  const uint32_t P = w.P, G = w.G, T = w.T;
+  const uint32_t W = (P + 31) / 32;
+  std::vector<uint32_t> dbits(std::max<uint32_t>(W, 1), 0), cbits(std::max<uint32_t>(W, 1), 0);
+  std::vector<float> smax((size_t)P * G + 1, 0.f);
+
+  // lookback = duration + grace (main.rs:413-414); `now` once per tick
+  const int64_t now_ns = args_.now_override ? args_.now_override * 1000000000ll : clock_.now_ns();
+  const int64_t lookback_ns = (args_.duration * 60 + args_.grace_period) * 1000000000ll;
+  const int64_t cutoff = now_ns - lookback_ns;
+
+  // Pod metadata for the fused gate.  With a pod cache (fixtures / informer) every pod's phase and
+  // creation time are known up front and ride along into the kernel; pods that cannot be
+  // fetched are skipped exactly as main.rs:452-471 does.
+  std::vector<uint8_t> eligible(std::max<uint32_t>(P, 1), 1);
+  std::vector<int64_t> created(std::max<uint32_t>(P, 1), std::numeric_limits<int64_t>::max());
+  std::vector<Json> pod_objs(P);
+  std::vector<std::string> skip_reason(P);
+  for (uint32_t p = 0; p < P && kube_; ++p) {
+    const PodEntry& pe = w.pods[p];
+    std::optional<Json> pod;
+    try {
+      pod = kube_->get_pod(pe.ns, pe.name);
+    } catch (const std::exception& e) {
+      eligible[p] = 0;
+      skip_reason[p] = std::string("retrieval error: ") + e.what();
+      continue;
+    }
+    if (!pod) {
+      eligible[p] = 0;
+      skip_reason[p] = "pod no longer exists";
+      continue;
+    }
+    if ((*pod)["status"]["phase"].as_string() == "Pending") {   // main.rs:473-483
+      eligible[p] = 0;
+      skip_reason[p] = "it's still pending";
+    }
+    const Json& ct = (*pod)["metadata"]["creationTimestamp"];
+    if (ct.is_string()) {
+      try {
+        created[p] = parse_rfc3339(ct.as_string());
+      } catch (const std::exception&) {
+        skip_reason[p] = "unparseable creation timestamp";
+      }
+    } else if (skip_reason[p].empty()) {
+      skip_reason[p] = "has no creation timestamp";            // main.rs:485-492
+    }
+    pod_objs[p] = std::move(*pod);
+  }
+
+  if (P > 0) {
+    if (!ensure_engine(w)) {
+      out.error = engine_error_;
+      return out;
+    }
+    gpr_window win;
+    memset(&win, 0, sizeof win);
+    win.struct_size = sizeof win;
+    win.mem_kind = GPR_MEM_HOST;
+    win.util = w.util.data();
+    const bool power_on = !w.power.empty() && args_.power_threshold && *args_.power_threshold != 0.0;
+    win.power = power_on ? w.power.data() : nullptr;
+    win.power_threshold = power_on ? *args_.power_threshold : 0.0;
+    win.eligible = kube_ ? eligible.data() : nullptr;
+    win.created_ts = kube_ ? created.data() : nullptr;
+    win.cutoff_ts = cutoff;
+    win.n_pods = P, win.n_gpus = G, win.n_samples = T;
+    gpr_result res;
+    memset(&res, 0, sizeof res);
+    res.struct_size = sizeof res;
+    res.out_mem_kind = GPR_MEM_HOST;
+    res.decision_bits = dbits.data();
+    res.candidate_bits = cbits.data();
+    res.series_max = smax.data();
+    const int rc = gpr_decide(ctx_, &win, &res);
+    if (rc != GPR_OK) {
+      out.error = std::string("Failed to run query! idle engine (") + std::to_string(rc) + "): " +
+                  gpr_last_error(ctx_);
+      return out;
+    }
+    out.qr.num_pods = (size_t)res.n_series;
+    out.kernel_ms = res.kernel_ms;
+    out.n_candidates = res.n_candidates;
+    out.n_decisions = res.n_decisions;
+  }
+
+  // candidates -> PodMetricData rows (first idle series of the pod wins, main.rs:430-435)
+  for (uint32_t p = 0; p < P; ++p) {
+    if (!(cbits[p >> 5] >> (p & 31) & 1u)) continue;
+    const PodEntry& pe = w.pods[p];
+    PodMetricData pmd;
+    pmd.name = pe.name, pmd.ns = pe.ns;
+    for (uint32_t g = 0; g < pe.slots.size(); ++g) {
+      if (smax[(size_t)p * G + g] == 0.0f) {
+        const GpuSlot& s = pe.slots[g];
+        pmd.container = s.container, pmd.node_type = s.node_type, pmd.gpu_model = s.model;
+        pmd.value = s.from_prof ? 0.0 : 0.0 / 100.0;   // max / 100 on the UTIL branch (j2:20); idle => 0
+        break;
+      }
+    }
+    out.unique_pods.push_back(pmd);
+  }
+  log_.info("Query returned " + std::to_string(out.qr.num_pods) + " series across " +
+            std::to_string(out.unique_pods.size()) + " unique pods");
+
+  // gates (already folded into decision_bits) + owner walk (main.rs:444-532)
+  std::unordered_set<ScaleKind, ScaleKindHash> seen;
+  for (uint32_t p = 0; p < P; ++p) {
+    if (!(cbits[p >> 5] >> (p & 31) & 1u)) continue;
+    const PodEntry& pe = w.pods[p];
+    const bool decided = (dbits[p >> 5] >> (p & 31)) & 1u;
+    if (!kube_) continue;
+    if (!decided) {
+      const std::string why = !skip_reason[p].empty() ? skip_reason[p]
+                              : "created after the lookback window (" + rfc3339(created[p]) + " >= " + rfc3339(cutoff) + ")";
+      log_.info("Skipping " + pe.ns + ":" + pe.name + ", " + why);
+      continue;
+    }
+    log_.info("Pod " + pe.ns + ":" + pe.name + " is idle and eligible for scaledown");
+    RootResult rr;
+    try {
+      rr = find_root_object(*kube_, pod_objs[p]["metadata"]);
+    } catch (const std::exception& e) {
+      rr.error = e.what();
+    }
+    if (!rr.root) {
+      log_.warn("Skipping " + pe.ns + ":" + pe.name + ", no scalable root object: " + rr.error);
+      continue;
+    }
+    if (seen.insert(*rr.root).second) out.shutdown.push_back(*rr.root);
+  }
+  out.qr.shutdown_events = out.shutdown.size();
+
+  const char* pod_name_env = getenv("POD_NAME");
+  for (const ScaleKind& sk : out.shutdown) {
+    const std::string id = "[" + sk.kind_name() + "] " + sk.ns().value_or("") + ":" + sk.name();
+    if (args_.run_mode == Mode::DryRun) {               // main.rs:540-551
+      log_.info("Dry-run: Would have sent " + id + " for scaledown");
+      continue;
+    }
+    log_.info("Sending " + id + " for scaledown");
+    if (!(enabled_ & sk.resource_kind())) {             // main.rs:337-345
+      log_.info("Skipping resource type \"" + sk.kind_name() + "\" because it is not enabled");
+      continue;
+    }
+    for (Request& rq : scale_requests(sk, clock_, pod_name_env ? pod_name_env : "")) out.requests.push_back(std::move(rq));
+    ++scale_successes;
+    log_.counter("INFO", "monotonic_counter.scale_successes", 1,
+                 "Scaled Resource: [" + sk.kind_name() + "] - " + sk.ns().value_or("default") + ":" + sk.name());
+  }
+  out.ok = true;
+  return out;
+}
+
+int Controller::run(WindowSource& src) {
+  size_t consecutive_failures = 0;   // QUERY_FAILURES, main.rs:136
+  int ticks = 0;
+  std::ofstream patch_out;
+  if (args_.patch_out) patch_out.open(*args_.patch_out, std::ios::app);
+  auto next_tick = std::chrono::steady_clock::now();
+  while (true) {
+    if (args_.daemon_mode) {          // first tick fires immediately (tokio interval), main.rs:292-294
+      std::this_thread::sleep_until(next_tick);
+      next_tick += std::chrono::seconds(args_.check_interval);
+    }
+    TickResult tr;
+    try {
+      Window w = src.fetch(args_);
+      tr = run_query_and_scale(w);
+    } catch (const std::exception& e) {
+      tr.ok = false;
+      tr.error = e.what();
+    }
+    if (tr.ok) {
+      consecutive_failures = 0;
+      ++query_successes;
+      log_.counter("INFO", "monotonic_counter.query_successes", 1, "Query succeeded");
+      log_.counter("INFO", "counter.query_returned_candidates", tr.qr.num_pods, "Returned candidates");
+      log_.counter("INFO", "counter.query_returned_shutdown_events", tr.qr.shutdown_events,
+                   "Returned shutdown events");
+      for (const Request& rq : tr.requests) {
+        Json j = Json::object();
+        j.set("method", rq.method), j.set("path", rq.path), j.set("contentType", rq.content_type);
+        j.set("body", rq.body);
+        if (patch_out.is_open()) patch_out << j.dump() << "\n" << std::flush;
+        else fprintf(stdout, "%s\n", j.dump().c_str());
+      }
+    } else {
+      const size_t failures = consecutive_failures++;   // fetch_add returns the previous value
+      ++query_failures;
+      log_.counter("ERROR", "monotonic_counter.query_failures", 1,
+                   "Failed to run query and scale down: " + tr.error);
+      if (failures > 5) {                               // main.rs:317-320
+        log_.error("Too many consecutive failures, exiting");
+        break;   // the reference leaves the loop and main() still returns Ok(()) -> exit code 0
+      }
+    }
+    ++ticks;
+    if (!args_.daemon_mode) break;
+    if (args_.max_ticks && ticks >= args_.max_ticks) break;
+  }
+  return 0;  // like the reference: failures are logged and counted, never turned into an exit code
+}
+
+}  // namespace gph

@@ -1,0 +1,36 @@
+// gpu-pruner — C++ host of the B200 idle-decision engine, with the reference controller's
+// command-line surface (/root/reference/gpu-pruner/src/main.rs:46-134, 273-375).
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cli.hpp"
+#include "controller.hpp"
+#include "kube.hpp"
+#include "promql.hpp"
+
+int main(int argc, char** argv) {
+  std::vector<std::string> args(argv + 1, argv + argc);
+  gph::ParseOutcome po = gph::parse_cli(args);
+  if (!po.ok) {
+    fputs(po.message.c_str(), po.exit_code == 0 ? stdout : stderr);
+    return po.exit_code;
+  }
+  const gph::Cli& cli = po.cli;
+  if (cli.print_query) {  // the text the reference logs as "Running w/ Query: ..." (main.rs:282)
+    fputs(gph::render_query(cli).c_str(), stdout);
+    return 0;
+  }
+  gph::Logger log(cli.log_format, stderr);
+  log.info("Enabled resources: " + std::to_string((int)gph::get_enabled_resources(cli.enabled_resources)));
+  log.info("Running w/ Query: " + gph::render_query(cli));
+  const gph::Selectors sel = gph::render_selectors(cli);
+  log.info("Engine selectors: " + sel.util + (sel.power.empty() ? "" : " ; " + sel.power));
+
+  std::unique_ptr<gph::FixtureKubeApi> kube;
+  if (cli.kube_fixture) kube = std::make_unique<gph::FixtureKubeApi>(*cli.kube_fixture);
+  std::unique_ptr<gph::WindowSource> src = gph::make_window_source(cli.prometheus_url);
+  gph::Controller ctl(cli, kube.get(), log, gph::system_clock());
+  return ctl.run(*src);
+}

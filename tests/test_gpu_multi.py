@@ -1,0 +1,75 @@
+"""GPU, >= 2 devices: pod-sharded decision with the NCCL allgather of the packed bitmap, one process
+per GPU, through the C ABI (gpr_comm_unique_id / gpr_comm_init / gpr_decide).  Skips on a 1-GPU box;
+run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank(rank, world, port, total, G, T, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import gpu_pruner_b200 as g
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    eng = g.IdleEngine(device=rank)
+    uid = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(uid[0], rank, world)
+    sh = g.shard_pods(total, rank, world)
+    P = sh.pods_per_rank
+    dev = f"cuda:{rank}"
+    u = torch.full((P, G, T), float("nan"), dtype=torch.float32, device=dev)
+    eng.synth_fill(seed, 0, u, sh.pod_begin, sh.pods_real, G, T)
+    e = torch.zeros(P, dtype=torch.uint8, device=dev)
+    eng.synth_eligible(seed, e, sh.pod_begin, sh.pods_real)
+    db = torch.zeros(world * P // 32, dtype=torch.int32, device=dev)
+    cb = torch.zeros(world * P // 32, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for it in range(3):   # repeated calls reuse the communicator
+        r = eng.decide_ptr(u, P, G, T, db, eligible=e, candidate_bits=cb)
+    np.save(os.path.join(out_dir, f"d_{rank}.npy"), db.cpu().numpy().view(np.uint32))
+    np.save(os.path.join(out_dir, f"c_{rank}.npy"), cb.cpu().numpy().view(np.uint32))
+    np.save(os.path.join(out_dir, f"n_{rank}.npy"), np.array([r.n_series, r.n_candidates, r.n_decisions]))
+    # host outputs through the same path
+    hd = np.zeros(world * P // 32, np.uint32)
+    eng.decide_ptr(u, P, G, T, hd, eligible=e, out_kind=0)
+    np.save(os.path.join(out_dir, f"h_{rank}.npy"), hd)
+    dist.barrier()
+    eng.comm_destroy()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [5000, 64 * 1000 + 7])
+def test_sharded_decision_allgather(total, tmp_path, oracle_c):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    G, T, seed = 4, 600, 0x5EED0004
+    mp.spawn(_rank, args=(world, _free_port(), total, G, T, seed, str(tmp_path)), nprocs=world, join=True)
+    ref = oracle_c.decide_synth(seed, 0, total, G, T, use_elig=True)
+    W = (total + 31) // 32
+    n = np.zeros(3, np.int64)
+    for rank in range(world):
+        for tag, key in (("d", "decision_bits"), ("h", "decision_bits"), ("c", "candidate_bits")):
+            full = np.load(tmp_path / f"{tag}_{rank}.npy")
+            assert np.array_equal(full[:W], ref[key]), (tag, rank)
+            assert not full[W:].any()
+        n += np.load(tmp_path / f"n_{rank}.npy")
+    assert tuple(n) == (ref["n_series"], ref["n_candidates"], ref["n_decisions"])

@@ -50,9 +50,16 @@ if __name__ == "__main__":
     ap.add_argument("--configs", default="c2,c3")
     ap.add_argument("--variants", default="ldg,tma")
     ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--shape", default="", help="P,G,T,rot (overrides --configs)")
+    ap.add_argument("--power", action="store_true")
     a = ap.parse_args()
     shapes = {"c2": (10000, 4, 1800, 6), "c3": (100000, 8, 3600, 2), "c4": (250000, 4, 1800, 2),
               "c5s": (312500, 4, 7200, 1)}
+    if a.shape:
+        P, G, T, rot = map(int, a.shape.split(","))
+        for v in a.variants.split(","):
+            run(v, P, G, T, a.iters, rot, power=a.power)
+        sys.exit(0)
     for c in a.configs.split(","):
         P, G, T, rot = shapes[c]
         for v in a.variants.split(","):
