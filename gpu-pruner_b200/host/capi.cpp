@@ -206,3 +206,22 @@ GPH_API long long gph_parse_rfc3339(const char* s) {
     return -1;
   }
 }
+
+// Event that generate_scale_event builds (lib.rs:388-427)
+GPH_API int gph_generate_event(const char* kind, const char* object_json, long long now_ns,
+                               const char* uuid, const char* pod_name_env, char* out, int cap) {
+  try {
+    gph::Kind k;
+    if (!kind_from(kind, &k)) return -1;
+    gph::ScaleKind sk{k, gph::Json::parse(object_json)};
+    gph::Clock c = gph::system_clock();
+    if (now_ns) c.now_ns = [now_ns] { return (int64_t)now_ns; };
+    if (uuid && *uuid) {
+      std::string u = uuid;
+      c.uuid_simple = [u] { return u; };
+    }
+    return put(gph::generate_scale_event(sk, c, pod_name_env ? pod_name_env : "").dump(), out, cap);
+  } catch (const std::exception&) {
+    return -2;
+  }
+}

@@ -17,15 +17,42 @@ LabelNames label_names(bool honor) {
 std::string format_float(double v) {
   if (std::isnan(v)) return "nan";
   if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-  char buf[40];
-  for (int prec = 1; prec <= 17; ++prec) {
-    snprintf(buf, sizeof buf, "%.*g", prec, v);
+  if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+  // shortest digit string that round-trips (what repr / minijinja print)
+  char buf[48];
+  int prec = 1;
+  for (; prec <= 17; ++prec) {
+    snprintf(buf, sizeof buf, "%.*e", prec - 1, v);
     if (strtod(buf, nullptr) == v) break;
   }
-  std::string s = buf;
-  if (s.find_first_of(".en") == std::string::npos) s += ".0";
-  // Python/minijinja write exponents as e-07 / e+20; %g already pads to two digits
-  return s;
+  // buf = [-]d.ddddde[+-]XX
+  std::string m = buf;
+  const size_t epos = m.find('e');
+  const int exp10 = atoi(m.c_str() + epos + 1);
+  std::string digits;
+  bool neg = false;
+  for (size_t k = 0; k < epos; ++k) {
+    if (m[k] == '-') neg = true;
+    else if (m[k] != '.') digits += m[k];
+  }
+  std::string out = neg ? "-" : "";
+  if (exp10 >= -4 && exp10 < 16) {  // positional notation, always with a fractional part
+    if (exp10 >= 0) {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)exp10 + 1));
+      while ((int)ip.size() < exp10 + 1) ip += '0';
+      std::string fp = digits.size() > (size_t)exp10 + 1 ? digits.substr((size_t)exp10 + 1) : "0";
+      out += ip + "." + fp;
+    } else {
+      out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+    }
+  } else {  // scientific: d[.ddd]e[+-]XX with at least two exponent digits
+    out += digits.substr(0, 1);
+    if (digits.size() > 1) out += "." + digits.substr(1);
+    char e[16];
+    snprintf(e, sizeof e, "e%c%02d", exp10 < 0 ? '-' : '+', exp10 < 0 ? -exp10 : exp10);
+    out += e;
+  }
+  return out;
 }
 
 namespace {

@@ -1,0 +1,120 @@
+"""ctypes access to libgprhost.so (the C++ host logic) for the CPU tests."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_DIR = os.path.join(ROOT, "gpu-pruner_b200", "host")
+SO = os.path.join(ROOT, "gpu-pruner_b200", "libgprhost.so")
+BIN = os.path.join(ROOT, "gpu-pruner_b200", "gpu-pruner")
+_lib = None
+CAP = 1 << 22
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            subprocess.check_call(["make", "-C", HOST_DIR, "-s", "../libgprhost.so"])
+        _lib = C.CDLL(SO)
+        _lib.gph_parse_rfc3339.restype = C.c_longlong
+        _lib.gph_format_float.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        _lib.gph_rfc3339.argtypes = [C.c_longlong, C.c_char_p, C.c_int]
+    return _lib
+
+
+def _args(argv):
+    blob = b"".join(a.encode() + b"\0" for a in argv)
+    return blob, len(argv)
+
+
+def _call(fn, *args):
+    buf = C.create_string_buffer(CAP)
+    rc = fn(*args, buf, CAP)
+    return rc, buf.value.decode()
+
+
+def parse_cli(argv):
+    blob, n = _args(argv)
+    rc, s = _call(lib().gph_parse_cli, blob, n)
+    assert rc >= 0
+    return json.loads(s)
+
+
+def render_query(argv):
+    blob, n = _args(argv)
+    rc, s = _call(lib().gph_render_query, blob, n)
+    assert rc >= 0, s
+    return s
+
+
+def render_selectors(argv):
+    blob, n = _args(argv)
+    rc, s = _call(lib().gph_render_selectors, blob, n)
+    assert rc >= 0
+    return json.loads(s)
+
+
+def enabled_resources(letters):
+    return lib().gph_enabled_resources(letters.encode())
+
+
+def format_float(v):
+    rc, s = _call(lib().gph_format_float, C.c_double(v))
+    return s
+
+
+def find_root(fixture_dir, pod_meta):
+    rc, s = _call(lib().gph_find_root, fixture_dir.encode(), json.dumps(pod_meta).encode())
+    assert rc >= 0
+    return json.loads(s)
+
+
+def scale_requests(kind, obj, now_ns=1_700_000_000_123_456_789, uuid="0123456789abcdef0123456789abcdef", pod_name=""):
+    rc, s = _call(lib().gph_scale_requests, kind.encode(), json.dumps(obj).encode(), C.c_longlong(now_ns),
+                  uuid.encode(), pod_name.encode())
+    assert rc >= 0, rc
+    return json.loads(s)
+
+
+def generate_event(kind, obj, now_ns=0, uuid="", pod_name=""):
+    rc, s = _call(lib().gph_generate_event, kind.encode(), json.dumps(obj).encode(), C.c_longlong(now_ns),
+                  uuid.encode(), pod_name.encode())
+    assert rc >= 0, rc
+    return json.loads(s)
+
+
+def scalekind_eq(kind_a, a, kind_b, b):
+    h = (C.c_ulonglong * 2)()
+    rc = lib().gph_scalekind_eq(kind_a.encode(), json.dumps(a).encode(), kind_b.encode(), json.dumps(b).encode(), h)
+    assert rc >= 0
+    return bool(rc), h[0], h[1]
+
+
+def rfc3339(ns):
+    rc, s = _call(lib().gph_rfc3339, C.c_longlong(ns))
+    return s
+
+
+def parse_rfc3339(s):
+    return lib().gph_parse_rfc3339(s.encode())
+
+
+def ingest(util, prof=None, power=None, duration_min=30, step=0, t_end=0):
+    import numpy as np
+    dims = (C.c_uint * 3)()
+    enc = lambda j: None if j is None else json.dumps(j).encode()
+    meta = C.create_string_buffer(CAP)
+    rc = lib().gph_ingest(enc(util), enc(prof), enc(power), C.c_longlong(duration_min), C.c_longlong(step),
+                          C.c_longlong(t_end), dims, None, None, meta, CAP)
+    if rc != 0:
+        raise RuntimeError(json.loads(meta.value.decode()).get("error", "ingest failed"))
+    P, G, T = dims[0], dims[1], dims[2]
+    u = np.zeros((P, G, T), np.float32)
+    w = np.zeros((P, G, T), np.float32) if power is not None else None
+    rc = lib().gph_ingest(enc(util), enc(prof), enc(power), C.c_longlong(duration_min), C.c_longlong(step),
+                          C.c_longlong(t_end), dims, u.ctypes.data_as(C.c_void_p),
+                          None if w is None else w.ctypes.data_as(C.c_void_p), meta, CAP)
+    assert rc == 0
+    return u, w, json.loads(meta.value.decode())

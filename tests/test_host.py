@@ -1,0 +1,478 @@
+"""CPU: the C++ host side (gpu-pruner_b200/host) against the reference's own tests as specification.
+
+* CLI: flags / shorts / defaults of /root/reference/gpu-pruner/src/main.rs:46-134
+* K15: the 11 template-text assertions of main.rs:584-739, plus byte-exact equality with the
+  reference template rendered by jinja2 (tests/golden/query_render.json)
+* the 36 unit tests of /root/reference/gpu-pruner/src/lib.rs:578-998 (enabled resources, bitflags,
+  ScaleKind Eq/Hash/Meta, Event fields) re-stated against the C++ port
+* the owner-walk scenarios of /root/reference/gpu-pruner/tests/e2e.rs:168-252 on JSON fixtures
+* ingest of the Prometheus matrix wire format (querytest.rs:41-53)
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hostlib as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "query_render.json")
+URL = ["--prometheus-url", "http://prom:9090"]
+
+
+# ---------------------------------------------------------------------------------------------
+# CLI (main.rs:46-134)
+# ---------------------------------------------------------------------------------------------
+def test_cli_defaults():
+    r = H.parse_cli(URL)
+    assert r["ok"]
+    c = r["cli"]
+    assert c == {"duration": 30, "daemon_mode": False, "enabled_resources": "drsin", "check_interval": 180,
+                 "namespace": None, "grace_period": 300, "model_name": None, "power_threshold": None,
+                 "honor_labels": False, "run_mode": "dry-run", "prometheus_url": "http://prom:9090",
+                 "prometheus_token": None, "prometheus_tls_mode": "verify", "prometheus_tls_cert": None,
+                 "log_format": "default"}
+
+
+def test_cli_short_and_long_forms():
+    r = H.parse_cli(["-t", "45", "-d", "-e", "dn", "-c", "60", "-n", "ml-.*", "-g", "120", "-m", "NVIDIA A100",
+                     "--power-threshold", "150", "--honor-labels", "-r", "scale-down", "-l", "json",
+                     "--prometheus-tls-mode", "skip", "--prometheus-tls-cert", "/x.crt",
+                     "--prometheus-token", "tok"] + URL)
+    assert r["ok"], r["message"]
+    c = r["cli"]
+    assert (c["duration"], c["daemon_mode"], c["enabled_resources"], c["check_interval"]) == (45, True, "dn", 60)
+    assert (c["namespace"], c["grace_period"], c["model_name"]) == ("ml-.*", 120, "NVIDIA A100")
+    assert c["power_threshold"] == 150.0 and c["honor_labels"] is True
+    assert (c["run_mode"], c["log_format"], c["prometheus_tls_mode"]) == ("scale-down", "json", "skip")
+    assert c["prometheus_tls_cert"] == "/x.crt" and c["prometheus_token"] == "tok"
+    r2 = H.parse_cli(["--duration=45", "-c60", "--run-mode=scale-down", "--namespace=a b"] + URL)
+    assert r2["ok"] and r2["cli"]["duration"] == 45 and r2["cli"]["check_interval"] == 60
+    assert r2["cli"]["run_mode"] == "scale-down" and r2["cli"]["namespace"] == "a b"
+
+
+@pytest.mark.parametrize("argv,needle", [
+    ([], "--prometheus-url"),
+    (URL + ["--run-mode", "nuke"], "possible values: scale-down, dry-run"),
+    (URL + ["--log-format", "xml"], "possible values: json, default, pretty"),
+    (URL + ["--prometheus-tls-mode", "maybe"], "possible values: skip, verify"),
+    (URL + ["-t", "abc"], "invalid value 'abc' for '--duration'"),
+    (URL + ["-c", "-5"], "invalid value '-5' for '--check-interval'"),
+    (URL + ["--bogus"], "unexpected argument '--bogus'"),
+    (URL + ["-z"], "unexpected argument '-z'"),
+    (URL + ["--duration"], "a value is required for '--duration'"),
+    (URL + ["--daemon-mode=yes"], "unexpected value 'yes'"),
+    (URL + ["stray"], "unexpected argument 'stray'"),
+])
+def test_cli_errors_exit_2(argv, needle):
+    r = H.parse_cli(argv)
+    assert not r["ok"] and r["exit_code"] == 2
+    assert needle in r["message"] and r["message"].startswith("error: ")
+
+
+def test_cli_help_exits_0_and_lists_every_flag():
+    r = H.parse_cli(["--help"])
+    assert not r["ok"] and r["exit_code"] == 0
+    for flag in ("-t, --duration", "-d, --daemon-mode", "-e, --enabled-resources", "-c, --check-interval",
+                 "-n, --namespace", "-g, --grace-period", "-m, --model-name", "--power-threshold",
+                 "--honor-labels", "-r, --run-mode", "--prometheus-url", "--prometheus-token",
+                 "--prometheus-tls-mode", "--prometheus-tls-cert", "-l, --log-format"):
+        assert flag in r["message"], flag
+
+
+def test_binary_cli_surface():
+    if not os.path.exists(H.BIN):
+        pytest.skip("gpu-pruner binary not built")
+    p = subprocess.run([H.BIN, "--help"], capture_output=True, text=True)
+    assert p.returncode == 0 and "Usage: gpu-pruner [OPTIONS] --prometheus-url <PROMETHEUS_URL>" in p.stdout
+    p = subprocess.run([H.BIN], capture_output=True, text=True)
+    assert p.returncode == 2 and "--prometheus-url" in p.stderr
+    p = subprocess.run([H.BIN, "--print-query", "-t", "45"], capture_output=True, text=True)
+    assert p.returncode == 0 and "[45m]" in p.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# K15: template-text parity
+# ---------------------------------------------------------------------------------------------
+def _argv(a):
+    v = ["--print-query", "-t", str(a["duration"])]
+    if a.get("namespace"):
+        v += ["-n", a["namespace"]]
+    if a.get("model_name"):
+        v += ["-m", a["model_name"]]
+    if a.get("power_threshold") is not None:
+        v += ["--power-threshold", repr(a["power_threshold"])]
+    if a.get("honor_labels"):
+        v += ["--honor-labels"]
+    return v
+
+
+def test_render_is_byte_exact_with_the_reference_template():
+    cases = json.load(open(GOLD))
+    assert len(cases) == 120
+    for c in cases:
+        assert H.render_query(_argv(c["args"])) == c["text"], c["args"]
+
+
+def render(**a):
+    a.setdefault("duration", 30)
+    return H.render_query(_argv(a))
+
+
+def test_query_uses_max_over_time():                      # main.rs:584-595
+    q = render()
+    assert "max_over_time(" in q and "avg_over_time(" not in q
+
+
+def test_query_includes_gpu_util_fallback():              # main.rs:597-612
+    q = render()
+    assert "DCGM_FI_PROF_GR_ENGINE_ACTIVE" in q and "DCGM_FI_DEV_GPU_UTIL" in q and "/ 100" in q
+
+
+def test_query_without_power_threshold_has_no_unless():   # main.rs:614-625
+    q = render()
+    assert "unless" not in q and "DCGM_FI_DEV_POWER_USAGE" not in q
+
+
+def test_query_with_power_threshold_adds_unless():        # main.rs:627-642
+    q = render(power_threshold=150.0)
+    assert "unless on (exported_pod, exported_namespace)" in q
+    assert "DCGM_FI_DEV_POWER_USAGE" in q and ">= 150" in q
+
+
+def test_query_with_namespace_filter():                   # main.rs:644-654
+    assert render(duration=15, namespace="ml-team").count('exported_namespace =~ "ml-team"') == 4
+
+
+def test_query_with_namespace_and_power_threshold():      # main.rs:656-668
+    q = render(duration=15, namespace="ml-team", power_threshold=100.0)
+    assert q.count('exported_namespace =~ "ml-team"') == 5
+
+
+def test_query_with_model_name_filter():                  # main.rs:670-679
+    assert render(model_name="NVIDIA A100").count('modelName =~ "NVIDIA A100"') == 4
+
+
+def test_query_duration_is_interpolated():                # main.rs:681-688
+    assert "[45m]" in render(duration=45)
+
+
+def test_query_default_uses_exported_labels():            # main.rs:690-705
+    q = render()
+    assert "exported_pod" in q and "exported_namespace" in q and "exported_container" in q
+
+
+def test_query_honor_labels_uses_native_labels():         # main.rs:707-726
+    q = render(honor_labels=True)
+    assert "exported_pod" not in q and "exported_namespace" not in q
+    assert "pod !=" in q and "sum by (Hostname, container, pod, namespace" in q
+
+
+def test_query_honor_labels_with_power_threshold():       # main.rs:728-739
+    assert "unless on (pod, namespace)" in render(honor_labels=True, power_threshold=120.0)
+
+
+def test_zero_power_threshold_is_falsy():                 # query.promql.j2:36
+    assert "unless" not in render(power_threshold=0.0)
+
+
+def test_selector_forms_share_the_filters():
+    s = H.render_selectors(["-t", "15", "-n", "ml-team", "-m", "A100", "--power-threshold", "150"] + URL)
+    assert s["util"] == 'DCGM_FI_DEV_GPU_UTIL{exported_pod != "", exported_namespace =~ "ml-team", modelName =~ "A100"}[15m]'
+    assert s["prof"].startswith("DCGM_FI_PROF_GR_ENGINE_ACTIVE{") and s["prof"].endswith("}[15m]")
+    assert s["power"] == 'DCGM_FI_DEV_POWER_USAGE{exported_pod != "", exported_namespace =~ "ml-team"}[15m]'
+    assert H.render_selectors(URL)["power"] == ""
+
+
+@pytest.mark.parametrize("v,s", [(150.0, "150.0"), (120.5, "120.5"), (100.0, "100.0"), (0.1, "0.1"),
+                                 (1e-7, "1e-07"), (1e21, "1e+21"), (-3.25, "-3.25")])
+def test_float_formatting_matches_jinja(v, s):
+    assert H.format_float(v) == s
+
+
+# ---------------------------------------------------------------------------------------------
+# lib.rs unit tests, re-stated (lib.rs:656-997)
+# ---------------------------------------------------------------------------------------------
+D, R, S, I, N = 1, 2, 4, 8, 16
+
+
+def test_enabled_resources():
+    assert H.enabled_resources("drsin") == D | R | S | I | N          # all flags
+    assert H.enabled_resources("n") == N                               # single flag
+    assert H.enabled_resources("di") == D | I                          # subset
+    assert H.enabled_resources("") == 0                                # empty
+    assert H.enabled_resources("xdqz") == D                            # unknown chars ignored
+    assert H.enabled_resources("dddd") == H.enabled_resources("d")     # idempotent
+
+
+def mk(name, ns, uid=None, **extra):
+    meta = {"name": name}
+    if ns is not None:
+        meta["namespace"] = ns
+    if uid is not None:
+        meta["uid"] = uid
+    o = {"metadata": meta}
+    o.update(extra)
+    return o
+
+
+KINDS = {"Deployment": D, "ReplicaSet": R, "StatefulSet": S, "InferenceService": I, "Notebook": N}
+
+
+def test_scale_kind_equality_and_hash():
+    eq = lambda ka, a, kb, b: H.scalekind_eq(ka, a, kb, b)
+    assert eq("Deployment", mk("d", "ns", "uid-1"), "Deployment", mk("d", "ns", "uid-1"))[0]      # same
+    assert not eq("Deployment", mk("d", "ns", "uid-1"), "Deployment", mk("d", "ns", "uid-2"))[0]  # uid differs
+    assert not eq("Deployment", mk("x", "ns", "uid-1"), "ReplicaSet", mk("x", "ns", "uid-1"))[0]  # variants
+    assert eq("Notebook", mk("nb-a", "ns", "same-uid"), "Notebook", mk("nb-b", "ns", "same-uid"))[0]
+    assert eq("InferenceService", mk("is-a", "ns", "uid-x"), "InferenceService", mk("is-b", "ns", "uid-x"))[0]
+    # hash = variant + uid: equal objects hash equal; same uid in another variant hashes differently
+    _, h1, h2 = eq("Deployment", mk("d", "ns", "uid-1"), "Deployment", mk("d", "ns", "uid-1"))
+    assert h1 == h2
+    _, h1, h2 = eq("Deployment", mk("x", "ns", "uid-1"), "ReplicaSet", mk("x", "ns", "uid-1"))
+    assert h1 != h2
+    _, h1, h2 = eq("Notebook", mk("nb-a", "ns", "uid-nb"), "Notebook", mk("nb-b", "ns", "uid-nb"))
+    assert h1 == h2
+
+
+@pytest.mark.parametrize("kind,api", [("Deployment", "apps/v1"), ("ReplicaSet", "apps/v1"),
+                                      ("StatefulSet", "apps/v1"), ("Notebook", "v1"),
+                                      ("InferenceService", "v1beta1")])
+def test_meta_and_event_fields(kind, api):
+    ev = H.generate_event(kind, mk("my-obj", "prod", "the-uid", **{"metadata": {
+        "name": "my-obj", "namespace": "prod", "uid": "the-uid", "resourceVersion": "42"}}))
+    io = ev["involvedObject"]
+    assert (io["name"], io["namespace"], io["kind"], io["uid"], io["apiVersion"]) == (
+        "my-obj", "prod", kind, "the-uid", api)
+    assert io["resourceVersion"] == "42"
+    assert ev["action"] == "scale_down" and ev["type"] == "Normal"
+    assert ev["reason"] == "Pod prod::my-obj was not using GPU"
+    assert ev["reportingComponent"] == "gpu-pruner" and ev["reportingInstance"] == "gpu_pruner"
+    assert ev["metadata"]["name"].startswith("gpuscaler-") and len(ev["metadata"]["name"]) == 10 + 32
+    assert ev["metadata"]["namespace"] == "prod"
+    assert ev["firstTimestamp"] and ev["lastTimestamp"] and ev["eventTime"]
+
+
+def test_event_names_are_unique_and_pod_name_env():
+    a = H.generate_event("Notebook", mk("nb", "ns"))
+    b = H.generate_event("Notebook", mk("nb", "ns"), pod_name="gpu-pruner-7d9f")
+    assert a["metadata"]["name"] != b["metadata"]["name"]
+    assert b["reportingInstance"] == "gpu-pruner-7d9f"
+    assert "uid" not in a["involvedObject"]                       # event_for_replica_set: uid None
+
+
+def test_event_with_no_namespace():
+    ev = H.generate_event("Deployment", mk("orphan", None))
+    assert "namespace" not in ev["involvedObject"] and ev["reason"] == "Pod ::orphan was not using GPU"
+    # and scale() emits no Event POST without a namespace (lib.rs:340)
+    rq = H.scale_requests("Deployment", mk("orphan", None))
+    assert [r["method"] for r in rq] == ["PATCH"]
+
+
+def test_filter_integration():
+    enabled = H.enabled_resources("dn")
+    assert enabled & KINDS["Deployment"] and enabled & KINDS["Notebook"] and not enabled & KINDS["StatefulSet"]
+
+
+# ---------------------------------------------------------------------------------------------
+# scale-to-zero request bodies (lib.rs:517-576)
+# ---------------------------------------------------------------------------------------------
+def test_scale_requests():
+    now = 1_700_000_000_123_456_789
+    rq = H.scale_requests("Deployment", mk("web", "prod", "u1"), now)
+    assert rq[0]["method"] == "POST" and rq[0]["path"] == "/api/v1/namespaces/prod/events"
+    assert rq[0]["body"]["metadata"]["name"] == "gpuscaler-0123456789abcdef0123456789abcdef"
+    assert rq[0]["body"]["eventTime"] == "2023-11-14T22:13:20.123456Z"
+    assert rq[1] == {"method": "PATCH", "path": "/apis/apps/v1/namespaces/prod/deployments/web/scale",
+                     "contentType": "application/merge-patch+json", "body": {"spec": {"replicas": 0}}}
+    assert H.scale_requests("ReplicaSet", mk("rs", "a"))[1]["path"] == "/apis/apps/v1/namespaces/a/replicasets/rs/scale"
+    assert H.scale_requests("StatefulSet", mk("ss", "a"))[1]["path"] == "/apis/apps/v1/namespaces/a/statefulsets/ss/scale"
+    nb = H.scale_requests("Notebook", mk("nb", "ml"), now)[1]
+    assert nb["path"] == "/apis/kubeflow.org/v1/namespaces/ml/notebooks/nb"
+    assert nb["body"] == {"metadata": {"annotations": {"kubeflow-resource-stopped": "2023-11-14T22:13:20.123456789Z"}}}
+    isv = H.scale_requests("InferenceService", mk("llm", "serving"), now)[1]
+    assert isv["path"] == "/apis/serving.kserve.io/v1beta1/namespaces/serving/inferenceservices/llm"
+    assert isv["body"] == {"spec": {"predictor": {"minReplicas": 0}}}
+
+
+def test_rfc3339_round_trip():
+    assert H.rfc3339(1_700_000_000_000_000_000) == "2023-11-14T22:13:20Z"
+    assert H.rfc3339(1_700_000_000_500_000_000) == "2023-11-14T22:13:20.5Z"
+    for s in ("2023-11-14T22:13:20Z", "2024-02-29T00:00:00Z", "1999-12-31T23:59:59Z"):
+        assert H.rfc3339(H.parse_rfc3339(s)) == s
+    assert H.parse_rfc3339("2023-11-14T23:13:20+01:00") == 1_700_000_000_000_000_000
+
+
+# ---------------------------------------------------------------------------------------------
+# owner walk on fixtures (lib.rs:437-513; scenarios of tests/e2e.rs:168-252)
+# ---------------------------------------------------------------------------------------------
+def _write(root, plural, ns, obj):
+    d = root / plural / ns
+    d.mkdir(parents=True, exist_ok=True)
+    (d / (obj["metadata"]["name"] + ".json")).write_text(json.dumps(obj))
+
+
+def _owner(kind, name):
+    return {"apiVersion": "apps/v1", "kind": kind, "name": name, "uid": "o-" + name}
+
+
+@pytest.fixture()
+def cluster(tmp_path):
+    ns = "team-a"
+    _write(tmp_path, "deployments", ns, mk("web", ns, "dep-uid"))
+    _write(tmp_path, "replicasets", ns, {"metadata": {"name": "web-5d9", "namespace": ns, "uid": "rs-uid",
+                                                      "ownerReferences": [_owner("Deployment", "web")]}})
+    _write(tmp_path, "replicasets", ns, mk("bare-rs", ns, "rs2-uid"))
+    _write(tmp_path, "replicasets", ns, {"metadata": {"name": "dangling-rs", "namespace": ns, "uid": "rs3-uid",
+                                                      "ownerReferences": [_owner("Deployment", "gone")]}})
+    _write(tmp_path, "statefulsets", ns, mk("db", ns, "ss-uid"))
+    _write(tmp_path, "statefulsets", ns, {"metadata": {"name": "nb-ss", "namespace": ns, "uid": "ss2-uid",
+                                                       "ownerReferences": [{"kind": "Notebook", "name": "my-nb"}]}})
+    _write(tmp_path, "notebooks", ns, mk("my-nb", ns, "nb-uid"))
+    _write(tmp_path, "inferenceservices", ns, mk("llm", ns, "is-uid"))
+    return str(tmp_path), ns
+
+
+def test_deployment_chain_resolves_to_deployment_not_replicaset(cluster):   # e2e.rs:168-197
+    d, ns = cluster
+    r = H.find_root(d, {"name": "web-5d9-abc", "namespace": ns, "ownerReferences": [_owner("ReplicaSet", "web-5d9")]})
+    assert (r["kind"], r["name"], r["uid"], r["apiVersion"]) == ("Deployment", "web", "dep-uid", "apps/v1")
+    assert r["calls"] == 2
+
+
+def test_bare_statefulset_and_bare_replicaset(cluster):                      # e2e.rs:199-236
+    d, ns = cluster
+    r = H.find_root(d, {"name": "db-0", "namespace": ns, "ownerReferences": [_owner("StatefulSet", "db")]})
+    assert (r["kind"], r["name"]) == ("StatefulSet", "db")
+    r = H.find_root(d, {"name": "p", "namespace": ns, "ownerReferences": [_owner("ReplicaSet", "bare-rs")]})
+    assert (r["kind"], r["name"]) == ("ReplicaSet", "bare-rs")
+
+
+def test_orphan_pod_errors(cluster):                                         # e2e.rs:238-252
+    d, ns = cluster
+    r = H.find_root(d, {"name": "orphan", "namespace": ns})
+    assert "no scalable root object found" in r["error"] and "orphan" in r["error"]
+    r = H.find_root(d, {"name": "job-pod", "namespace": ns, "ownerReferences": [_owner("Job", "batch")]})
+    assert "no scalable root object found" in r["error"]
+
+
+def test_statefulset_owned_by_notebook(cluster):
+    d, ns = cluster
+    r = H.find_root(d, {"name": "nb-ss-0", "namespace": ns, "ownerReferences": [_owner("StatefulSet", "nb-ss")]})
+    assert (r["kind"], r["name"], r["apiVersion"], r["resource_kind"]) == ("Notebook", "my-nb", "v1", N)
+
+
+def test_kserve_label_shortcut_wins_over_owner_refs(cluster):
+    d, ns = cluster
+    r = H.find_root(d, {"name": "llm-predictor-0", "namespace": ns,
+                        "labels": {"serving.kserve.io/inferenceservice": "llm"},
+                        "ownerReferences": [_owner("ReplicaSet", "web-5d9")]})
+    assert (r["kind"], r["name"], r["calls"]) == ("InferenceService", "llm", 1)
+    r = H.find_root(d, {"name": "x", "namespace": ns, "labels": {"serving.kserve.io/inferenceservice": "nope"}})
+    assert "not found" in r["error"]          # the GET error propagates (`?`, lib.rs:454)
+
+
+def test_missing_replicaset_is_swallowed_missing_deployment_propagates(cluster):
+    d, ns = cluster
+    # RS lookup fails -> `if let Ok(rs)` falls through to the next owner ref (lib.rs:465)
+    r = H.find_root(d, {"name": "p", "namespace": ns,
+                        "ownerReferences": [_owner("ReplicaSet", "nope"), _owner("StatefulSet", "db")]})
+    assert (r["kind"], r["name"]) == ("StatefulSet", "db")
+    # RS found, its Deployment is gone -> error propagates (lib.rs:472)
+    r = H.find_root(d, {"name": "p", "namespace": ns, "ownerReferences": [_owner("ReplicaSet", "dangling-rs")]})
+    assert "error" in r and "gone" in r["error"]
+
+
+# ---------------------------------------------------------------------------------------------
+# ingest of the matrix wire format
+# ---------------------------------------------------------------------------------------------
+def series(labels, samples):
+    return {"metric": labels, "values": [[t, str(v)] for t, v in samples]}
+
+
+def resp(*ss):
+    return {"status": "success", "data": {"resultType": "matrix", "result": list(ss)}}
+
+
+BASE = {"Hostname": "node1", "modelName": "NVIDIA A100", "UUID": "GPU-x"}
+
+
+def lab(pod, gpu, ns="ml", ctr="main", exported=True, **kw):
+    d = dict(BASE, gpu=str(gpu), **kw)
+    if exported:
+        d.update(exported_pod=pod, exported_namespace=ns, exported_container=ctr)
+    else:
+        d.update(pod=pod, namespace=ns, container=ctr)
+    return d
+
+
+def test_ingest_layout_and_label_precedence():
+    t_end = 1_700_000_060
+    u = resp(series(lab("a", 0), [(t_end - 50, 0), (t_end - 40, 0), (t_end, 7)]),
+             series(lab("a", 1), [(t_end - 10, 0)]),
+             series(lab("b", 0, exported=False, node_type="DGX"), [(t_end - 20, "NaN"), (t_end - 10, 3.5)]),
+             # exported_* wins over the bare label (lib.rs:158-175)
+             series(dict(lab("c", 0), pod="prometheus-exporter", namespace="monitoring"), [(t_end, 0)]),
+             # no pod label at all / empty pod label: not part of the selection (j2:11)
+             series({"Hostname": "n", "gpu": "0", "modelName": "m"}, [(t_end, 0)]),
+             series(lab("", 0), [(t_end, 0)]))
+    util, _, meta = H.ingest(u, duration_min=1, step=10, t_end=t_end)
+    assert util.shape == (3, 2, 6)
+    pods = meta["pods"]
+    assert [(p["name"], p["namespace"]) for p in pods] == [("a", "ml"), ("b", "ml"), ("c", "ml")]
+    assert pods[1]["slots"][0]["node_type"] == "DGX" and pods[0]["slots"][0]["node_type"] == "unknown"
+    assert meta["series_skipped"] == 2
+    nan = np.nan
+    np.testing.assert_array_equal(util[0, 0], np.array([0, 0, nan, nan, nan, 7], np.float32))
+    np.testing.assert_array_equal(util[0, 1], np.array([nan, nan, nan, nan, 0, nan], np.float32))
+    np.testing.assert_array_equal(util[1, 0], np.array([nan, nan, nan, nan, 3.5, nan], np.float32))
+    assert np.isnan(util[1, 1]).all()                        # pod b has one GPU: second slot absent
+
+
+def test_ingest_window_edges_duplicates_and_specials():
+    t_end = 1000
+    u = resp(series(lab("a", 0), [(t_end - 60, 9), (t_end - 59, 5), (t_end, "+Inf")]),   # -60 is outside (t-N, t]
+             series(dict(lab("a", 0), UUID="GPU-dup"), [(t_end - 59, 8), (t_end - 1, 1e-60)]),  # same group
+             series(lab("a", 0, ctr="sidecar"), [(t_end, 0)]))                           # other group
+    util, _, meta = H.ingest(u, duration_min=1, step=1, t_end=t_end)
+    assert util.shape == (1, 2, 60)
+    assert meta["samples_out_of_window"] == 1 and meta["duplicates_merged"] == 1
+    assert util[0, 0, 0] == 8 and np.isinf(util[0, 0, 59])          # per-step max of the duplicates
+    assert util[0, 0, 58] > 0 and meta["tiny_values_clamped"] == 1  # 1e-60 stays non-zero in f32
+    assert util[0, 1, 59] == 0
+
+
+def test_ingest_prof_shadows_util_and_power_plane():
+    t_end = 500
+    prof = resp(series(lab("a", 0), [(t_end, 0.25)]))
+    u = resp(series(lab("a", 0), [(t_end, 99)]), series(lab("a", 1), [(t_end, 0)]))
+    pw = resp(series({k: v for k, v in lab("a", 1).items() if k != "modelName"}, [(t_end - 1, 180), (t_end, 60)]))
+    util, power, meta = H.ingest(u, prof, pw, duration_min=1, step=1, t_end=t_end)
+    assert util[0, 0, 59] == np.float32(0.25) and meta["pods"][0]["slots"][0]["from_prof"]   # `A or B` (j2:10-20)
+    assert util[0, 1, 59] == 0 and not meta["pods"][0]["slots"][1]["from_prof"]
+    assert power.shape == util.shape and np.nanmax(power[0]) == 180
+
+
+def test_ingest_rejects_non_matrix():
+    with pytest.raises(RuntimeError, match="expected matrix"):
+        H.ingest({"status": "success", "data": {"resultType": "vector", "result": []}})
+    with pytest.raises(RuntimeError, match="status"):
+        H.ingest({"status": "error", "error": "query timed out"})
+
+
+def test_ingested_window_feeds_the_oracle(oracle_np):
+    """wire format -> tensor -> decision: the verdicts the PromQL would have produced"""
+    t_end = 10_000
+    ts = list(range(t_end - 59, t_end + 1))
+    u = resp(series(lab("idle-pod", 0), [(t, 0) for t in ts]),
+             series(lab("busy-pod", 0), [(t, 40 if t % 7 == 0 else 0) for t in ts]),
+             series(lab("two-gpu", 0), [(t, 90) for t in ts]),
+             series(lab("two-gpu", 1), [(t, 0) for t in ts[30:]]),     # young series, leading gap
+             series(lab("hot-idle", 0), [(t, 0) for t in ts]))
+    pw = resp(series(lab("hot-idle", 0), [(t, 200) for t in ts]), series(lab("idle-pod", 0), [(t, 55) for t in ts]))
+    util, power, meta = H.ingest(u, None, pw, duration_min=1, step=1, t_end=t_end)
+    names = [p["name"] for p in meta["pods"]]
+    r = oracle_np.decide(util, power, power_threshold=150.0)
+    verdict = dict(zip(names, r["candidate"]))
+    assert verdict == {"idle-pod": True, "busy-pod": False, "two-gpu": True, "hot-idle": False}
