@@ -107,19 +107,21 @@ class ClockSampler:
 # reference arm: the CPU restatement on the box's host cores
 # ---------------------------------------------------------------------------------------------
 def cpu_pass_factory(n_threads):
-    """returns (run_one_pass(), samples_per_pass, description, bits) over the C2 window on the host"""
+    """returns run(step_index, pods) over ROTATE distinct C2 windows held in host RAM (1.15 GB in total,
+    like the GPU arm, so that no arm is timed out of a last-level cache)"""
     import numpy as np
     from oracle import oracle_c
     lib = oracle_c.load()
-    u = oracle_c.synth_fill(SEED, 0, 0, PODS, GPUS, SAMPLES)
-    e = oracle_c.synth_eligible(SEED, 0, PODS)
+    wins = [(oracle_c.synth_fill(SEED + 16 * i, 0, 0, PODS, GPUS, SAMPLES),
+             oracle_c.synth_eligible(SEED + 16 * i, 0, PODS)) for i in range(ROTATE)]
     W = (PODS + 31) // 32
     dbits = np.zeros(W, np.uint32)
     cbits = np.zeros(W, np.uint32)
     counts = np.zeros(3, np.uint64)
 
-    def run(pods=PODS):
-        rc = lib.gpo_decide_mt(n_threads, u.ctypes.data, None, e.ctypes.data, None, 0, pods, GPUS,
+    def run(i=0, pods=PODS, threads=n_threads):
+        u, e = wins[i % ROTATE]
+        rc = lib.gpo_decide_mt(threads, u.ctypes.data, None, e.ctypes.data, None, 0, pods, GPUS,
                                SAMPLES, 0, 0.0, dbits.ctypes.data, cbits.ctypes.data, None,
                                counts.ctypes.data)
         assert rc == 0
@@ -133,24 +135,25 @@ def run_reference(args):
     from oracle import oracle_c
     n_threads = oracle_c.hardware_threads()
     run, dbits, counts = cpu_pass_factory(n_threads)
+    run(0)
     t0 = time.perf_counter()
-    run()
+    run(1)
     one = time.perf_counter() - t0
     # bound the whole run to ~150 s: shrink the per-step sample if the full window is too slow
     pods = PODS
     budget = 150.0
     if one * (args.steps + args.warmup) > budget:
         pods = max(32, int(PODS * budget / (one * (args.steps + args.warmup))) // 32 * 32)
-    for _ in range(args.warmup):
-        run(pods)
+    for i in range(args.warmup):
+        run(i, pods)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run(pods)
+    for i in range(args.steps):
+        run(i, pods)
     dt = time.perf_counter() - t0
     samples = pods * GPUS * SAMPLES
     value = samples * args.steps / dt
     sample_desc = (f"{pods} of {PODS} pods x {GPUS} x {SAMPLES} per step ({samples * 4 / 1e6:.0f} MB), "
-                   f"window resident in host RAM, {n_threads} POSIX threads over contiguous pod ranges")
+                   f"{ROTATE} windows rotated in host RAM, {n_threads} POSIX threads over contiguous pod ranges")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "pod_decisions_per_sec": pods * args.steps / dt,
@@ -168,12 +171,12 @@ def run_reference(args):
     return 0
 
 
-def workload_config(world, kernel):
+def workload_config(world, kernel, collective="fused NVLink peer stores in the decision kernel"):
     c = {"workload": f"C2 (BASELINE configs[1]): {PODS} pods x {GPUS} GPUs x {SAMPLES} samples "
                      f"(30 min @ 1 s) per B200, util plane + age/phase gate",
          "pods_per_gpu": PODS, "gpus_per_pod": GPUS, "samples_per_series": SAMPLES,
          "bytes_per_step_per_gpu": 4 * PODS * GPUS * SAMPLES, "seed": hex(SEED),
-         "sharding": f"pod axis, {world} rank(s), one ncclAllGather of the packed bitmap per step"
+         "sharding": f"pod axis, {world} rank(s), one exchange of the packed bitmap per step ({collective})"
                      if world > 1 else "single GPU",
          "l2": f"{ROTATE} distinct 288 MB windows rotated (1.15 GB vs 126 MB L2), no flush needed"}
     if kernel:
@@ -214,10 +217,14 @@ def run_cuda(args):
     sh = g.shard_pods(PODS * world, rank, world) if world > 1 else g.Shard(0, 1, PODS, PODS, 0, PODS)
     P, G, T = sh.pods_per_rank, GPUS, SAMPLES
     eng = g.IdleEngine(device=local, max_pods=P, max_gpus=G, max_samples=T, kernel=args.kernel)
-    if world > 1:
+    if world > 1 and args.collective == "nccl":
         uid = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0], rank, world)
+    elif world > 1:   # fused: the decision kernel itself pushes the words to the peers over NVLink
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.p2p_init(rank, world, P))
+        eng.p2p_attach(handles)
 
     # ---- synthetic windows, generated on the owning GPU (no scatter) --------------------------
     wins = []
@@ -235,11 +242,12 @@ def run_cuda(args):
         return eng.decide_ptr(u, P, G, T, dbits, eligible=e, blocking=blocking)
 
     # ---- parity of the benchmarked workload against the oracle (outside the timed region) ----
+    # every rank takes the step (with a communicator it contains the allgather); rank 0 checks its shard
     parity = None
+    r = step(0, blocking=True)
     if rank == 0:
         from oracle import oracle_c
         exp = oracle_c.decide_synth(SEED, sh.pod_begin, sh.pods_real, G, T, use_elig=True)
-        r = step(0, blocking=True)
         got = dbits.cpu().numpy().view(np.uint32)[: (sh.pods_real + 31) // 32]
         ok = np.array_equal(got, exp["decision_bits"]) and r.n_decisions == exp["n_decisions"]
         parity = "PASS" if ok else "FAIL"
@@ -313,14 +321,16 @@ def run_cuda(args):
             "pod_decisions_per_sec": real_pods_total / (ms_per_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world, args.kernel),
+            "data": "synthetic",
+            "config": workload_config(world, args.kernel, "fused NVLink peer stores in the decision kernel"
+                                      if args.collective == "p2p" else "ncclAllGather"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
                          "peak_source": peak_src,
                          "kernel": "gpr::k_reduce_%s (one launch per step%s)" % (
-                             args.kernel if args.kernel != "auto" else "ldg",
-                             "; step time also contains the bitmap allgather" if world > 1 else ""),
+                             args.kernel if args.kernel != "auto" else "tma",
+                             "; step time contains the bitmap exchange" if world > 1 else ""),
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "e2e": {"value": samples_per_step / e2e_s_per_step, "unit": UNIT,
                     "pod_decisions_per_sec": real_pods_total / e2e_s_per_step,
@@ -347,24 +357,23 @@ def cpu_baseline():
     from oracle import oracle_c
     n_threads = oracle_c.hardware_threads()
     run, _, _ = cpu_pass_factory(n_threads)
-    run()
+    run(0)
     t0 = time.perf_counter()
-    run()
+    run(1)
     one = time.perf_counter() - t0
-    passes = max(3, min(400, int(12.0 / max(one, 1e-4))))
+    passes = max(4, min(2000, int(12.0 / max(one, 1e-4))))
     t0 = time.perf_counter()
-    for _ in range(passes):
-        run()
+    for i in range(passes):
+        run(i)
     dt = time.perf_counter() - t0
-    run1, _, _ = cpu_pass_factory(1)
     t1 = time.perf_counter()
-    run1()
+    run(2, PODS, 1)
     one_thread = time.perf_counter() - t1
     samples = PODS * GPUS * SAMPLES
     return {"value": samples * passes / dt, "unit": UNIT, "cores": n_threads, "kind": "port",
             "pod_decisions_per_sec": PODS * passes / dt,
             "single_thread_value": samples / one_thread,
-            "sample": f"{passes} passes over the full C2 window ({samples * 4 / 1e6:.0f} MB in host RAM), "
+            "sample": f"{passes} passes over {ROTATE} rotated C2 windows ({samples * 4 / 1e6:.0f} MB each, host RAM), "
                       f"{n_threads} POSIX threads; oracle/gpr_oracle.c -O3 -march=x86-64-v3, scalar f64"}
 
 
@@ -377,6 +386,8 @@ def main():
     ap.add_argument("--kernel", default=os.environ.get("GPR_BENCH_KERNEL", "auto"),
                     choices=["auto", "ldg", "tma"])
     ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: bitmap exchange fused into the kernel over peer memory, or one ncclAllGather")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:

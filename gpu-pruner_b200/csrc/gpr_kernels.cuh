@@ -30,6 +30,8 @@ namespace gpr {
 // ------------------------------------------------------------------------------------------
 // parameters
 // ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;  // one NVSwitch box
+
 struct Segment {
   const float* base;   // first row of this segment (device)
   uint32_t* mask;      // per-pod bitmask, bit g set when series (pod, g) is flagged:
@@ -54,6 +56,19 @@ struct FoldParams {
   unsigned long long* done;   // completed in-kernel folds on this scratch set (monotonic)
   unsigned long long need;    // folds that must have completed before this launch may publish
   uint32_t P, G;
+  // ---- fused bitmap exchange over NVLink peer memory (world > 1, gpr_p2p_*) -------------------
+  // Instead of a separate collective launch, the folding CTA stores this rank's packed words
+  // straight into every peer's gather buffer, raises a per-source step flag on each peer with
+  // release.sys semantics, waits for the peers' flags, and copies the assembled global bitmap to
+  // the caller's buffers.  peer_gather[r] / peer_flag[r] are peer-mapped (CUDA IPC) addresses.
+  int world, rank;                       // world <= 1: no exchange
+  uint32_t rank_stride;                  // words per rank slot in a gather buffer (2 * W_max)
+  uint32_t* peer_gather[kMaxPeers];      // gather buffer (this call's parity) on rank r
+  unsigned long long* peer_flag[kMaxPeers];  // &flags[my_rank] on rank r
+  const unsigned long long* my_flags;    // local flags[world], written by the peers
+  unsigned long long step;               // exchange sequence number of this call (same on all ranks)
+  uint32_t* out_dbits;                   // caller's global bitmaps on this device (may be null)
+  uint32_t* out_cbits;
 };
 
 struct ReduceParams {
@@ -108,6 +123,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ float nan_f() { return __int_as_float(0x7fffffff); }
@@ -195,6 +219,36 @@ __device__ __forceinline__ void block_counts(unsigned long long* sh3, unsigned l
   }
 }
 
+// The one exchange of the multi-GPU path, fused into the folding CTA.  f.dbits / f.cbits point at
+// this rank's slot of the LOCAL gather buffer; the same 2*W words are pushed to every peer.
+__device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n_words) {
+  __syncthreads();  // the fold's word stores are visible to the whole CTA
+  const uint32_t* mine = f.peer_gather[f.rank] + (size_t)f.rank * f.rank_stride;
+  const uint32_t span = 2u * n_words;  // [decision | candidate], candidate slot always present
+  for (uint32_t i = threadIdx.x; i < span * (uint32_t)f.world; i += blockDim.x) {
+    const uint32_t r = i / span, w = i - r * span;
+    if ((int)r == f.rank) continue;
+    // word w of the decision half or of the candidate half (which starts at n_words)
+    f.peer_gather[r][(size_t)f.rank * f.rank_stride + w] = mine[w];   // NVLink peer store
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < f.world && (int)threadIdx.x != f.rank) {
+    st_release_sys_u64(f.peer_flag[threadIdx.x], f.step);             // "rank's words of step k are there"
+    while (ld_acquire_sys_u64(f.my_flags + threadIdx.x) < f.step) __nanosleep(128);
+  }
+  __syncthreads();
+  // assemble the caller's rank-major global bitmaps from the local gather buffer
+  if (f.out_dbits) {
+    const uint32_t* g = f.peer_gather[f.rank];
+    for (uint32_t i = threadIdx.x; i < n_words * (uint32_t)f.world; i += blockDim.x) {
+      const uint32_t r = i / n_words, w = i - r * n_words;
+      f.out_dbits[i] = __ldcg(g + (size_t)r * f.rank_stride + w);
+      if (f.out_cbits) f.out_cbits[i] = __ldcg(g + (size_t)r * f.rank_stride + n_words + w);
+    }
+  }
+}
+
 // Ticket fold at the end of a reduce grid: every CTA publishes its flags, the last one to
 // arrive packs the whole bitmap.  The ticket resets itself so the buffer is reusable by the
 // next launch on the stream without a memset.
@@ -219,6 +273,7 @@ __device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
   unsigned long long a = 0, b = 0, c = 0;
   fold_words<8>(f, warp, n_words, n_warps, lane, a, b, c);
   block_counts(s_cnt, a, b, c, lane);
+  if (f.world > 1) exchange_bitmaps(f, n_words);
   __threadfence();  // mask clears and outputs before the completion signal
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -230,7 +285,8 @@ __device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
   }
 }
 
-// Standalone fold (chunked host-window path): counts must be zeroed by the caller.
+// Standalone fold (chunked host-window path): counts must be zeroed by the caller.  With a fused
+// exchange the host launches a single CTA, which then also pushes / gathers the bitmap.
 __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   __shared__ unsigned long long s_cnt[3];
   if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
@@ -240,8 +296,9 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   const uint32_t gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
   const uint32_t n_words = (f.P + 31u) / 32u;
   unsigned long long a = 0, b = 0, c = 0;
-  fold_words<1>(f, gw, n_words, gridDim.x * warps_per_cta, lane, a, b, c);
+  fold_words<4>(f, gw, n_words, gridDim.x * warps_per_cta, lane, a, b, c);
   block_counts(s_cnt, a, b, c, lane);
+  if (f.world > 1 && gridDim.x == 1) exchange_bitmaps(f, n_words);
   __syncthreads();
   if (threadIdx.x == 0 && (s_cnt[0] | s_cnt[1] | s_cnt[2])) {
     atomicAdd(&f.counts[0], s_cnt[0]);

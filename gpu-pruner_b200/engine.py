@@ -215,6 +215,17 @@ class IdleEngine:
         buf = C.create_string_buffer(unique_id, ffi.GPR_UNIQUE_ID_BYTES)
         self._check(self._lib.gpr_comm_init(self._h, buf, rank, world))
 
+    def p2p_init(self, rank: int, world: int, max_pods_per_rank: int) -> bytes:
+        """allocate this rank's exchange block; returns the 64-byte CUDA IPC handle to publish"""
+        buf = C.create_string_buffer(ffi.GPR_P2P_HANDLE_BYTES)
+        self._check(self._lib.gpr_p2p_init(self._h, rank, world, max_pods_per_rank, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """handles: the world handles in rank order (bytes each); enables the fused exchange"""
+        blob = b"".join(handles)
+        self._check(self._lib.gpr_p2p_attach(self._h, C.create_string_buffer(blob, len(blob))))
+
     def comm_destroy(self):
         self._check(self._lib.gpr_comm_destroy(self._h))
 

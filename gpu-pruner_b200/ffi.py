@@ -19,6 +19,7 @@ GPR_MEM_HOST, GPR_MEM_DEVICE = 0, 1
 GPR_KERNEL_AUTO, GPR_KERNEL_LDG, GPR_KERNEL_TMA = 0, 1, 2
 GPR_F_POWER_PLANE = 0x1
 GPR_UNIQUE_ID_BYTES = 128
+GPR_P2P_HANDLE_BYTES = 64
 
 
 class gpr_config(C.Structure):
@@ -76,6 +77,8 @@ PROTOTYPES = {
     "gpr_comm_unique_id": (C.c_int, [_P]),
     "gpr_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "gpr_comm_destroy": (C.c_int, [_P]),
+    "gpr_p2p_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, _P]),
+    "gpr_p2p_attach": (C.c_int, [_P, _P]),
     "gpr_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "gpr_host_free": (C.c_int, [_P, _P]),
     "gpr_device_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),

@@ -189,6 +189,17 @@ GPR_API int gpr_comm_unique_id(void *id128);                       /* rank 0; sh
 GPR_API int gpr_comm_init(gpr_ctx *ctx, const void *id128, int rank, int world);
 GPR_API int gpr_comm_destroy(gpr_ctx *ctx);
 
+/* ---- multi-GPU, fused: the decision kernel itself exchanges the bitmap over NVLink peer memory.
+ * Each rank: gpr_p2p_init -> ship the 64-byte handle to every rank (any side channel) ->
+ * gpr_p2p_attach(all handles, rank-major).  Afterwards gpr_decide behaves as with a communicator
+ * (global rank-major bitmaps, n_pods a multiple of 32 and <= max_pods_per_rank, all ranks calling
+ * in lock-step) but launches no collective: the folding CTA stores this rank's words into every
+ * peer's buffer, signals, waits for the peers and assembles the result.  At most 8 ranks.        */
+#define GPR_P2P_HANDLE_BYTES 64
+GPR_API int gpr_p2p_init(gpr_ctx *ctx, int rank, int world, uint32_t max_pods_per_rank,
+                         void *handle64);
+GPR_API int gpr_p2p_attach(gpr_ctx *ctx, const void *handles /* world * 64 bytes */);
+
 /* ---- memory helpers ------------------------------------------------------------------ */
 GPR_API int gpr_host_alloc(gpr_ctx *ctx, size_t bytes, void **out); /* pinned host memory         */
 GPR_API int gpr_host_free(gpr_ctx *ctx, void *p);

@@ -143,21 +143,75 @@ static uint32_t split32(uint32_t P, int n, int i) {
   return (uint32_t)(p > P ? P : p);
 }
 
-static int run_jobs(job_t *jobs, int n, void *(*fn)(void *)) {
-  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n);
-  if (!th) return -1;
-  int started = 0, rc = 0;
-  for (int i = 1; i < n; ++i) {
-    if (pthread_create(&th[i], NULL, fn, &jobs[i]) != 0) {
-      rc = -1;
-      break;
+/* Persistent worker pool: the timed CPU baseline must not pay 128 pthread_create calls per pass.
+ * Worker i (1..n-1) runs job i of the current batch; the caller runs job 0. */
+static struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv_start, cv_done;
+  pthread_t *th;
+  int *ids;
+  int n;               /* workers alive (excluding the caller) */
+  unsigned long gen;   /* batch generation */
+  int n_jobs, pending;
+  void *(*fn)(void *);
+  job_t *jobs;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+            NULL, NULL, 0, 0, 0, 0, NULL, NULL};
+
+static void *pool_worker(void *arg) {
+  const int id = *(int *)arg; /* 1-based */
+  unsigned long seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
+  for (;;) {
+    while (g_pool.gen == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
+    seen = g_pool.gen;
+    if (id < g_pool.n_jobs) {
+      job_t *job = &g_pool.jobs[id];
+      void *(*fn)(void *) = g_pool.fn;
+      pthread_mutex_unlock(&g_pool.mu);
+      fn(job);
+      pthread_mutex_lock(&g_pool.mu);
+      if (--g_pool.pending == 0) pthread_cond_signal(&g_pool.cv_done);
     }
-    started = i;
   }
-  if (rc == 0) fn(&jobs[0]);
-  for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
-  free(th);
-  return rc;
+  return NULL;
+}
+
+static int pool_grow(int want_workers) {
+  if (want_workers <= g_pool.n) return 0;
+  pthread_t *th = (pthread_t *)realloc(g_pool.th, sizeof(pthread_t) * (size_t)want_workers);
+  int *ids = (int *)malloc(sizeof(int) * (size_t)want_workers); /* stable storage per growth step */
+  if (!th || !ids) return -1;
+  g_pool.th = th;
+  for (int i = g_pool.n; i < want_workers; ++i) {
+    ids[i] = i + 1;
+    if (pthread_create(&g_pool.th[i], NULL, pool_worker, &ids[i]) != 0) return -1;
+    pthread_detach(g_pool.th[i]);
+    g_pool.n = i + 1;
+  }
+  g_pool.ids = ids;
+  return 0;
+}
+
+static int run_jobs(job_t *jobs, int n, void *(*fn)(void *)) {
+  if (n <= 1) {
+    fn(&jobs[0]);
+    return 0;
+  }
+  pthread_mutex_lock(&g_pool.mu);
+  if (pool_grow(n - 1) != 0) {
+    pthread_mutex_unlock(&g_pool.mu);
+    return -1;
+  }
+  g_pool.jobs = jobs, g_pool.fn = fn, g_pool.n_jobs = n, g_pool.pending = n - 1;
+  ++g_pool.gen;
+  pthread_cond_broadcast(&g_pool.cv_start);
+  pthread_mutex_unlock(&g_pool.mu);
+  fn(&jobs[0]);
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.pending > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+  return 0;
 }
 
 int gpo_decide_mt(int n_threads, const float *util, const float *power, const uint8_t *eligible,

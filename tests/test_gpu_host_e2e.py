@@ -118,14 +118,14 @@ def test_dry_run_reports_the_same_roots_and_sends_nothing(world):
         "Dry-run: Would have sent [StatefulSet] team-a:db for scaledown",
         "Dry-run: Would have sent [Notebook] team-a:my-nb for scaledown",
         "Dry-run: Would have sent [InferenceService] team-a:llm for scaledown"])
-    # 12 idle series (hot-0 is idle too: no power clause without --power-threshold) across 10 unique pods
-    assert "Query returned 12 series across 10 unique pods" in msgs
+    # 11 idle series (hot-0 is idle too: no power clause without --power-threshold) across 10 unique pods
+    assert "Query returned 11 series across 10 unique pods" in msgs
     assert any("Skipping team-a:young-0, created after the lookback window" in m for m in msgs)
     assert any("Skipping team-a:pending-0, it's still pending" in m for m in msgs)
     assert any("Skipping team-a:gone-0, pod no longer exists" in m for m in msgs)
     assert any("Skipping team-a:orphan-0, no scalable root object" in m for m in msgs)
     cnt = {k: v for l in logs for k, v in l["fields"].items() if k.startswith(("counter.", "monotonic_counter."))}
-    assert cnt["counter.query_returned_candidates"] == "12"
+    assert cnt["counter.query_returned_candidates"] == "11"
     assert cnt["counter.query_returned_shutdown_events"] == "4"
     assert cnt["monotonic_counter.query_successes"] == "1"
 
@@ -157,8 +157,8 @@ def test_enabled_resources_filter_and_power_veto(world):
     assert kinds == ["Deployment", "Notebook"]
     msgs = _msgs(logs)
     assert any('Skipping resource type "StatefulSet" because it is not enabled' in m for m in msgs)
-    # hot-0 draws 300 W >= 150 W: vetoed pod-wide, so 11 series / 9 pods survive the query
-    assert "Query returned 11 series across 9 unique pods" in msgs
+    # hot-0 draws 300 W >= 150 W: vetoed pod-wide, so 10 series / 9 pods survive the query
+    assert "Query returned 10 series across 9 unique pods" in msgs
 
 
 def test_query_failure_is_counted_not_fatal(world, tmp_path):

@@ -19,19 +19,24 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _rank(rank, world, port, total, G, T, seed, out_dir):
+def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
     import gpu_pruner_b200 as g
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    eng = g.IdleEngine(device=rank)
-    uid = [eng.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    eng.comm_init(uid[0], rank, world)
+    eng = g.IdleEngine(device=rank, max_pods=20000, max_gpus=G, max_samples=T)
     sh = g.shard_pods(total, rank, world)
     P = sh.pods_per_rank
+    if mode == "nccl":      # one ncclAllGather of the packed words per decision
+        uid = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
+    else:                   # fused: the folding CTA writes the words into every peer over NVLink
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.p2p_init(rank, world, P))
+        eng.p2p_attach(handles)
     dev = f"cuda:{rank}"
     u = torch.full((P, G, T), float("nan"), dtype=torch.float32, device=dev)
     eng.synth_fill(seed, 0, u, sh.pod_begin, sh.pods_real, G, T)
@@ -40,8 +45,14 @@ def _rank(rank, world, port, total, G, T, seed, out_dir):
     db = torch.zeros(world * P // 32, dtype=torch.int32, device=dev)
     cb = torch.zeros(world * P // 32, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
-    for it in range(3):   # repeated calls reuse the communicator
+    for it in range(3):   # repeated calls reuse the communicator / exchange block
         r = eng.decide_ptr(u, P, G, T, db, eligible=e, candidate_bits=cb)
+    # back-to-back async decisions (overlapped launches) must still exchange step by step
+    db2 = torch.zeros_like(db)
+    for it in range(8):
+        eng.decide_ptr(u, P, G, T, db2, eligible=e, blocking=False)
+    eng.sync()
+    assert torch.equal(db, db2)
     np.save(os.path.join(out_dir, f"d_{rank}.npy"), db.cpu().numpy().view(np.uint32))
     np.save(os.path.join(out_dir, f"c_{rank}.npy"), cb.cpu().numpy().view(np.uint32))
     np.save(os.path.join(out_dir, f"n_{rank}.npy"), np.array([r.n_series, r.n_candidates, r.n_decisions]))
@@ -49,20 +60,27 @@ def _rank(rank, world, port, total, G, T, seed, out_dir):
     hd = np.zeros(world * P // 32, np.uint32)
     eng.decide_ptr(u, P, G, T, hd, eligible=e, out_kind=0)
     np.save(os.path.join(out_dir, f"h_{rank}.npy"), hd)
+    # host window (chunked H2D path) through the same exchange
+    if P <= 20000:
+        hw = np.zeros(world * P // 32, np.uint32)
+        eng.decide_ptr(u.cpu().numpy(), P, G, T, hw, eligible=e.cpu().numpy(), in_kind=0, out_kind=0)
+        assert np.array_equal(hw, hd)
     dist.barrier()
-    eng.comm_destroy()
+    if mode == "nccl":
+        eng.comm_destroy()
     eng.close()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
 @pytest.mark.parametrize("total", [5000, 64 * 1000 + 7])
-def test_sharded_decision_allgather(total, tmp_path, oracle_c):
+def test_sharded_decision_allgather(total, mode, tmp_path, oracle_c):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 8)
     G, T, seed = 4, 600, 0x5EED0004
-    mp.spawn(_rank, args=(world, _free_port(), total, G, T, seed, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_rank, args=(world, _free_port(), total, G, T, seed, str(tmp_path), mode), nprocs=world, join=True)
     ref = oracle_c.decide_synth(seed, 0, total, G, T, use_elig=True)
     W = (total + 31) // 32
     n = np.zeros(3, np.int64)
