@@ -118,19 +118,19 @@ struct gpr_ctx {
   uint32_t* d_masks[2] = {nullptr, nullptr};  // each [idle P | veto P], all-zero between uses
   size_t masks_cap[2] = {0, 0};
   bool masks_dirty = false;     // a failed call may have left bits behind
-  unsigned int* d_tickets = nullptr;          // [2]
-  unsigned long long* d_done = nullptr;       // [2] completed in-kernel folds per scratch set
-  unsigned long long uses[2] = {0, 0};        // in-kernel-fold launches issued per scratch set
+  unsigned int* d_tickets = nullptr;          // [2] fold-grid tickets
+  unsigned long long* d_acc = nullptr;        // [2][3] fold-grid count accumulators
+  unsigned long long* d_done = nullptr;       // [2] completed folds per scratch set
+  unsigned long long uses[2] = {0, 0};        // folds issued per scratch set
   unsigned parity = 0;
   bool pdl_enabled = true;      // GPR_PDL=0 disables programmatic dependent launch
-  bool last_was_reduce = false; // the newest op on the stream is a self-folding reduce kernel
+  bool last_was_reduce = false; // the newest op on the stream is one of our fold kernels
   uint32_t* d_bits = nullptr;  // [dbits W | cbits W]
   size_t bits_cap = 0;
   uint32_t* d_gather = nullptr;  // [world][2W]
   size_t gather_cap = 0;
   float* d_smax = nullptr;
   size_t smax_cap = 0;
-  unsigned long long* d_counts = nullptr;
   unsigned long long* h_counts = nullptr;  // pinned [kSlots][3]
   std::vector<Pending> pending;
 
@@ -265,7 +265,7 @@ cudaError_t launch_tma(gpr_ctx* ctx, const gpr::ReduceParams& rp, uint32_t grid,
 
 // launch one reduce pass over the rows described by rp
 int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok, bool pdl) {
-  if (rp.total_rows == 0 && !rp.fold_in_kernel) return GPR_OK;
+  if (rp.total_rows == 0) return GPR_OK;
   // AUTO = the TMA pipeline (measured winner on B200 at C2 and C3, profiles/README.md); rows that are
   // not 16-byte aligned or have T % 4 != 0 cannot be bulk-copied and take the LDG kernel
   int variant = ctx->variant == GPR_KERNEL_AUTO ? GPR_KERNEL_TMA : ctx->variant;
@@ -364,6 +364,11 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   int rc;
   const unsigned sset = ctx->parity;  // scratch set of this call; successive calls alternate
   ctx->parity ^= 1u;
+  if (ctx->masks_dirty) {  // a failed launch may also have left ticket / accumulators behind
+    CU(cudaMemsetAsync(ctx->d_tickets, 0, 2 * sizeof(unsigned int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_acc, 0, 6 * sizeof(unsigned long long), ctx->stream));
+    ctx->last_was_reduce = false;
+  }
   for (int k = 0; k < 2; ++k) {
     const size_t cap_before = ctx->masks_cap[k];
     if ((rc = grow(ctx, &ctx->d_masks[k], &ctx->masks_cap[k], (size_t)2 * P + 16)) != GPR_OK) return rc;
@@ -436,10 +441,13 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   // pinned (device-mapped, UVA) host slot, so no copy operation separates back-to-back steps
   const int slot = (int)ctx->pending.size();
   unsigned long long* h_slot = ctx->h_counts + (size_t)slot * 3;
-  fp.counts = host_in ? ctx->d_counts : h_slot;
+  fp.counts = h_slot;
+  fp.acc = ctx->d_acc + 3 * sset;
   fp.ticket = ctx->d_tickets + sset;
   fp.done = ctx->d_done + sset;
-  fp.need = host_in ? 0ull : ctx->uses[sset];
+  fp.need = ctx->uses[sset];
+  fp.prev_done = ctx->d_done + (sset ^ 1u);
+  fp.prev_need = ctx->uses[sset ^ 1u];
   fp.P = P;
   fp.G = G;
   fp.world = 1, fp.rank = 0;
@@ -461,7 +469,11 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   rp.T = T;
   rp.G = G;
   rp.thr = threshold_f32(win->power_threshold);
-  rp.fold = fp;
+  rp.done = fp.done;
+  rp.need = fp.need;
+  const bool can_pdl = ctx->pdl_enabled && ctx->own_stream;
+  // the fold grid: 32 bitmap words per CTA and round; a handful of CTAs even at millions of pods
+  const uint32_t fold_grid = std::max<uint32_t>(1u, std::min<uint32_t>((W + 31u) / 32u, 64u));
 
   if (!async) {
     CU(cudaEventRecord(ctx->ev_k0, ctx->stream));
@@ -469,20 +481,22 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   }
 
   if (!host_in) {
-    // ---- device-resident window: ONE launch, reduce + ticket fold -------------------------
+    // ---- device-resident window: one reduce launch + the PDL-chained fold -------------------
     rp.ld = ld;
     rp.seg[0] = gpr::Segment{util, masks, smax_dev, S, 0u};
     rp.seg[1] = gpr::Segment{power, masks + P, nullptr, use_power ? S : 0u, 1u};
     rp.total_rows = S + (use_power ? S : 0u);
-    rp.fold_in_kernel = 1;
     const bool tma_ok = (T % 4u) == 0 && (ld % 4u) == 0 && aligned16(util) &&
                         (!use_power || aligned16(power));
     if (P > 0) {
-      // Overlap with the previous decision only when that is provably safe: our own stream (no
-      // foreign producer kernels), the newest op on it is a self-folding reduce kernel, and this
-      // launch writes nothing before its fold except into its own scratch set.
-      const bool pdl = ctx->pdl_enabled && ctx->own_stream && ctx->last_was_reduce && !want_smax;
+      // The reduce grid may start while the previous decision's fold is still running, but only
+      // when that is provably safe: our own stream (no foreign producer kernels between), the
+      // newest op on it is one of our fold kernels, and this launch writes nothing but its own
+      // scratch set (series_max would go straight to the caller's buffer).
+      const bool pdl = can_pdl && ctx->last_was_reduce && !want_smax;
       if ((rc = launch_reduce(ctx, rp, tma_ok, pdl)) != GPR_OK) return rc;
+      CU(launch_ex(gpr::k_fold, fold_grid, 256, 0, ctx->stream, can_pdl, fp));
+      ctx->launches++;
       ctx->uses[sset]++;
       ctx->last_was_reduce = true;
     }
@@ -495,7 +509,6 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
     uint32_t chunk_pods = (uint32_t)std::max<size_t>(1, ctx->chunk_bytes / std::max<size_t>(pod_bytes, 1));
     uint32_t n_chunks = P ? (P + chunk_pods - 1) / chunk_pods : 0;
     rp.ld = T;  // staging is dense
-    rp.fold_in_kernel = 0;
     const bool tma_ok = (T % 4u) == 0;
     for (uint32_t c = 0; c < n_chunks; ++c) {
       const uint32_t p0 = c * chunk_pods, p1 = std::min(P, p0 + chunk_pods);
@@ -519,18 +532,13 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       rp.total_rows = (uint32_t)n_rows * (use_power ? 2u : 1u);
       if ((rc = launch_reduce(ctx, rp, tma_ok, false)) != GPR_OK) return rc;
     }
-    CU(cudaMemsetAsync(ctx->d_counts, 0, 3 * sizeof(unsigned long long), ctx->stream));
-    if (W > 0) {
-      const uint32_t warps_per_cta = 8;
-      uint32_t grid = std::min<uint32_t>((W + warps_per_cta - 1) / warps_per_cta,
-                                         (uint32_t)ctx->sm_count * 4u);
-      if (fused) grid = 1;  // the exchange needs the whole bitmap in one CTA; the fold is tiny
-      gpr::k_fold<<<grid, warps_per_cta * 32, 0, ctx->stream>>>(fp);
+    if (P > 0) {
+      CU(launch_ex(gpr::k_fold, fold_grid, 256, 0, ctx->stream, false, fp));
       ctx->launches++;
-      CU(cudaGetLastError());
+      ctx->uses[sset]++;
     }
   }
-  if (P == 0 && !host_in) h_slot[0] = h_slot[1] = h_slot[2] = 0;  // slot is not in flight
+  if (P == 0) h_slot[0] = h_slot[1] = h_slot[2] = 0;  // slot is not in flight
 
   // ---- the one collective: allgather of the packed bitmap over NVLink ----------------------
   if ((comm && !fused) || host_out || !async) ctx->last_was_reduce = false;  // something follows
@@ -568,9 +576,6 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   if (want_smax && host_out && S > 0)
     CU(cudaMemcpyAsync(res->series_max, ctx->d_smax, (size_t)S * 4u, cudaMemcpyDeviceToHost,
                        ctx->stream));
-  if (host_in)
-    CU(cudaMemcpyAsync(h_slot, ctx->d_counts, 3 * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, ctx->stream));
   ctx->pending.push_back(Pending{res, slot});
   res->kernel_ms = 0.0;
   return GPR_OK;
@@ -640,7 +645,7 @@ void gpr_destroy(gpr_ctx* ctx) {
   if (ctx->p2p_block) cudaFree(ctx->p2p_block);
   void* dev[] = {ctx->d_util_stage, ctx->d_power_stage, ctx->d_elig_stage, ctx->d_created_stage,
                  ctx->d_masks[0],   ctx->d_masks[1],    ctx->d_bits,       ctx->d_gather,
-                 ctx->d_smax,       ctx->d_counts,      ctx->d_tickets,    ctx->d_done,
+                 ctx->d_smax,       ctx->d_acc,         ctx->d_tickets,    ctx->d_done,
                  ctx->d_flush,      ctx->d_res_util,    ctx->d_res_power,  ctx->d_cols};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -707,10 +712,10 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     CU(cudaEventCreate(&c->ev_t1));
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (cudaEvent_t& ev : c->ev_chunk) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_counts), 3 * sizeof(unsigned long long)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_acc), 6 * sizeof(unsigned long long)));
     CU(cudaMalloc(reinterpret_cast<void**>(&c->d_tickets), 2 * sizeof(unsigned int)));
     CU(cudaMalloc(reinterpret_cast<void**>(&c->d_done), 2 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_counts, 0, 3 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_acc, 0, 6 * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_done, 0, 2 * sizeof(unsigned long long)));
     c->pdl_enabled = env_int("GPR_PDL", 1) != 0;

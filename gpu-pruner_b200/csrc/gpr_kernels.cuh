@@ -16,8 +16,12 @@
 //              k_reduce_ldg  128-bit ld.global.nc streaming loads, warp per row
 //              k_reduce_tma  cp.async.bulk (TMA, SASS UBLKCP) row chunks into warp-private,
 //                            mbarrier-guarded shared-memory rings
-//   fold   : flags -> per-pod verdict -> packed uint32 bitmaps + counts (touches S bytes, <0.1 %).
-//            Either the last CTA of the reduce grid (ticket) or a standalone kernel.
+//   fold   : per-pod masks -> verdict -> packed uint32 bitmaps + counts (touches 4 B per pod, <0.1 %),
+//            plus, on more than one GPU, the exchange of the packed words over NVLink peer memory.
+//            A small second kernel (k_fold) chained to the reduce kernel by programmatic dependent
+//            launch: it is resident before the reduce ends, folds the moment the reduce grid has
+//            completed, and never occupies a streaming CTA's SM slot, so the next decision's reduce
+//            kernel takes over the SMs while this one is still folding / exchanging.
 //
 // HBM-bound streaming max: ~1 FMNMX per 4 bytes, no tensor cores, no reuse.
 #pragma once
@@ -51,10 +55,15 @@ struct FoldParams {
   int64_t cutoff;
   uint32_t* dbits;            // [ceil(P/32)]
   uint32_t* cbits;            // [ceil(P/32)] or nullptr
-  unsigned long long* counts; // [3] n_series, n_candidates, n_decisions (overwritten)
-  unsigned int* ticket;       // self-resetting arrival counter (ticket mode)
-  unsigned long long* done;   // completed in-kernel folds on this scratch set (monotonic)
-  unsigned long long need;    // folds that must have completed before this launch may publish
+  unsigned long long* counts; // [3] n_series, n_candidates, n_decisions of this call (host-mapped slot
+                              //     or device memory); written once by the last fold CTA
+  unsigned long long* acc;    // [3] device accumulator of the fold grid, zero between calls
+  unsigned int* ticket;       // self-resetting arrival counter of the fold grid
+  unsigned long long* done;   // folds completed on this scratch set (monotonic)
+  unsigned long long need;    // value of *done required before this decision may touch the set
+  const unsigned long long* prev_done;  // the other scratch set's counter ...
+  unsigned long long prev_need;         // ... and the value it must have reached (previous decision
+                                        // folded) before this fold may write the caller's outputs
   uint32_t P, G;
   // ---- fused bitmap exchange over NVLink peer memory (world > 1, gpr_p2p_*) -------------------
   // Instead of a separate collective launch, the folding CTA stores this rank's packed words
@@ -78,8 +87,8 @@ struct ReduceParams {
   uint32_t G;         // rows per pod
   uint32_t total_rows;
   float thr;          // smallest f32 >= (double) power threshold
-  int fold_in_kernel; // 1: last CTA folds (single-launch path)
-  FoldParams fold;
+  const unsigned long long* done;  // scratch-set guard, see wait_scratch_free
+  unsigned long long need;
 };
 
 #ifdef GPR_TIMELINE
@@ -106,10 +115,13 @@ __device__ __forceinline__ void tl_mark(int slot) {
 #endif
 
 // ---- programmatic dependent launch (back-to-back decisions on the context's own stream) -------
-// A reduce kernel lets its successor start while it drains (launch_dependents at entry).  The
-// successor streams its input and publishes into the OTHER scratch set; before its first publish
-// it checks that the launch two back (same scratch set) has finished (`done` counter), and before
-// it writes outputs it waits for its predecessor's completion (griddepcontrol.wait).
+// Stream order of successive decisions: R0 F0 R1 F1 R2 ...  (R = reduce grid, F = fold grid).
+// Every kernel executes launch_dependents at entry, so its successor may become resident as soon
+// as SM resources allow: F_n sits in griddepcontrol.wait until R_n has completed; R_{n+1} streams
+// its input while F_n folds / exchanges.  Decisions alternate between two scratch sets (masks,
+// ticket, accumulator); R_{n+2} checks the set's `done` counter (F_n finished) before its first
+// mask update, and F_{n+1} checks the other set's counter (F_n finished) before it writes the
+// caller's outputs.
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
@@ -229,7 +241,7 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
     const uint32_t r = i / span, w = i - r * span;
     if ((int)r == f.rank) continue;
     // word w of the decision half or of the candidate half (which starts at n_words)
-    f.peer_gather[r][(size_t)f.rank * f.rank_stride + w] = mine[w];   // NVLink peer store
+    f.peer_gather[r][(size_t)f.rank * f.rank_stride + w] = __ldcg(mine + w);   // NVLink peer store
   }
   __threadfence_system();
   __syncthreads();
@@ -249,47 +261,20 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
   }
 }
 
-// Ticket fold at the end of a reduce grid: every CTA publishes its flags, the last one to
-// arrive packs the whole bitmap.  The ticket resets itself so the buffer is reusable by the
-// next launch on the stream without a memset.
-__device__ __forceinline__ void fold_by_last_cta(const FoldParams& f) {
-  __shared__ unsigned int s_last;
-  __shared__ unsigned long long s_cnt[3];
-  __threadfence();  // this thread's mask updates are visible device-wide
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
-    const unsigned int t = atomicAdd(f.ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  // outputs may still be owned by the previous launch on the stream until it has completed
-  pdl_wait_prior_grids();
-  __threadfence();
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const uint32_t n_words = (f.P + 31u) / 32u;
-  unsigned long long a = 0, b = 0, c = 0;
-  fold_words<8>(f, warp, n_words, n_warps, lane, a, b, c);
-  block_counts(s_cnt, a, b, c, lane);
-  if (f.world > 1) exchange_bitmaps(f, n_words);
-  __threadfence();  // mask clears and outputs before the completion signal
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    f.counts[0] = s_cnt[0];
-    f.counts[1] = s_cnt[1];
-    f.counts[2] = s_cnt[2];
-    *f.ticket = 0u;
-    st_release_u64(f.done, f.need + 1ull);
-  }
-}
-
-// Standalone fold (chunked host-window path): counts must be zeroed by the caller.  With a fused
-// exchange the host launches a single CTA, which then also pushes / gathers the bitmap.
+// The fold kernel.  Launched right behind the reduce kernel with the programmatic-stream-
+// serialization attribute: its CTAs become resident while the reduce grid is still streaming, park
+// in griddepcontrol.wait (no polling) and run the moment the reduce grid has completed and its
+// mask updates are visible.  Grid = a handful of CTAs (32 words each); the last one to finish
+// (ticket) performs the multi-GPU exchange, publishes the counters and releases the scratch set.
 __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   __shared__ unsigned long long s_cnt[3];
+  __shared__ unsigned int s_last;
+  pdl_launch_dependents();   // the next decision's reduce kernel may start streaming right away
   if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+  pdl_wait_prior_grids();    // reduce grid of THIS decision complete, masks visible
+  // the caller's output buffers may still be written by the previous decision's fold
+  if (threadIdx.x == 0)
+    while (ld_acquire_u64(f.prev_done) < f.prev_need) __nanosleep(64);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t warps_per_cta = blockDim.x >> 5;
@@ -298,28 +283,45 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   unsigned long long a = 0, b = 0, c = 0;
   fold_words<4>(f, gw, n_words, gridDim.x * warps_per_cta, lane, a, b, c);
   block_counts(s_cnt, a, b, c, lane);
-  if (f.world > 1 && gridDim.x == 1) exchange_bitmaps(f, n_words);
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0 && (s_cnt[0] | s_cnt[1] | s_cnt[2])) {
-    atomicAdd(&f.counts[0], s_cnt[0]);
-    atomicAdd(&f.counts[1], s_cnt[1]);
-    atomicAdd(&f.counts[2], s_cnt[2]);
+  if (threadIdx.x == 0) {
+    if (s_cnt[0] | s_cnt[1] | s_cnt[2]) {
+      atomicAdd(&f.acc[0], s_cnt[0]);
+      atomicAdd(&f.acc[1], s_cnt[1]);
+      atomicAdd(&f.acc[2], s_cnt[2]);
+    }
+    __threadfence();
+    s_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (f.world > 1) exchange_bitmaps(f, n_words);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    f.counts[0] = __ldcg(&f.acc[0]);
+    f.counts[1] = __ldcg(&f.acc[1]);
+    f.counts[2] = __ldcg(&f.acc[2]);
+    f.acc[0] = f.acc[1] = f.acc[2] = 0ull;
+    *f.ticket = 0u;
+    __threadfence();
+    st_release_u64(f.done, f.need + 1ull);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // shared row bookkeeping
 // ------------------------------------------------------------------------------------------
+// (kernel parameters live in constant memory: select fields with ?: — a runtime index into
+// p.seg[] would force a stack copy of the whole struct)
 __device__ __forceinline__ const float* row_ptr(const ReduceParams& p, uint32_t r, uint32_t& seg,
                                                 uint32_t& local) {
-  seg = r >= p.seg[0].n_rows ? 1u : 0u;
-  local = r - (seg ? p.seg[0].n_rows : 0u);
-  return p.seg[seg].base + (size_t)local * p.ld;
-}
-
-// before a warp's first publish: the launch that last used this scratch set must be finished
-__device__ __forceinline__ void wait_scratch_free(const FoldParams& f) {
-  while (ld_acquire_u64(f.done) < f.need) __nanosleep(64);
+  const uint32_t n0 = p.seg[0].n_rows;
+  seg = r >= n0 ? 1u : 0u;
+  local = r - (seg ? n0 : 0u);
+  const float* base = seg ? p.seg[1].base : p.seg[0].base;
+  return base + (size_t)local * p.ld;
 }
 
 // rows owned by this CTA under the strided assignment row = blockIdx.x + j * gridDim.x
@@ -327,14 +329,21 @@ __device__ __forceinline__ uint32_t cta_row_count(uint32_t total_rows) {
   return total_rows > blockIdx.x ? (total_rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 }
 
+// before a warp's first publish: the decision that last used this scratch set must have folded
+__device__ __forceinline__ void wait_scratch_free(const ReduceParams& p) {
+  while (ld_acquire_u64(p.done) < p.need) __nanosleep(64);
+}
+
 __device__ __forceinline__ void publish_row(const ReduceParams& p, uint32_t seg, uint32_t local,
                                             float m) {
-  const Segment& s = p.seg[seg];
+  const bool is_power = seg ? p.seg[1].is_power != 0 : p.seg[0].is_power != 0;
+  uint32_t* mask = seg ? p.seg[1].mask : p.seg[0].mask;
+  float* smax = seg ? p.seg[1].smax : p.seg[0].smax;
   // util: `== 0` (NaN fails, -0.0 passes); power: `>= T` (NaN fails)
-  const bool flag = s.is_power ? (m >= p.thr) : (m == 0.0f);
+  const bool flag = is_power ? (m >= p.thr) : (m == 0.0f);
   // fire-and-forget RED at L2; unflagged rows write nothing at all
-  if (flag) atomicOr(s.mask + local / p.G, 1u << (local % p.G));
-  if (s.smax) s.smax[local] = m;
+  if (flag) atomicOr(mask + local / p.G, 1u << (local % p.G));
+  if (smax) smax[local] = m;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -399,17 +408,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_reduce_ldg(ReduceParams p) {
     const float* row = row_ptr(p, blockIdx.x + j * gridDim.x, seg, local);
     const float m = row_max_ldg<U>(row, p.T, lane);
     if (lane == 0) {
-      if (!scratch_ok) wait_scratch_free(p.fold), scratch_ok = true;
+      if (!scratch_ok) wait_scratch_free(p), scratch_ok = true;
       publish_row(p, seg, local, m);
       j = atomicAdd(&s_next, 1u);
     }
     j = __shfl_sync(0xffffffffu, j, 0);
   }
-#ifdef GPR_TIMELINE
-  __syncthreads();
   TL_MARK(1);
-#endif
-  if (p.fold_in_kernel) fold_by_last_cta(p.fold);
   TL_MARK(2);
 }
 
@@ -539,11 +544,10 @@ __global__ void __launch_bounds__(NW * 32) k_reduce_tma(ReduceParams p, TmaLayou
     if (lane == 0) {
       uint32_t seg, local;
       (void)row_ptr(p, blockIdx.x + (w + NW * i) * gridDim.x, seg, local);
-      if (!scratch_ok) wait_scratch_free(p.fold), scratch_ok = true;
+      if (!scratch_ok) wait_scratch_free(p), scratch_ok = true;
       publish_row(p, seg, local, m);
     }
   }
-  if (p.fold_in_kernel) fold_by_last_cta(p.fold);
 }
 
 }  // namespace gpr
