@@ -216,7 +216,9 @@ def run_cuda(args):
 
     sh = g.shard_pods(PODS * world, rank, world) if world > 1 else g.Shard(0, 1, PODS, PODS, 0, PODS)
     P, G, T = sh.pods_per_rank, GPUS, SAMPLES
-    eng = g.IdleEngine(device=local, max_pods=P, max_gpus=G, max_samples=T, kernel=args.kernel)
+    profiling_only = bool(args.strong_total)      # c4 / c5: device-resident timing only
+    eng = g.IdleEngine(device=local, max_pods=0 if profiling_only else P, max_gpus=G, max_samples=T,
+                       kernel=args.kernel)
     if world > 1 and args.collective == "nccl":
         uid = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -282,38 +284,41 @@ def run_cuda(args):
     samples_per_step = real_pods_total * G * T
     value = samples_per_step / (ms_per_step * 1e-3)
 
-    # ---- timed region 2: end to end through gpr_decide() with pinned HOST buffers ----------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_u = eng.host_array((P, G, T), np.float32)
-    h_e = eng.host_array((P,), np.uint8)
-    h_bits = eng.host_array((max(W_out, 1),), np.uint32)
-    eng.memcpy(h_u, wins[0][0], h_u.nbytes, 0, 1)
-    eng.memcpy(h_e, wins[0][1], h_e.nbytes, 0, 1)
+    e2e_s_per_step, e2e_ok, e2e_steps = float("nan"), True, 0
+    h_u = h_e = None
+    if not profiling_only:
+        # ---- timed region 2: end to end through gpr_decide() with pinned HOST buffers ----------------
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        h_u = eng.host_array((P, G, T), np.float32)
+        h_e = eng.host_array((P,), np.uint8)
+        h_bits = eng.host_array((max(W_out, 1),), np.uint32)
+        eng.memcpy(h_u, wins[0][0], h_u.nbytes, 0, 1)
+        eng.memcpy(h_e, wins[0][1], h_e.nbytes, 0, 1)
 
-    def e2e_step():
-        return eng.decide_ptr(h_u, P, G, T, h_bits, eligible=h_e, in_kind=0, out_kind=0, blocking=True)
+        def e2e_step():
+            return eng.decide_ptr(h_u, P, G, T, h_bits, eligible=h_e, in_kind=0, out_kind=0, blocking=True)
 
-    for _ in range(3):
-        r = e2e_step()
-    e2e_ok = True
-    if rank == 0:
-        e2e_ok = bool(np.array_equal(h_bits[: (sh.pods_real + 31) // 32], exp["decision_bits"]))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s_per_step = float(t.item()) / e2e_steps
-    barrier()
+        for _ in range(3):
+            r = e2e_step()
+        e2e_ok = True
+        if rank == 0:
+            e2e_ok = bool(np.array_equal(h_bits[: (sh.pods_real + 31) // 32], exp["decision_bits"]))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s_per_step = float(t.item()) / e2e_steps
+        barrier()
 
     # ---- extra: daemon steady state (--daemon-mode, --check-interval 180 s): the window stays
     # resident in HBM, a tick moves only the 180 new columns per series across PCIe and rescans.
     resident = None
-    if world == 1:
+    if world == 1 and not profiling_only:
         n_new = 180
         eng.resident_init(P, G, T)
         u_ptr, _, _ = eng.resident_planes()
@@ -351,7 +356,8 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT,
             "pod_decisions_per_sec": real_pods_total / (ms_per_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if args.strong_total else "weak",
+            "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": workload_config(world, args.kernel, "fused NVLink peer stores in the decision kernel"
                                       if args.collective == "p2p" else "ncclAllGather"),
@@ -363,7 +369,7 @@ def run_cuda(args):
                              args.kernel if args.kernel != "auto" else "tma",
                              "; step time contains the bitmap exchange" if world > 1 else ""),
                          "algorithmic_bytes_per_launch": bytes_per_launch},
-            "e2e": {"value": samples_per_step / e2e_s_per_step, "unit": UNIT,
+            "e2e": None if profiling_only else {"value": samples_per_step / e2e_s_per_step, "unit": UNIT,
                     "pod_decisions_per_sec": real_pods_total / e2e_s_per_step,
                     "ms_per_step": e2e_s_per_step * 1e3, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h_u.nbytes + h_e.nbytes),
@@ -421,7 +427,21 @@ def main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: bitmap exchange fused into the kernel over peer memory, or one ncclAllGather")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default, the judged workload): 10k pods x 4 x 1800 per GPU, weak scaling.  "
+                         "c4 / c5 (profiling only): BASELINE configs[3] / [4], a FIXED total of 250k x 4 x 1800 "
+                         "/ 2.5M x 4 x 7200 pods sharded over the ranks (strong scaling)")
     args = ap.parse_args()
+    global PODS, GPUS, SAMPLES, ROTATE
+    args.strong_total = 0
+    if args.config != "c2":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        total, GPUS, SAMPLES = (250000, 4, 1800) if args.config == "c4" else (2500000, 4, 7200)
+        args.strong_total = total
+        PODS = total // world           # pods per rank (both totals divide by 1, 2, 4, 8)
+        ROTATE = 2 if args.config == "c4" else 1
+        args.no_cpu = True
+        args.e2e_steps = min(args.e2e_steps, 3)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
