@@ -771,6 +771,21 @@ int gpr_decide_async(gpr_ctx* ctx, const gpr_window* win, gpr_result* res) {
   GPR_CATCH(ctx)
 }
 
+int gpr_decide_batch_async(gpr_ctx* ctx, const gpr_window* wins, gpr_result* results, uint32_t n) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (n && (!wins || !results)) return fail(ctx, GPR_E_INVALID, "windows/results is NULL");
+  for (uint32_t i = 0; i < n; ++i) {
+    const int rc = decide_impl(ctx, &wins[i], &results[i], false, true);
+    if (rc != GPR_OK) {
+      ctx->masks_dirty = true;
+      return rc;
+    }
+  }
+  return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
 int gpr_sync(gpr_ctx* ctx) {
   if (!ctx) return GPR_E_INVALID;
   GPR_TRY

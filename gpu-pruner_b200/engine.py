@@ -178,6 +178,31 @@ class IdleEngine:
             self._check(self._lib.gpr_decide_async(self._h, C.byref(w), C.byref(r)))
         return r
 
+    def make_batch(self, calls):
+        """Pre-marshal a list of decide_ptr-style keyword dicts into contiguous gpr_window /
+        gpr_result arrays for :meth:`decide_batch_async` (build once, enqueue many times)."""
+        n = len(calls)
+        wins = (ffi.gpr_window * n)()
+        ress = (ffi.gpr_result * n)()
+        for i, kw in enumerate(calls):
+            w = self._window(kw["util"], kw.get("power"), kw.get("eligible"), kw.get("created_ts"),
+                             kw.get("cutoff_ts", 0), kw["P"], kw["G"], kw["T"], kw.get("row_stride", 0),
+                             kw.get("power_threshold", 0.0), kw.get("in_kind", ffi.GPR_MEM_DEVICE))
+            C.memmove(C.byref(wins, i * C.sizeof(ffi.gpr_window)), C.byref(w), C.sizeof(ffi.gpr_window))
+            r = ress[i]
+            r.struct_size = C.sizeof(ffi.gpr_result)
+            r.out_mem_kind = kw.get("out_kind", ffi.GPR_MEM_DEVICE)
+            r.decision_bits = _ptr(kw["decision_bits"])
+            r.candidate_bits = _ptr(kw.get("candidate_bits"))
+            r.series_max = _ptr(kw.get("series_max"))
+        return wins, ress, calls   # `calls` keeps the tensors alive
+
+    def decide_batch_async(self, batch, n: Optional[int] = None):
+        wins, ress, _ = batch
+        n = len(wins) if n is None else n
+        self._check(self._lib.gpr_decide_batch_async(self._h, wins, ress, n))
+        return ress
+
     def sync(self):
         self._check(self._lib.gpr_sync(self._h))
         self._keep.clear()

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gpr_decide": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result)]),
     "gpr_decide_async": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result)]),
     "gpr_sync": (C.c_int, [_P]),
+    "gpr_decide_batch_async": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result), C.c_uint32]),
     "gpr_resident_init": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "gpr_append": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_int32]),
     "gpr_decide_resident": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result)]),

@@ -168,6 +168,11 @@ GPR_API int gpr_decide(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
 /* Enqueue only (device or pinned-host buffers); counters are filled by gpr_sync().       */
 GPR_API int gpr_decide_async(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
 GPR_API int gpr_sync(gpr_ctx *ctx);
+/* Enqueue n independent decisions (windows[i] -> results[i]) in one call: the same as n calls of
+ * gpr_decide_async, without n trips through the caller's FFI.  At most 256 results may be
+ * outstanding between two gpr_sync calls.  Stops at the first failing window and returns its code. */
+GPR_API int gpr_decide_batch_async(gpr_ctx *ctx, const gpr_window *windows, gpr_result *results,
+                                   uint32_t n);
 
 /* ---- resident window for daemon mode (--daemon-mode / --check-interval, main.rs:286-330)
  * The window lives in HBM as a ring over the time axis; each tick appends the columns that

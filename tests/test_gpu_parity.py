@@ -293,6 +293,29 @@ def test_async_back_to_back(variant, engines, oracle_c):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_batch_entry_point(variant, engines, oracle_c):
+    """gpr_decide_batch_async == n calls of gpr_decide_async, including overlapped launches"""
+    eng = engines[variant]
+    P, G, T = 4096, 4, 360
+    calls, keep = [], []
+    for i in range(12):
+        u, w, e = _synth_device(eng, 900 + i, P, G, T, i % 3 == 0)
+        db = torch.zeros(P // 32, dtype=torch.int32, device="cuda:0")
+        cb = torch.zeros(P // 32, dtype=torch.int32, device="cuda:0")
+        calls.append(dict(util=u, power=w, power_threshold=150.0 if w is not None else 0.0, eligible=e,
+                          P=P, G=G, T=T, decision_bits=db, candidate_bits=cb))
+        keep.append((900 + i, w is not None, db, cb))
+    batch = eng.make_batch(calls)
+    for rep in range(3):
+        ress = eng.decide_batch_async(batch)
+        eng.sync()
+    for (seed, power, db, cb), r in zip(keep, ress):
+        exp = oracle_c.decide_synth(seed, 0, P, G, T, use_power=power, power_threshold=150.0, use_elig=True)
+        _check(db.cpu().numpy().view(np.uint32), cb.cpu().numpy().view(np.uint32),
+               (r.n_series, r.n_candidates, r.n_decisions), exp)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_resident_window_ring(variant, engines, oracle_c):
     """daemon mode: append columns tick by tick into the HBM ring, rescan, compare with the
     oracle on the window a fresh range query would have returned"""
