@@ -95,6 +95,7 @@ typedef struct gpr_config {
 /*
  * One window = the range-vector result laid out densely.
  *
+ *   n_gpus          series slots per pod, 1..32 (a pod cannot span nodes; GPR_E_UNSUPPORTED above).
  *   util[p][g][t]   f32, t fastest; NaN = "no sample" (stale / absent / scrape gap).
  *                   Restates DCGM_FI_DEV_GPU_UTIL{pod != ""}[Nm]   (query.promql.j2:16-20)
  *   power[p][g][t]  f32 or NULL.  Restates DCGM_FI_DEV_POWER_USAGE{...}[Nm]
