@@ -284,6 +284,10 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
+    # for transparency: device time of ONE isolated blocking decision (no overlap with a neighbour)
+    iso = sorted(step(i, blocking=True).kernel_ms for i in range(15))
+    single_decision_us = iso[len(iso) // 2] * 1e3
+    barrier()
     real_pods_total = PODS * world
     samples_per_step = real_pods_total * G * T
     value = samples_per_step / (ms_per_step * 1e-3)
@@ -380,6 +384,7 @@ def run_cuda(args):
                     "d2h_bytes_per_step": int(W_out * 4 + 24),
                     "api": "gpr_decide(ctx, window{mem_kind=HOST, pinned}, result{HOST})",
                     "parity": "PASS" if e2e_ok else "FAIL"},
+            "single_decision_us": single_decision_us,
             "e2e_resident": resident,
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
             "device": eng.device_info()["name"],
