@@ -26,6 +26,10 @@
  *     and keeps no thread-local state, because tokio may migrate the caller between ticks.
  *   - plain pointers and sizes only; no torch / C++ types.
  *
+ *   - device buffers handed to the library must be complete when the call is made: the context's
+ *     own stream is not ordered with the caller's streams.  Either synchronise first or give the
+ *     context the caller's stream (gpr_config.stream), in which case stream order is enough.
+ *
  * There is no CPU fallback: without a CUDA device gpr_create fails with GPR_E_CUDA.
  */
 #ifndef GPR_H_

@@ -49,6 +49,7 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
         r = eng.decide_ptr(u, P, G, T, db, eligible=e, candidate_bits=cb)
     # back-to-back async decisions (overlapped launches) must still exchange step by step
     db2 = torch.zeros_like(db)
+    torch.cuda.synchronize()
     for it in range(8):
         eng.decide_ptr(u, P, G, T, db2, eligible=e, blocking=False)
     eng.sync()

@@ -168,6 +168,7 @@ def test_strided_and_misaligned_rows(T, stride, offset, variant, engines, oracle
     db = torch.zeros(W, dtype=torch.int32, device="cuda:0")
     cb = torch.zeros(W, dtype=torch.int32, device="cuda:0")
     sm = torch.zeros(P * G, dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()   # the engine's stream is not ordered with torch's: buffers must be ready
     r = engines[variant].decide_ptr(u_t.data_ptr(), P, G, T, db, candidate_bits=cb, series_max=sm,
                                     row_stride=stride)
     _check(db.cpu().numpy().view(np.uint32), cb.cpu().numpy().view(np.uint32),
@@ -283,6 +284,7 @@ def test_async_back_to_back(variant, engines, oracle_c):
     for i in range(5):
         u, _, e = _synth_device(eng, seed + i, P, G, T, False)
         db = torch.zeros(P // 32, dtype=torch.int32, device="cuda:0")
+        torch.cuda.synchronize()
         r = eng.decide_ptr(u, P, G, T, db, eligible=e, blocking=False)
         outs.append((u, e, db, r, seed + i))
     eng.sync()
@@ -306,6 +308,7 @@ def test_batch_entry_point(variant, engines, oracle_c):
                           P=P, G=G, T=T, decision_bits=db, candidate_bits=cb))
         keep.append((900 + i, w is not None, db, cb))
     batch = eng.make_batch(calls)
+    torch.cuda.synchronize()
     for rep in range(3):
         ress = eng.decide_batch_async(batch)
         eng.sync()
@@ -350,6 +353,7 @@ def test_error_paths(engines):
     with pytest.raises(g.GprError) as ei:          # over capacity
         eng.decide(np.zeros((12001, 1, 8), np.float32))
     assert ei.value.code == g.ffi.GPR_E_CAPACITY
+    torch.cuda.synchronize()
     with pytest.raises(g.GprError) as ei:          # missing required output
         eng.decide_ptr(torch.zeros(8, device="cuda:0"), 1, 1, 8, None)
     assert ei.value.code == g.ffi.GPR_E_INVALID
@@ -384,3 +388,59 @@ def test_native_library_is_what_ran(engines):
     assert engines["ldg"].launch_count() > 0 and engines["tma"].launch_count() > 0
     info = engines["ldg"].device_info()
     assert info["cc"][0] >= 10 and info["sm_count"] > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded fuzz over shape / stride / alignment / clause combinations, G up to the 32-slot limit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_shapes(seed, variant, engines, oracle_c):
+    rng = np.random.default_rng(10_000 + seed)
+    P = int(rng.choice([1, 2, 31, 32, 33, 63, 100, 257, 1000, 3000]))
+    G = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16, 31, 32]))
+    T = int(rng.choice([1, 3, 4, 7, 16, 60, 179, 180, 181, 900, 1800, 2047, 2052]))
+    if P * G * T > 6_000_000:
+        P = max(1, 6_000_000 // (G * T))
+    pad = int(rng.choice([0, 0, 1, 3, 4, 12]))
+    off = int(rng.choice([0, 0, 1, 2, 3]))
+    with_power, with_gates = bool(rng.integers(2)), bool(rng.integers(2))
+    u, kw = _random_window(rng, P, G, T, with_power, with_gates)
+    exp = oracle_c.decide(u, **kw)
+    stride = T + pad
+
+    def plane(x):
+        buf = np.full(off + P * G * stride + 8, 77.0, np.float32)      # poison: never part of a window
+        buf[off: off + P * G * stride].reshape(P * G, stride)[:, :T] = x.reshape(P * G, T)
+        return torch.from_numpy(buf).to("cuda:0")
+
+    ut = plane(u)
+    wt = plane(kw["power"]) if with_power else None
+    et = torch.from_numpy(kw["eligible"]).to("cuda:0") if with_gates else None
+    ct = torch.from_numpy(kw["created_ts"]).to("cuda:0") if with_gates else None
+    W = (P + 31) // 32
+    db = torch.full((W,), -1, dtype=torch.int32, device="cuda:0")
+    cb = torch.full((W,), -1, dtype=torch.int32, device="cuda:0")
+    sm = torch.zeros(P * G, dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()
+    r = engines[variant].decide_ptr(ut[off:].data_ptr(), P, G, T, db,
+                                    power=None if wt is None else wt[off:].data_ptr(), eligible=et,
+                                    created_ts=ct, cutoff_ts=kw.get("cutoff_ts", 0),
+                                    power_threshold=kw.get("power_threshold", 0.0), candidate_bits=cb,
+                                    series_max=sm, row_stride=stride)
+    _check(db.cpu().numpy().view(np.uint32), cb.cpu().numpy().view(np.uint32),
+           (r.n_series, r.n_candidates, r.n_decisions), exp, sm.cpu().numpy().reshape(P, G))
+
+
+def test_gpu_slot_limit(engines):
+    import gpu_pruner_b200 as g
+    eng = engines["tma"]
+    # all 32 slots usable: only the last GPU of each pod is idle
+    P, G, T = 40, 32, 16
+    u = np.full((P, G, T), 5.0, np.float32)
+    u[:, 31, :] = 0.0
+    bits, cbits, counts, smax, _ = _device_decide(eng, u)
+    assert counts == (P, P, P) and int(np.unpackbits(cbits.view(np.uint8)).sum()) == P
+    with pytest.raises(g.GprError) as ei:
+        eng.decide(np.zeros((2, 33, 4), np.float32))
+    assert ei.value.code == g.ffi.GPR_E_UNSUPPORTED

@@ -22,6 +22,7 @@ def run(variant, P, G, T, iters, rot, power=False):
             eng.synth_fill(0x5EED0002 + i, 1, w, 0, P, G, T)
         wins.append((u, w))
     db = torch.zeros((P + 31) // 32, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
     for i in range(5):
         eng.decide_ptr(wins[i % rot][0], P, G, T, db, power=wins[i % rot][1], power_threshold=150.0 if power else 0.0,
                        blocking=False)
