@@ -1,5 +1,6 @@
 #include "ingest.hpp"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -63,6 +64,7 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
   std::map<std::pair<std::string, std::string>, uint32_t> pod_index;
   std::vector<std::map<std::string, uint32_t>> slot_index;       // per pod: group key -> util slot
   std::vector<std::map<std::string, uint32_t>> pslot_index;      // per pod: group key -> power slot
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<std::string>> prof_sigs;  // (pod, slot) -> PROF label sets
   std::vector<RawSeries> useries, pseries;
   int64_t newest = std::numeric_limits<int64_t>::min();
   int64_t min_step = std::numeric_limits<int64_t>::max();
@@ -119,10 +121,28 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
           w.pods[p].slots.push_back(g);
         } else {
           slot = f->second;
-          // `A or B` (query.promql.j2:10-20): a PROF element shadows the UTIL element with the same
-          // label set; two series of the same plane in one group are `sum by` duplicates
-          if (w.pods[p].slots[slot].from_prof && !is_prof) continue;
           ++w.stats.duplicates_merged;
+        }
+        // `A or B` (query.promql.j2:10-20) matches on the FULL label set: a UTIL element is dropped
+        // only if a PROF element with identical labels exists; series that differ in any other label
+        // both survive the `or` and are then folded together by `sum by`
+        std::vector<std::string> parts;
+        for (const Json::Member& kv : m.members())
+          if (kv.first != "__name__") parts.push_back(kv.first + "\x1f" + kv.second.as_string());
+        std::sort(parts.begin(), parts.end());
+        std::string sig;
+        for (const std::string& x : parts) sig += x + "\x1e";
+        std::vector<std::string>& ps = prof_sigs[std::make_pair(p, slot)];
+        if (is_prof) {
+          ps.push_back(sig);
+          w.pods[p].slots[slot].from_prof = true;
+        } else {
+          bool shadowed = false;
+          for (const std::string& x : ps) shadowed |= (x == sig);
+          if (shadowed) {
+            --w.stats.duplicates_merged;
+            continue;
+          }
         }
         useries.push_back(RawSeries{p, slot, &vals, is_prof});
       }
