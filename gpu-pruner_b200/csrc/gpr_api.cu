@@ -153,6 +153,7 @@ struct gpr_ctx {
   size_t p2p_gather_off[2] = {0, 0};
   uint32_t p2p_stride = 0;                       // words per rank slot = 2 * W_max
   bool p2p_ready = false;
+  int exchange_debug = 0;                        // GPR_DEBUG_EXCHANGE (developer timing switch)
   unsigned long long p2p_step = 0;
 
   uint64_t launches = 0;
@@ -451,7 +452,9 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   fp.P = P;
   fp.G = G;
   fp.world = 1, fp.rank = 0;
+  fp.exchange_debug = 0;
   if (fused) {
+    fp.exchange_debug = ctx->exchange_debug;
     fp.world = ctx->world, fp.rank = ctx->rank;
     fp.rank_stride = ctx->p2p_stride;
     for (int r = 0; r < ctx->world; ++r) {
@@ -719,6 +722,7 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     CU(cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_done, 0, 2 * sizeof(unsigned long long)));
     c->pdl_enabled = env_int("GPR_PDL", 1) != 0;
+    c->exchange_debug = env_int("GPR_DEBUG_EXCHANGE", 0);
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
                       (size_t)kSlots * 3 * sizeof(unsigned long long)));
     c->pending.reserve(kSlots);

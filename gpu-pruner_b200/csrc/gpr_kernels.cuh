@@ -78,6 +78,8 @@ struct FoldParams {
   unsigned long long step;               // exchange sequence number of this call (same on all ranks)
   uint32_t* out_dbits;                   // caller's global bitmaps on this device (may be null)
   uint32_t* out_cbits;
+  int exchange_debug;                    // 0 normal; developer timing switches: 1 = do not wait for the
+                                         // peers, 2 = no push at all (results are then NOT global)
 };
 
 struct ReduceParams {
@@ -237,17 +239,30 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
   __syncthreads();  // the fold's word stores are visible to the whole CTA
   const uint32_t* mine = f.peer_gather[f.rank] + (size_t)f.rank * f.rank_stride;
   const uint32_t span = 2u * n_words;  // [decision | candidate], candidate slot always present
-  for (uint32_t i = threadIdx.x; i < span * (uint32_t)f.world; i += blockDim.x) {
-    const uint32_t r = i / span, w = i - r * span;
-    if ((int)r == f.rank) continue;
-    // word w of the decision half or of the candidate half (which starts at n_words)
-    f.peer_gather[r][(size_t)f.rank * f.rank_stride + w] = __ldcg(mine + w);   // NVLink peer store
+  // each word is read once and fanned out to every peer (a per-peer reload would put world-1
+  // dependent L2 round trips per word on this CTA's critical path)
+  for (uint32_t w0 = threadIdx.x; w0 < span && f.exchange_debug != 2; w0 += 4u * blockDim.x) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w = w0 + k * blockDim.x;
+      v[k] = w < span ? __ldcg(mine + w) : 0u;
+    }
+    for (int r = 0; r < f.world; ++r) {
+      if (r == f.rank) continue;
+      uint32_t* dst = f.peer_gather[r] + (size_t)f.rank * f.rank_stride;   // NVLink peer stores
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w = w0 + k * blockDim.x;
+        if (w < span) dst[w] = v[k];
+      }
+    }
   }
   __threadfence_system();
   __syncthreads();
-  if ((int)threadIdx.x < f.world && (int)threadIdx.x != f.rank) {
+  if ((int)threadIdx.x < f.world && (int)threadIdx.x != f.rank && f.exchange_debug != 2) {
     st_release_sys_u64(f.peer_flag[threadIdx.x], f.step);             // "rank's words of step k are there"
-    while (ld_acquire_sys_u64(f.my_flags + threadIdx.x) < f.step) __nanosleep(128);
+    while (f.exchange_debug == 0 && ld_acquire_sys_u64(f.my_flags + threadIdx.x) < f.step) __nanosleep(128);
   }
   __syncthreads();
   // assemble the caller's rank-major global bitmaps from the local gather buffer

@@ -1,6 +1,7 @@
 // capi.cpp — a small extern "C" surface over the host library so the test-suite (pytest + ctypes)
 // can exercise the pure host logic — CLI parsing, PromQL rendering, matrix ingest, owner walk,
 // scale requests — without a GPU.  Strings are returned in a caller-provided buffer as JSON.
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,17 +84,32 @@ GPH_API int gph_format_float(double v, char* out, int cap) { return put(gph::for
 
 // ingest: JSON texts in, tensor out.  Returns 0 or negative; dims written to dims[3] = P,G,T.
 // util_out/power_out may be NULL to query dimensions + the pod table (JSON) first.
+static int g_ingest_threads = -1;  // -1: DOM path; >= 0: text path with that many threads (0 = all)
+GPH_API void gph_ingest_mode(int threads) { g_ingest_threads = threads; }
+
 GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char* power_json,
                        long long duration_min, long long step, long long t_end, unsigned* dims,
                        float* util_out, float* power_out, char* pods_json, int cap) {
   try {
-    gph::Json u = gph::Json::parse(util_json), pf, pw;
-    const gph::Json *ppf = nullptr, *ppw = nullptr;
-    if (prof_json) pf = gph::Json::parse(prof_json), ppf = &pf;
-    if (power_json) pw = gph::Json::parse(power_json), ppw = &pw;
     gph::IngestOptions o;
     o.duration_min = duration_min, o.step = step, o.t_end = t_end;
-    gph::Window w = gph::ingest_matrix(u, ppf, ppw, o);
+    gph::Window w;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (g_ingest_threads >= 0) {
+      std::string us(util_json), ps, ws;
+      if (prof_json) ps = prof_json;
+      if (power_json) ws = power_json;
+      w = gph::ingest_matrix_text(us, prof_json ? &ps : nullptr, power_json ? &ws : nullptr, o,
+                                  g_ingest_threads);
+    } else {
+      gph::Json u = gph::Json::parse(util_json), pf, pw;
+      const gph::Json *ppf = nullptr, *ppw = nullptr;
+      if (prof_json) pf = gph::Json::parse(prof_json), ppf = &pf;
+      if (power_json) pw = gph::Json::parse(power_json), ppw = &pw;
+      w = gph::ingest_matrix(u, ppf, ppw, o);
+    }
+    const double ingest_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     dims[0] = w.P, dims[1] = w.G, dims[2] = w.T;
     if (util_out) memcpy(util_out, w.util.data(), w.util.size() * sizeof(float));
     if (power_out && !w.power.empty()) memcpy(power_out, w.power.data(), w.power.size() * sizeof(float));
@@ -115,6 +131,7 @@ GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char*
     gph::Json meta = gph::Json::object();
     meta.set("pods", pods);
     meta.set("t_end", (int64_t)w.t_end), meta.set("step", (int64_t)w.step);
+    meta.set("ingest_ms", ingest_ms);
     meta.set("series_in", (int64_t)w.stats.series_in), meta.set("series_skipped", (int64_t)w.stats.series_skipped);
     meta.set("samples_out_of_window", (int64_t)w.stats.samples_out_of_window);
     meta.set("duplicates_merged", (int64_t)w.stats.duplicates_merged);

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <limits>
 #include <stdexcept>
 #include <sys/stat.h>
@@ -58,21 +59,26 @@ class FileSource : public WindowSource {
   Window fetch(const Cli& args) override {
     const std::string up = dir_ + "/util.json";
     if (!file_exists(up)) throw std::runtime_error("Failed to run query! " + up + " not found");
-    Json util = Json::parse_file(up);
-    Json prof, power, meta;
-    const Json *pprof = nullptr, *ppower = nullptr;
-    if (file_exists(dir_ + "/prof.json")) prof = Json::parse_file(dir_ + "/prof.json"), pprof = &prof;
+    auto slurp = [](const std::string& path) {
+      std::ifstream f(path, std::ios::binary);
+      if (!f) throw std::runtime_error("cannot open " + path);
+      std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      return s;
+    };
+    const std::string util = slurp(up);
+    std::string prof, power;
+    const std::string *pprof = nullptr, *ppower = nullptr;
+    if (file_exists(dir_ + "/prof.json")) prof = slurp(dir_ + "/prof.json"), pprof = &prof;
     const bool want_power = args.power_threshold && *args.power_threshold != 0.0;
-    if (want_power && file_exists(dir_ + "/power.json"))
-      power = Json::parse_file(dir_ + "/power.json"), ppower = &power;
+    if (want_power && file_exists(dir_ + "/power.json")) power = slurp(dir_ + "/power.json"), ppower = &power;
     IngestOptions opt;
     opt.duration_min = args.duration;
     if (file_exists(dir_ + "/query.json")) {
-      meta = Json::parse_file(dir_ + "/query.json");
+      const Json meta = Json::parse_file(dir_ + "/query.json");
       opt.t_end = (int64_t)meta["end"].as_number(0);
       opt.step = (int64_t)meta["step"].as_number(0);
     }
-    return ingest_matrix(util, pprof, ppower, opt);
+    return ingest_matrix_text(util, pprof, ppower, opt);
   }
 
  private:

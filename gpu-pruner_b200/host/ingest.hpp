@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <map>
 #include <string>
+#include <string>
 #include <vector>
 
 #include "json.hpp"
@@ -52,5 +53,13 @@ struct IngestOptions {
 // response ({"status":"success","data":{"resultType":"matrix","result":[...]}}) or just the
 // "result" array.  Throws std::runtime_error on malformed input / non-matrix result types.
 Window ingest_matrix(const Json& util, const Json* prof, const Json* power, const IngestOptions& opt);
+
+// Same result from the raw response TEXT, without building a DOM for the samples: series boundaries
+// are found with one memmem per series, label sets go through the small DOM parser, and the sample
+// arrays — >99 % of the bytes — are parsed by n_threads workers (0 = hardware concurrency) straight
+// into the tensor rows.  This is the path the controller uses; ingest_matrix() is the reference
+// implementation it is tested against (tests/test_host.py).
+Window ingest_matrix_text(const std::string& util, const std::string* prof, const std::string* power,
+                          const IngestOptions& opt, int n_threads = 0);
 
 }  // namespace gph

@@ -101,6 +101,11 @@ def parse_rfc3339(s):
     return lib().gph_parse_rfc3339(s.encode())
 
 
+def ingest_mode(threads):
+    """-1: DOM reference path; >= 0: text path with that many parser threads (0 = all cores)"""
+    lib().gph_ingest_mode(threads)
+
+
 def ingest(util, prof=None, power=None, duration_min=30, step=0, t_end=0):
     import numpy as np
     dims = (C.c_uint * 3)()

@@ -385,8 +385,15 @@ def test_missing_replicaset_is_swallowed_missing_deployment_propagates(cluster):
 
 
 # ---------------------------------------------------------------------------------------------
-# ingest of the matrix wire format
+# ingest of the matrix wire format: DOM reference path and the threaded text path
 # ---------------------------------------------------------------------------------------------
+@pytest.fixture(params=[-1, 1, 4], ids=["dom", "text-1thread", "text-4threads"], autouse=True)
+def ingest_path(request):
+    H.ingest_mode(request.param)
+    yield request.param
+    H.ingest_mode(-1)
+
+
 def series(labels, samples):
     return {"metric": labels, "values": [[t, str(v)] for t, v in samples]}
 
@@ -476,3 +483,72 @@ def test_ingested_window_feeds_the_oracle(oracle_np):
     r = oracle_np.decide(util, power, power_threshold=150.0)
     verdict = dict(zip(names, r["candidate"]))
     assert verdict == {"idle-pod": True, "busy-pod": False, "two-gpu": True, "hot-idle": False}
+
+
+def test_text_ingest_equals_dom_ingest_on_random_responses():
+    """the fast path must reproduce the reference path bit for bit: odd spacing, float timestamps,
+    exponent / NaN / Inf value strings, empty series, duplicates, out-of-window samples"""
+    import random
+    for seed in range(25):
+        rng = random.Random(seed)
+        t_end = 1_700_000_000 + rng.randrange(1000)
+        step = rng.choice([1, 5, 15])
+        dur = rng.choice([1, 2, 5])
+        sers = []
+        for p in range(rng.randrange(1, 9)):
+            for g in range(rng.randrange(1, 4)):
+                n = rng.randrange(0, 40)
+                tss = sorted({t_end - step * rng.randrange(0, dur * 60 // step + 10) for _ in range(n)})
+                smp = []
+                for t in tss:
+                    tv = t if rng.random() < 0.8 else t + rng.choice([0.123, 0.4, 0.499])
+                    v = rng.choice(["0", "0", "37", "100", "0.25", "1e-3", "2.5E+1", "NaN", "+Inf", "-Inf",
+                                    "99.99999999999999", "0.30000000000000004", "1e-60", "12345678901234567890"])
+                    smp.append((tv, v))
+                lab = lab_(rng, p, g)
+                sers.append({"metric": lab, "values": [[t, v] for t, v in smp]})
+                if rng.random() < 0.2:
+                    sers.append({"metric": dict(lab, UUID="dup"), "values": [[t_end, "3"]]})
+        text = {"status": "success", "data": {"resultType": "matrix", "result": sers}}
+        pw = {"status": "success", "data": {"result": [s for s in sers if rng.random() < 0.5], "resultType": "matrix"}}
+        outs = []
+        for mode in (-1, 1, 3):
+            H.ingest_mode(mode)
+            for kw in (dict(step=step, t_end=t_end), dict()):      # given, or inferred from the data
+                outs.append((mode, kw, H.ingest(text, None, pw, duration_min=dur, **kw)))
+        ref = {repr(kw): o for m, kw, o in outs if m == -1}
+        for m, kw, (u, w, meta) in outs:
+            ru, rw, rmeta = ref[repr(kw)]
+            assert u.shape == ru.shape and np.array_equal(u.view(np.uint32), ru.view(np.uint32)), (seed, m, kw)
+            assert np.array_equal(w.view(np.uint32), rw.view(np.uint32))
+            meta.pop("ingest_ms"), rmeta.pop("ingest_ms", None)
+            assert meta == rmeta
+    H.ingest_mode(-1)
+
+
+def lab_(rng, p, g):
+    d = {"Hostname": f"n{p % 3}", "gpu": str(g), "modelName": "NVIDIA B200", "UUID": f"GPU-{p}-{g}",
+         "exported_pod": f"pod-{p}", "exported_namespace": "ml", "exported_container": "main"}
+    if rng.random() < 0.1:
+        d["weird \"label\\name"] = "va\"lue, with ]] brackets [[ and \\ slashes"
+    return d
+
+
+def test_text_ingest_throughput_smoke():
+    """not a benchmark: the text path must be far quicker than the DOM path on a mid-size response"""
+    import time
+    t_end, T = 1_700_000_000, 600
+    sers = [{"metric": {"Hostname": "n", "gpu": str(g), "modelName": "m", "exported_pod": f"p{p}",
+                        "exported_namespace": "ns", "exported_container": "c"},
+             "values": [[t_end - T + 1 + i, "0" if (i + p) % 7 else "42"] for i in range(T)]}
+            for p in range(300) for g in range(2)]
+    text = {"status": "success", "data": {"resultType": "matrix", "result": sers}}
+    times = {}
+    for mode in (-1, 0):
+        H.ingest_mode(mode)
+        t0 = time.perf_counter()
+        u, _, _ = H.ingest(text, duration_min=10, step=1, t_end=t_end)
+        times[mode] = time.perf_counter() - t0
+        assert u.shape == (300, 2, 600)
+    H.ingest_mode(-1)
+    assert times[0] < times[-1]

@@ -113,7 +113,11 @@ def test_dense_path_equals_promql_semantics(seed, oracle_np, oracle_c):
     if not util["data"]["result"] and not prof["data"]["result"]:
         assert pods_a == []
         return
-    u, w, meta = H.ingest(util, prof, power, duration_min=dur, step=1, t_end=t_eval)
+    H.ingest_mode(-1 if seed % 3 == 0 else seed % 3)      # DOM reference path / threaded text path
+    try:
+        u, w, meta = H.ingest(util, prof, power, duration_min=dur, step=1, t_end=t_eval)
+    finally:
+        H.ingest_mode(-1)
     names = [(p["name"], p["namespace"]) for p in meta["pods"]]
     for orc in (oracle_np, oracle_c):
         r = orc.decide(u, w, power_threshold=thr)
