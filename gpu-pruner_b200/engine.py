@@ -82,6 +82,7 @@ class IdleEngine:
         self._h = h
         self.device = device
         self._keep = []  # result structs / arrays referenced by outstanding async calls
+        self._host_arrays = []  # pinned allocations handed out by host_array(), freed in close()
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -90,6 +91,9 @@ class IdleEngine:
 
     def close(self):
         if getattr(self, "_h", None):
+            for ptr in getattr(self, "_host_arrays", []):
+                self._lib.gpr_host_free(self._h, ptr)
+            self._host_arrays = []
             self._lib.gpr_destroy(self._h)
             self._h = None
 
@@ -220,8 +224,7 @@ class IdleEngine:
             if power_cols is not None:
                 power_cols = np.ascontiguousarray(power_cols, dtype=np.float32)
         self._check(self._lib.gpr_append(self._h, _ptr(util_cols), _ptr(power_cols), n_new,
-                                         row_stride, mem_kind))
-        self._keep_cols = (util_cols, power_cols)
+                                         row_stride, mem_kind))  # blocking: the columns are consumed
 
     def resident_planes(self):
         u, p, ld = C.c_void_p(), C.c_void_p(), C.c_uint64()
@@ -268,6 +271,7 @@ class IdleEngine:
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
         ptr = self.host_alloc(max(n, 1))
+        self._host_arrays.append(ptr)
         buf = (C.c_char * max(n, 1)).from_address(ptr)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
         return arr

@@ -444,3 +444,33 @@ def test_gpu_slot_limit(engines):
     with pytest.raises(g.GprError) as ei:
         eng.decide(np.zeros((2, 33, 4), np.float32))
     assert ei.value.code == g.ffi.GPR_E_UNSUPPORTED
+
+
+def test_memory_and_timing_helpers(engines):
+    """the small utility entry points of include/gpr.h: device/pinned allocation, copies, timer, L2 flush"""
+    eng = engines["tma"]
+    n = 1 << 16
+    d = eng.device_alloc(4 * n)
+    h = eng.host_array((n,), np.float32)
+    h[:] = np.arange(n, dtype=np.float32)
+    eng.memcpy(d, h, 4 * n, 1, 0)
+    back = np.zeros(n, np.float32)
+    eng.memcpy(back, d, 4 * n, 0, 1)
+    assert np.array_equal(back, h)
+    eng.timer_begin()
+    eng.flush_l2()
+    ms = eng.timer_end()
+    assert ms > 0
+    # a window living in gpr_device_alloc memory works like any other device pointer
+    P, G, T = 64, 4, 256
+    assert P * G * T == n
+    h[:] = 0.0
+    h.reshape(P, G, T)[::2] = 3.0
+    eng.memcpy(d, h, 4 * n, 1, 0)
+    bits = np.zeros(2, np.uint32)
+    r = eng.decide_ptr(d, P, G, T, bits, out_kind=0)
+    assert r.n_decisions == P // 2 and bits[0] == 0xAAAAAAAA and bits[1] == 0xAAAAAAAA
+    eng.device_free(d)
+    before = eng.launch_count()
+    eng.decide(np.zeros((3, 1, 4), np.float32))
+    assert eng.launch_count() >= before + 2          # one reduce + one fold
