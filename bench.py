@@ -214,6 +214,7 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity_failed = False
     sh = g.shard_pods(PODS * world, rank, world) if world > 1 else g.Shard(0, 1, PODS, PODS, 0, PODS)
     P, G, T = sh.pods_per_rank, GPUS, SAMPLES
     profiling_only = bool(args.strong_total)      # c4 / c5: device-resident timing only
@@ -243,16 +244,13 @@ def run_cuda(args):
         u, e = wins[i % ROTATE]
         return eng.decide_ptr(u, P, G, T, dbits, eligible=e, blocking=blocking)
 
-    # ---- parity of the benchmarked workload against the oracle (outside the timed region) ----
-    # every rank takes the step (with a communicator it contains the allgather); rank 0 checks its shard
-    parity = None
+    # One blocking step on window 0 before the timed region; its bitmap is kept so that the
+    # cpu_baseline leg (the only place of this arm that runs the oracle) can compare it bit for bit.
+    # Every rank takes the step: with an exchange attached it is collective.
     r = step(0, blocking=True)
-    if rank == 0:
-        from oracle import oracle_c
-        exp = oracle_c.decide_synth(SEED, sh.pod_begin, sh.pods_real, G, T, use_elig=True)
-        got = dbits.cpu().numpy().view(np.uint32)[: (sh.pods_real + 31) // 32]
-        ok = np.array_equal(got, exp["decision_bits"]) and r.n_decisions == exp["n_decisions"]
-        parity = "PASS" if ok else "FAIL"
+    n_words_mine = (sh.pods_real + 31) // 32
+    gpu_bits = dbits.cpu().numpy().view(np.uint32)[:n_words_mine].copy()
+    gpu_counts = (int(r.n_series), int(r.n_candidates), int(r.n_decisions))
     barrier()
 
     # ---- timed region 1: windows resident in HBM ------------------------------------------------
@@ -308,9 +306,8 @@ def run_cuda(args):
 
         for _ in range(3):
             r = e2e_step()
-        e2e_ok = True
-        if rank == 0:
-            e2e_ok = bool(np.array_equal(h_bits[: (sh.pods_real + 31) // 32], exp["decision_bits"]))
+        # the host-window path must reproduce the device-window bitmap of the same window
+        e2e_ok = bool(np.array_equal(h_bits[:n_words_mine], gpu_bits))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -383,28 +380,34 @@ def run_cuda(args):
                     "h2d_bytes_per_step": int(h_u.nbytes + h_e.nbytes),
                     "d2h_bytes_per_step": int(W_out * 4 + 24),
                     "api": "gpr_decide(ctx, window{mem_kind=HOST, pinned}, result{HOST})",
-                    "parity": "PASS" if e2e_ok else "FAIL"},
+                    "matches_device_path": e2e_ok},
             "single_decision_us": single_decision_us,
             "e2e_resident": resident,
-            "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "parity": "unchecked (no cpu_baseline leg in this run; see tests/ -m gpu)",
             "device": eng.device_info()["name"],
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_cpu and not profiling_only:
+            line["cpu_baseline"], ref = cpu_baseline()
+            ok = (np.array_equal(ref["decision_bits"], gpu_bits) and ref["counts"] == gpu_counts
+                  and (profiling_only or e2e_ok))
+            line["parity"] = "PASS" if ok else "FAIL"
+            parity_failed = not ok
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0 if (parity in (None, "PASS")) else 1
+    return 1 if parity_failed else 0
 
 
 def cpu_baseline():
     """the oracle timed on this box's host cores over a bounded sample of the same workload"""
     from oracle import oracle_c
     n_threads = oracle_c.hardware_threads()
-    run, _, _ = cpu_pass_factory(n_threads)
-    run(0)
+    run, dbits, counts = cpu_pass_factory(n_threads)
+    run(0)    # window 0 = the window of the CUDA arm's first step: the checker's verdict for it
+    ref = {"decision_bits": dbits.copy(), "counts": tuple(int(x) for x in counts)}
     t0 = time.perf_counter()
     run(1)
     one = time.perf_counter() - t0
@@ -421,7 +424,7 @@ def cpu_baseline():
             "pod_decisions_per_sec": PODS * passes / dt,
             "single_thread_value": samples / one_thread,
             "sample": f"{passes} passes over {ROTATE} rotated C2 windows ({samples * 4 / 1e6:.0f} MB each, host RAM), "
-                      f"{n_threads} POSIX threads; oracle/gpr_oracle.c -O3 -march=x86-64-v3, scalar f64"}
+                      f"{n_threads} POSIX threads; oracle/gpr_oracle.c -O3 -march=x86-64-v3, scalar f64"}, ref
 
 
 def main():
