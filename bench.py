@@ -233,12 +233,14 @@ def run_cuda(args):
     wins = []
     for i in range(ROTATE):
         u = torch.full((P, G, T), float("nan"), dtype=torch.float32, device=dev)
-        eng.synth_fill(SEED + 16 * i, 0, u, sh.pod_begin, sh.pods_real, G, T)
         e = torch.zeros(P, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()   # torch's fills first: the engine's stream is not ordered with torch's
+        eng.synth_fill(SEED + 16 * i, 0, u, sh.pod_begin, sh.pods_real, G, T)
         eng.synth_eligible(SEED + 16 * i, e, sh.pod_begin, sh.pods_real)
         wins.append((u, e))
     W_out = (P + 31) // 32 * world
     dbits = torch.zeros(W_out, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
 
     def step(i, blocking=False):
         u, e = wins[i % ROTATE]

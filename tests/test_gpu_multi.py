@@ -39,8 +39,9 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
         eng.p2p_attach(handles)
     dev = f"cuda:{rank}"
     u = torch.full((P, G, T), float("nan"), dtype=torch.float32, device=dev)
-    eng.synth_fill(seed, 0, u, sh.pod_begin, sh.pods_real, G, T)
     e = torch.zeros(P, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()   # torch's fills before the engine's stream touches the buffers
+    eng.synth_fill(seed, 0, u, sh.pod_begin, sh.pods_real, G, T)
     eng.synth_eligible(seed, e, sh.pod_begin, sh.pods_real)
     db = torch.zeros(world * P // 32, dtype=torch.int32, device=dev)
     cb = torch.zeros(world * P // 32, dtype=torch.int32, device=dev)
