@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in nsys / ncu --nvtx timelines
 
 #include <algorithm>
 #include <cmath>
@@ -304,8 +305,14 @@ int copy_rows_h2d(gpr_ctx* ctx, float* dst, const float* src, size_t n_rows, uin
   return GPR_OK;
 }
 
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resident, bool async) {
   if (!ctx) return GPR_E_INVALID;
+  NvtxRange nvtx_range(resident ? "gpr_decide_resident" : "gpr_decide");
   if (!win || !res) return fail(ctx, GPR_E_INVALID, "window/result is NULL");
   if (win->struct_size != sizeof(gpr_window) || res->struct_size != sizeof(gpr_result))
     return fail(ctx, GPR_E_INVALID, "struct_size mismatch (window %u/%zu result %u/%zu)",
