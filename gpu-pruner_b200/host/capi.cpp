@@ -242,3 +242,116 @@ GPH_API int gph_generate_event(const char* kind, const char* object_json, long l
     return -2;
   }
 }
+
+// ---- controller under test: one tick with RECORDED verdicts -----------------------------------------
+// The product engine is libgpr (gpr_engine.cpp) and is not linked into this test library.  Here the
+// test supplies the verdict arrays (computed by the CPU oracle on the ingested window) so that the
+// gates / owner walk / dedup / request emission of Controller::run_query_and_scale can run on CPU.
+namespace {
+class ScriptedEngine : public gph::VerdictEngine {
+ public:
+  gph::Verdict verdict;
+  bool fail = false;
+  gph::VerdictRequest last;
+  std::vector<uint8_t> eligible_seen;
+  std::vector<int64_t> created_seen;
+  bool decide(const gph::VerdictRequest& rq, gph::Verdict* out, std::string* error) override {
+    last = rq;
+    const uint32_t P = rq.window->P;
+    if (rq.eligible) eligible_seen.assign(rq.eligible, rq.eligible + P);
+    if (rq.created_ts) created_seen.assign(rq.created_ts, rq.created_ts + P);
+    if (fail) {
+      *error = "scripted failure";
+      return false;
+    }
+    *out = verdict;
+    // the fused gate (main.rs:473-510) is part of the verdict: apply it to the recorded candidates
+    const uint32_t W = (P + 31) / 32;
+    out->decision_bits.assign(W, 0);
+    out->n_decisions = 0;
+    for (uint32_t p = 0; p < P; ++p) {
+      const bool cand = (verdict.candidate_bits[p >> 5] >> (p & 31)) & 1u;
+      const bool elig = (!rq.eligible || rq.eligible[p]) && !(rq.created_ts && rq.created_ts[p] >= rq.cutoff_ts);
+      if (cand && elig) out->decision_bits[p >> 5] |= 1u << (p & 31), ++out->n_decisions;
+    }
+    return true;
+  }
+};
+}  // namespace
+
+// args: CLI argv (NUL separated).  candidate_bits / series_max / n_series are the recorded verdict for
+// the window the controller will ingest from --prometheus-url file://...  Output JSON:
+// {"ok":..,"error":..,"num_pods":..,"shutdown_events":..,"unique_pods":[..],"requests":[..],
+//  "eligible":[..],"cutoff":..,"power_on":..}
+GPH_API int gph_run_tick(const char* args, int n, const unsigned* candidate_bits, const float* series_max,
+                         unsigned long long n_series, int fail, const char* log_path, char* out, int cap) {
+  try {
+    gph::ParseOutcome po = gph::parse_cli(split_args(args, n));
+    if (!po.ok) return put(po.message, out, cap) >= 0 ? -1 : -2;
+    const gph::Cli& cli = po.cli;
+    std::unique_ptr<gph::FixtureKubeApi> kube;
+    if (cli.kube_fixture) kube = std::make_unique<gph::FixtureKubeApi>(*cli.kube_fixture);
+    FILE* lf = log_path && *log_path ? fopen(log_path, "w") : nullptr;
+    gph::Logger log(cli.log_format, lf ? lf : stderr);
+    ScriptedEngine eng;
+    eng.fail = fail != 0;
+    gph::Json j = gph::Json::object();
+    std::unique_ptr<gph::WindowSource> src = gph::make_window_source(cli.prometheus_url);
+    gph::Window w;
+    try {
+      w = src->fetch(cli);
+    } catch (const std::exception& e) {
+      j.set("ok", false), j.set("error", std::string(e.what()));
+      if (lf) fclose(lf);
+      return put(j.dump(), out, cap);
+    }
+    const uint32_t W = (w.P + 31) / 32;
+    eng.verdict.candidate_bits.assign(candidate_bits, candidate_bits + W);
+    eng.verdict.decision_bits.assign(W, 0);
+    eng.verdict.series_max.assign(series_max, series_max + (size_t)w.P * w.G);
+    eng.verdict.n_series = n_series;
+    for (uint32_t k = 0; k < W; ++k) eng.verdict.n_candidates += (uint64_t)__builtin_popcount(candidate_bits[k]);
+    gph::Clock clock = gph::system_clock();
+    clock.uuid_simple = [] { return std::string("00000000000040008000000000000000"); };
+    gph::Controller ctl(cli, kube.get(), &eng, log, clock);
+    gph::TickResult tr = ctl.run_query_and_scale(w);
+    if (lf) fclose(lf);
+    j.set("ok", tr.ok), j.set("error", tr.error);
+    j.set("num_pods", (int64_t)tr.qr.num_pods), j.set("shutdown_events", (int64_t)tr.qr.shutdown_events);
+    gph::Json ups = gph::Json::array();
+    for (const gph::PodMetricData& p : tr.unique_pods) {
+      gph::Json o = gph::Json::object();
+      o.set("name", p.name), o.set("namespace", p.ns), o.set("container", p.container);
+      o.set("node_type", p.node_type), o.set("gpu_model", p.gpu_model), o.set("value", p.value);
+      ups.push(o);
+    }
+    j.set("unique_pods", ups);
+    gph::Json roots = gph::Json::array();
+    for (const gph::ScaleKind& sk : tr.shutdown) {
+      gph::Json o = gph::Json::object();
+      o.set("kind", sk.kind_name()), o.set("name", sk.name());
+      roots.push(o);
+    }
+    j.set("roots", roots);
+    gph::Json reqs = gph::Json::array();
+    for (const gph::Request& rq : tr.requests) {
+      gph::Json o = gph::Json::object();
+      o.set("method", rq.method), o.set("path", rq.path), o.set("contentType", rq.content_type);
+      o.set("body", rq.body);
+      reqs.push(o);
+    }
+    j.set("requests", reqs);
+    gph::Json el = gph::Json::array();
+    for (uint8_t e : eng.eligible_seen) el.push((int)e);
+    j.set("eligible", el);
+    j.set("cutoff", (int64_t)eng.last.cutoff_ts), j.set("power_on", eng.last.power_on);
+    j.set("power_threshold", eng.last.power_threshold);
+    gph::Json pods = gph::Json::array();
+    for (const gph::PodEntry& pe : w.pods) pods.push(pe.name);
+    j.set("pods", pods);
+    j.set("shape", gph::Json::array());
+    return put(j.dump(), out, cap);
+  } catch (const std::exception& e) {
+    return put(std::string("{\"ok\":false,\"error\":\"") + gph::json_escape(e.what()) + "\"}", out, cap);
+  }
+}

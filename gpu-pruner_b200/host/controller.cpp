@@ -1,5 +1,6 @@
 #include "controller.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -105,42 +106,13 @@ std::unique_ptr<WindowSource> make_window_source(const std::string& url) {
 }
 
 // ---- controller -----------------------------------------------------------------------------------------
-Controller::Controller(const Cli& args, KubeApi* kube, Logger log, Clock clock)
-    : args_(args), kube_(kube), log_(log), clock_(std::move(clock)),
+Controller::Controller(const Cli& args, KubeApi* kube, VerdictEngine* engine, Logger log, Clock clock)
+    : args_(args), kube_(kube), engine_(engine), log_(log), clock_(std::move(clock)),
       enabled_(get_enabled_resources(args.enabled_resources)) {}
-
-Controller::~Controller() {
-  if (ctx_) gpr_destroy(ctx_);
-}
-
-bool Controller::ensure_engine(const Window& w) {
-  const uint64_t cells = (uint64_t)w.P * w.G * w.T;
-  const bool need_power = !w.power.empty();
-  if (ctx_ && cells <= cap_cells_ && (!need_power || cap_power_)) return true;
-  if (ctx_) gpr_destroy(ctx_), ctx_ = nullptr;
-  gpr_config cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.struct_size = sizeof cfg;
-  cfg.device = args_.gpu_device;
-  // head-room so that a growing cluster does not re-create the context every tick
-  cfg.max_pods = std::max<uint32_t>(64, w.P + w.P / 4);
-  cfg.max_gpus = std::max<uint32_t>(1, w.G);
-  cfg.max_samples = std::max<uint32_t>(1, w.T);
-  cfg.flags = need_power ? GPR_F_POWER_PLANE : 0;
-  const int rc = gpr_create(&cfg, &ctx_);
-  if (rc != GPR_OK) {
-    engine_error_ = std::string("idle engine unavailable (") + std::to_string(rc) + "): " + gpr_last_error(nullptr);
-    ctx_ = nullptr;
-    return false;
-  }
-  cap_cells_ = (uint64_t)cfg.max_pods * cfg.max_gpus * cfg.max_samples;
-  cap_power_ = need_power;
-  return true;
-}
 
 TickResult Controller::run_query_and_scale(const Window& w) {
   TickResult out;
-  const uint32_t P = w.P, G = w.G, T = w.T;
+  const uint32_t P = w.P, G = w.G;
   const uint32_t W = (P + 31) / 32;
   std::vector<uint32_t> dbits(std::max<uint32_t>(W, 1), 0), cbits(std::max<uint32_t>(W, 1), 0);
   std::vector<float> smax((size_t)P * G + 1, 0.f);
@@ -190,39 +162,31 @@ TickResult Controller::run_query_and_scale(const Window& w) {
   }
 
   if (P > 0) {
-    if (!ensure_engine(w)) {
-      out.error = engine_error_;
+    VerdictRequest rq;
+    rq.window = &w;
+    rq.power_on = !w.power.empty() && args_.power_threshold && *args_.power_threshold != 0.0;
+    rq.power_threshold = rq.power_on ? *args_.power_threshold : 0.0;
+    rq.eligible = kube_ ? eligible.data() : nullptr;
+    rq.created_ts = kube_ ? created.data() : nullptr;
+    rq.cutoff_ts = cutoff;
+    rq.gpu_device = args_.gpu_device;
+    Verdict v;
+    std::string err;
+    if (!engine_ || !engine_->decide(rq, &v, &err)) {
+      out.error = "Failed to run query! " + (engine_ ? err : std::string("no idle engine"));
       return out;
     }
-    gpr_window win;
-    memset(&win, 0, sizeof win);
-    win.struct_size = sizeof win;
-    win.mem_kind = GPR_MEM_HOST;
-    win.util = w.util.data();
-    const bool power_on = !w.power.empty() && args_.power_threshold && *args_.power_threshold != 0.0;
-    win.power = power_on ? w.power.data() : nullptr;
-    win.power_threshold = power_on ? *args_.power_threshold : 0.0;
-    win.eligible = kube_ ? eligible.data() : nullptr;
-    win.created_ts = kube_ ? created.data() : nullptr;
-    win.cutoff_ts = cutoff;
-    win.n_pods = P, win.n_gpus = G, win.n_samples = T;
-    gpr_result res;
-    memset(&res, 0, sizeof res);
-    res.struct_size = sizeof res;
-    res.out_mem_kind = GPR_MEM_HOST;
-    res.decision_bits = dbits.data();
-    res.candidate_bits = cbits.data();
-    res.series_max = smax.data();
-    const int rc = gpr_decide(ctx_, &win, &res);
-    if (rc != GPR_OK) {
-      out.error = std::string("Failed to run query! idle engine (") + std::to_string(rc) + "): " +
-                  gpr_last_error(ctx_);
+    if (v.decision_bits.size() < W || v.candidate_bits.size() < W || v.series_max.size() < (size_t)P * G) {
+      out.error = "Failed to run query! idle engine returned a short result";
       return out;
     }
-    out.qr.num_pods = (size_t)res.n_series;
-    out.kernel_ms = res.kernel_ms;
-    out.n_candidates = res.n_candidates;
-    out.n_decisions = res.n_decisions;
+    std::copy(v.decision_bits.begin(), v.decision_bits.begin() + W, dbits.begin());
+    std::copy(v.candidate_bits.begin(), v.candidate_bits.begin() + W, cbits.begin());
+    std::copy(v.series_max.begin(), v.series_max.begin() + (size_t)P * G, smax.begin());
+    out.qr.num_pods = (size_t)v.n_series;
+    out.kernel_ms = v.kernel_ms;
+    out.n_candidates = v.n_candidates;
+    out.n_decisions = v.n_decisions;
   }
 
   // candidates -> PodMetricData rows (first idle series of the pod wins, main.rs:430-435)

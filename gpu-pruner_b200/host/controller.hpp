@@ -12,7 +12,6 @@
 #include <unordered_set>
 #include <vector>
 
-#include "../../include/gpr.h"
 #include "cli.hpp"
 #include "ingest.hpp"
 #include "kube.hpp"
@@ -56,6 +55,32 @@ struct TickResult {
   uint64_t n_candidates = 0, n_decisions = 0;
 };
 
+// The idle decision itself, behind an interface so that the controller logic does not depend on how
+// it is produced.  The product implementation is GprVerdictEngine (gpr_engine.cpp: libgpr.so, CUDA,
+// no CPU fallback); the test-suite injects recorded verdicts through the C test API to exercise the
+// gates / owner walk / dedup / request emission without a GPU.
+struct VerdictRequest {
+  const Window* window = nullptr;
+  const uint8_t* eligible = nullptr;     // [P] or null
+  const int64_t* created_ts = nullptr;   // [P] or null
+  int64_t cutoff_ts = 0;
+  bool power_on = false;
+  double power_threshold = 0.0;
+  int gpu_device = 0;
+};
+struct Verdict {
+  std::vector<uint32_t> decision_bits, candidate_bits;   // ceil(P/32) words
+  std::vector<float> series_max;                         // [P*G]
+  uint64_t n_series = 0, n_candidates = 0, n_decisions = 0;
+  double kernel_ms = 0;
+};
+class VerdictEngine {
+ public:
+  virtual ~VerdictEngine() = default;
+  virtual bool decide(const VerdictRequest& rq, Verdict* out, std::string* error) = 0;
+};
+std::unique_ptr<VerdictEngine> make_gpr_engine();   // gpr_engine.cpp (links libgpr.so)
+
 // Where the window comes from, selected by the scheme of --prometheus-url.
 class WindowSource {
  public:
@@ -66,8 +91,7 @@ std::unique_ptr<WindowSource> make_window_source(const std::string& url);
 
 class Controller {
  public:
-  Controller(const Cli& args, KubeApi* kube, Logger log, Clock clock);
-  ~Controller();
+  Controller(const Cli& args, KubeApi* kube, VerdictEngine* engine, Logger log, Clock clock);
   Controller(const Controller&) = delete;
 
   // one pass of main.rs:390-570 on an already-fetched window
@@ -75,19 +99,14 @@ class Controller {
   // main.rs:286-330: one-shot or daemon loop with the consecutive-failure budget; returns exit code
   int run(WindowSource& src);
 
-  const std::string& engine_error() const { return engine_error_; }
   uint64_t query_successes = 0, query_failures = 0, scale_successes = 0, scale_failures = 0;
 
  private:
-  bool ensure_engine(const Window& w);
   Cli args_;
   KubeApi* kube_;
+  VerdictEngine* engine_;
   Logger log_;
   Clock clock_;
-  gpr_ctx* ctx_ = nullptr;
-  uint64_t cap_cells_ = 0;
-  bool cap_power_ = false;
-  std::string engine_error_;
   uint8_t enabled_;
 };
 

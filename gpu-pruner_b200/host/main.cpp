@@ -31,6 +31,7 @@ int main(int argc, char** argv) {
   std::unique_ptr<gph::FixtureKubeApi> kube;
   if (cli.kube_fixture) kube = std::make_unique<gph::FixtureKubeApi>(*cli.kube_fixture);
   std::unique_ptr<gph::WindowSource> src = gph::make_window_source(cli.prometheus_url);
-  gph::Controller ctl(cli, kube.get(), log, gph::system_clock());
+  std::unique_ptr<gph::VerdictEngine> engine = gph::make_gpr_engine();   // libgpr.so; no CPU fallback
+  gph::Controller ctl(cli, kube.get(), engine.get(), log, gph::system_clock());
   return ctl.run(*src);
 }

@@ -123,3 +123,16 @@ def ingest(util, prof=None, power=None, duration_min=30, step=0, t_end=0):
                           None if w is None else w.ctypes.data_as(C.c_void_p), meta, CAP)
     assert rc == 0
     return u, w, json.loads(meta.value.decode())
+
+
+def run_tick(argv, candidate_bits, series_max, n_series, fail=False, log_path=""):
+    """one Controller::run_query_and_scale with a RECORDED verdict (no GPU): see capi.cpp gph_run_tick"""
+    import numpy as np
+    blob, n = _args(argv)
+    cb = np.ascontiguousarray(candidate_bits, dtype=np.uint32)
+    sm = np.ascontiguousarray(series_max, dtype=np.float32)
+    buf = C.create_string_buffer(CAP)
+    rc = lib().gph_run_tick(blob, n, cb.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p),
+                            C.c_ulonglong(int(n_series)), int(fail), log_path.encode(), buf, CAP)
+    assert rc >= 0, buf.value.decode()
+    return json.loads(buf.value.decode())
