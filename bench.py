@@ -220,14 +220,30 @@ def run_cuda(args):
     profiling_only = bool(args.strong_total)      # c4 / c5: device-resident timing only
     eng = g.IdleEngine(device=local, max_pods=0 if profiling_only else P, max_gpus=G, max_samples=T,
                        kernel=args.kernel)
+    if world > 1 and args.collective == "p2p":
+        # fused: the fold kernel itself pushes the words to the peers over NVLink.  If peer mapping is
+        # not possible on this box (all ranks must agree), use the NCCL allgather instead.
+        ok = 1
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, eng.p2p_init(rank, world, P))
+            eng.p2p_attach(handles)
+        except g.GprError as ex:
+            ok = 0
+            print(f"[rank {rank}] peer-memory exchange unavailable ({ex}); falling back to ncclAllGather",
+                  file=sys.stderr)
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if ok:   # this rank attached but another could not: start over without the fused exchange
+                eng.close()
+                eng = g.IdleEngine(device=local, max_pods=0 if profiling_only else P, max_gpus=G,
+                                   max_samples=T, kernel=args.kernel)
+            args.collective = "nccl"
     if world > 1 and args.collective == "nccl":
         uid = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0], rank, world)
-    elif world > 1:   # fused: the decision kernel itself pushes the words to the peers over NVLink
-        handles = [None] * world
-        dist.all_gather_object(handles, eng.p2p_init(rank, world, P))
-        eng.p2p_attach(handles)
 
     # ---- synthetic windows, generated on the owning GPU (no scatter) --------------------------
     wins = []
