@@ -102,7 +102,7 @@ struct gpr_ctx {
   int tma_depth_max = 3;
   int tma_warps = 16;
   int tma_chunk_bytes = 8192;
-  size_t chunk_bytes = 8u << 20;
+  size_t chunk_bytes = 32u << 20;
 
   // capacity for host windows
   uint32_t max_pods = 0, max_gpus = 0, max_samples = 0;
@@ -272,6 +272,9 @@ int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok, bool pdl) {
   // not 16-byte aligned or have T % 4 != 0 cannot be bulk-copied and take the LDG kernel
   int variant = ctx->variant == GPR_KERNEL_AUTO ? GPR_KERNEL_TMA : ctx->variant;
   if (variant == GPR_KERNEL_TMA && !tma_ok) variant = GPR_KERNEL_LDG;
+  if (variant == GPR_KERNEL_TMA &&
+      tma_smem_bytes(tma_layout(ctx, rp.T, ctx->tma_warps), ctx->tma_warps) > kTmaSmemBudget)
+    variant = GPR_KERNEL_LDG;  // a tuning override (GPR_TMA_WARPS / GPR_TMA_CHUNK) that does not fit
   cudaError_t e;
   if (variant == GPR_KERNEL_TMA) {
     const int nw = ctx->tma_warps;
@@ -747,7 +750,7 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     if (c->tma_warps != 4 && c->tma_warps != 8 && c->tma_warps != 16 && c->tma_warps != 32)
       c->tma_warps = 16;
     c->tma_chunk_bytes = std::min(65536, std::max(512, env_int("GPR_TMA_CHUNK", 8192))) & ~15;
-    c->chunk_bytes = (size_t)std::max(1, env_int("GPR_CHUNK_MB", 8)) << 20;
+    c->chunk_bytes = (size_t)std::max(1, env_int("GPR_CHUNK_MB", 32)) << 20;  // sweep: profiles/README.md
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kTmaSmemBudget));
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
