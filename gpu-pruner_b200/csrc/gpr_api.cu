@@ -142,6 +142,12 @@ struct gpr_ctx {
   float* d_res_util = nullptr;
   float* d_res_power = nullptr;
   uint32_t res_P = 0, res_G = 0, res_T = 0, res_head = 0;
+  // optional index (GPR_F_BLOCK_INDEX): max of every 64-sample block of every resident row, kept up to
+  // date by gpr_append.  max-of-block-maxima == max-of-samples (NaN = block without a sample), so the
+  // index is itself a window tensor with ceil(T/64) "samples" per series and the same kernels decide on it
+  float* d_idx_util = nullptr;
+  float* d_idx_power = nullptr;
+  uint32_t idx_ld = 0;      // padded to a multiple of 4 (TMA-able rows), padding stays NaN
   float* d_cols = nullptr;
   size_t cols_cap = 0;
 
@@ -332,6 +338,11 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
     P = ctx->res_P, G = ctx->res_G, T = ctx->res_T, ld = T;
     util = ctx->d_res_util;
     power = ctx->d_res_power;
+    if (ctx->d_idx_util) {  // decide on the block-maxima index: same verdict, T/64 of the bytes
+      T = ctx->idx_ld, ld = ctx->idx_ld;
+      util = ctx->d_idx_util;
+      power = ctx->d_idx_power;
+    }
   }
   if (in_kind != GPR_MEM_HOST && in_kind != GPR_MEM_DEVICE)
     return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", in_kind);
@@ -612,8 +623,22 @@ int sync_impl(gpr_ctx* ctx) {
   return GPR_OK;
 }
 
-__global__ void k_append(float* __restrict__ dst, const float* __restrict__ src, uint32_t n_rows,
-                         uint32_t T, uint32_t head, uint32_t n_new, uint64_t ld_src) {
+constexpr uint32_t kIdxBlock = 64;
+
+// NaN-skipping max of block b (samples [64 b, 64 b + 64) of one resident row), one warp
+__device__ __forceinline__ float block_max_warp(const float* row, uint32_t T, uint32_t b, int lane) {
+  const uint32_t t0 = b * kIdxBlock;
+  float m = gpr::nan_f();
+  for (uint32_t t = t0 + lane; t < min(T, t0 + kIdxBlock); t += 32) m = fmaxf(m, row[t]);
+  return gpr::warp_max(m);
+}
+
+// Scatter n_new columns of every row into the time ring; with an index, recompute the maxima of the
+// blocks the new columns landed in (the overwritten samples may have been the old maximum).
+__global__ void __launch_bounds__(128) k_append(float* __restrict__ dst, const float* __restrict__ src,
+                                               uint32_t n_rows, uint32_t T, uint32_t head, uint32_t n_new,
+                                               uint64_t ld_src, float* __restrict__ idx, uint32_t idx_ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   for (uint32_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
     float* out = dst + (size_t)r * T;
     const float* in = src + (size_t)r * ld_src;
@@ -622,7 +647,39 @@ __global__ void k_append(float* __restrict__ dst, const float* __restrict__ src,
       if (t >= T) t -= T;
       out[t] = in[j];
     }
+    if (idx) {
+      __syncthreads();  // this CTA's column stores are visible to its own warps
+      // touched blocks: those of [head, head + n_new) modulo T — at most two contiguous runs
+      const uint32_t n_blocks = (T + kIdxBlock - 1) / kIdxBlock;
+      const uint32_t first = head / kIdxBlock;
+      const uint32_t span_end = head + n_new;  // exclusive, may exceed T (wraps)
+      const uint32_t last = (min(span_end, T) - 1) / kIdxBlock;
+      for (uint32_t b = first + warp; b <= last; b += n_warps) {
+        const float m = block_max_warp(out, T, b, lane);
+        if (lane == 0) idx[(size_t)r * idx_ld + b] = m;
+      }
+      if (span_end > T) {  // wrapped part [0, span_end - T)
+        const uint32_t wlast = min((span_end - T - 1) / kIdxBlock, n_blocks - 1);
+        for (uint32_t b = warp; b <= wlast; b += n_warps) {
+          const float m = block_max_warp(out, T, b, lane);
+          if (lane == 0) idx[(size_t)r * idx_ld + b] = m;
+        }
+      }
+      __syncthreads();
+    }
   }
+}
+
+// full rebuild of the index (after the caller wrote the resident planes directly)
+__global__ void __launch_bounds__(128) k_reindex(const float* __restrict__ plane, uint32_t n_rows, uint32_t T,
+                                                float* __restrict__ idx, uint32_t idx_ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const uint32_t n_blocks = (T + kIdxBlock - 1) / kIdxBlock;
+  for (uint32_t r = blockIdx.x; r < n_rows; r += gridDim.x)
+    for (uint32_t b = warp; b < n_blocks; b += n_warps) {
+      const float m = block_max_warp(plane + (size_t)r * T, T, b, lane);
+      if (lane == 0) idx[(size_t)r * idx_ld + b] = m;
+    }
 }
 
 }  // namespace
@@ -659,7 +716,8 @@ void gpr_destroy(gpr_ctx* ctx) {
   void* dev[] = {ctx->d_util_stage, ctx->d_power_stage, ctx->d_elig_stage, ctx->d_created_stage,
                  ctx->d_masks[0],   ctx->d_masks[1],    ctx->d_bits,       ctx->d_gather,
                  ctx->d_smax,       ctx->d_acc,         ctx->d_tickets,    ctx->d_done,
-                 ctx->d_flush,      ctx->d_res_util,    ctx->d_res_power,  ctx->d_cols};
+                 ctx->d_flush,      ctx->d_res_util,    ctx->d_res_power,  ctx->d_cols,
+                 ctx->d_idx_util,   ctx->d_idx_power};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -856,8 +914,42 @@ int gpr_resident_init(gpr_ctx* ctx, uint32_t P, uint32_t G, uint32_t T, uint32_t
     CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_res_power), bytes));
     CU(cudaMemsetAsync(ctx->d_res_power, 0xFF, bytes, ctx->stream));
   }
+  if (ctx->d_idx_util) CU(cudaFree(ctx->d_idx_util));
+  if (ctx->d_idx_power) CU(cudaFree(ctx->d_idx_power));
+  ctx->d_idx_util = ctx->d_idx_power = nullptr, ctx->idx_ld = 0;
+  if (flags & GPR_F_BLOCK_INDEX) {
+    ctx->idx_ld = (((T + kIdxBlock - 1) / kIdxBlock) + 3u) & ~3u;
+    const size_t ib = (size_t)P * G * ctx->idx_ld * sizeof(float);
+    CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_idx_util), ib));
+    CU(cudaMemsetAsync(ctx->d_idx_util, 0xFF, ib, ctx->stream));
+    if (flags & GPR_F_POWER_PLANE) {
+      CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_idx_power), ib));
+      CU(cudaMemsetAsync(ctx->d_idx_power, 0xFF, ib, ctx->stream));
+    }
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->res_P = P, ctx->res_G = G, ctx->res_T = T, ctx->res_head = 0;
+  return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
+int gpr_resident_reindex(gpr_ctx* ctx) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
+  if (!ctx->d_idx_util) return GPR_OK;  // no index to maintain
+  CU(cudaSetDevice(ctx->device));
+  ctx->last_was_reduce = false;
+  const size_t rows = (size_t)ctx->res_P * ctx->res_G;
+  const uint32_t grid = (uint32_t)std::min<size_t>(rows, (size_t)ctx->sm_count * 16);
+  k_reindex<<<grid, 128, 0, ctx->stream>>>(ctx->d_res_util, (uint32_t)rows, ctx->res_T, ctx->d_idx_util,
+                                           ctx->idx_ld);
+  if (ctx->d_res_power)
+    k_reindex<<<grid, 128, 0, ctx->stream>>>(ctx->d_res_power, (uint32_t)rows, ctx->res_T, ctx->d_idx_power,
+                                             ctx->idx_ld);
+  ctx->launches += ctx->d_res_power ? 2 : 1;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
   return GPR_OK;
   GPR_CATCH(ctx)
 }
@@ -882,6 +974,7 @@ int gpr_append(gpr_ctx* ctx, const float* util_cols, const float* power_cols, ui
   const uint32_t n_eff = n_new - skip;
   const float* planes_in[2] = {util_cols, ctx->d_res_power ? power_cols : nullptr};
   float* planes_out[2] = {ctx->d_res_util, ctx->d_res_power};
+  float* planes_idx[2] = {ctx->d_idx_util, ctx->d_idx_power};
   for (int pl = 0; pl < 2; ++pl) {
     if (!planes_in[pl]) continue;
     const float* src = planes_in[pl] + skip;
@@ -900,7 +993,8 @@ int gpr_append(gpr_ctx* ctx, const float* util_cols, const float* power_cols, ui
     }
     const uint32_t grid = (uint32_t)std::min<size_t>(rows, (size_t)ctx->sm_count * 16);
     k_append<<<grid, 128, 0, ctx->stream>>>(planes_out[pl], src, (uint32_t)rows, T,
-                                            (ctx->res_head + skip) % T, n_eff, ld_dev);
+                                            (ctx->res_head + skip) % T, n_eff, ld_dev, planes_idx[pl],
+                                            ctx->idx_ld);
     ctx->launches++;
     CU(cudaGetLastError());
   }

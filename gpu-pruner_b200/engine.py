@@ -212,9 +212,12 @@ class IdleEngine:
         self._keep.clear()
 
     # ---- resident window (daemon mode) --------------------------------------------------------
-    def resident_init(self, P: int, G: int, T: int, power_plane: bool = False):
-        self._check(self._lib.gpr_resident_init(self._h, P, G, T,
-                                                ffi.GPR_F_POWER_PLANE if power_plane else 0))
+    def resident_init(self, P: int, G: int, T: int, power_plane: bool = False, block_index: bool = False):
+        flags = (ffi.GPR_F_POWER_PLANE if power_plane else 0) | (ffi.GPR_F_BLOCK_INDEX if block_index else 0)
+        self._check(self._lib.gpr_resident_init(self._h, P, G, T, flags))
+
+    def resident_reindex(self):
+        self._check(self._lib.gpr_resident_reindex(self._h))
 
     def append(self, util_cols, power_cols=None, n_new: Optional[int] = None, row_stride: int = 0,
                mem_kind: int = ffi.GPR_MEM_HOST):

@@ -18,6 +18,7 @@ ERROR_NAMES = {
 GPR_MEM_HOST, GPR_MEM_DEVICE = 0, 1
 GPR_KERNEL_AUTO, GPR_KERNEL_LDG, GPR_KERNEL_TMA = 0, 1, 2
 GPR_F_POWER_PLANE = 0x1
+GPR_F_BLOCK_INDEX = 0x2
 GPR_UNIQUE_ID_BYTES = 128
 GPR_P2P_HANDLE_BYTES = 64
 
@@ -73,6 +74,7 @@ PROTOTYPES = {
     "gpr_decide_batch_async": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result), C.c_uint32]),
     "gpr_resident_init": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "gpr_append": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_int32]),
+    "gpr_resident_reindex": (C.c_int, [_P]),
     "gpr_decide_resident": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result)]),
     "gpr_resident_planes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gpr_comm_unique_id": (C.c_int, [_P]),

@@ -79,6 +79,9 @@ enum {
 
 /* ---- gpr_config.flags ---------------------------------------------------------------- */
 #define GPR_F_POWER_PLANE 0x1u /* reserve staging for the power plane (host windows)      */
+#define GPR_F_BLOCK_INDEX 0x2u /* gpr_resident_init: keep the max of every 64-sample block of the
+                                  resident rows up to date in gpr_append and decide on that index —
+                                  identical verdict and series_max, 1/64 of the bytes per tick      */
 
 typedef struct gpr_ctx gpr_ctx;
 
@@ -184,10 +187,13 @@ GPR_API int gpr_decide_batch_async(gpr_ctx *ctx, const gpr_window *windows, gpr_
  * arrived since the previous tick and rescans.  max is order-independent so ring order is
  * irrelevant to the verdict.                                                              */
 GPR_API int gpr_resident_init(gpr_ctx *ctx, uint32_t n_pods, uint32_t n_gpus, uint32_t n_samples,
-                      uint32_t flags /* GPR_F_POWER_PLANE */);
+                      uint32_t flags /* GPR_F_POWER_PLANE | GPR_F_BLOCK_INDEX */);
 /* new columns laid out [p][g][n_new] (row_stride 0 = n_new); power_cols may be NULL.      */
 GPR_API int gpr_append(gpr_ctx *ctx, const float *util_cols, const float *power_cols, uint32_t n_new,
                uint64_t row_stride, int32_t mem_kind);
+/* rebuild the GPR_F_BLOCK_INDEX index after writing the resident planes directly
+ * (gpr_resident_planes); a no-op without an index                                          */
+GPR_API int gpr_resident_reindex(gpr_ctx *ctx);
 /* win->util / win->power are ignored (resident planes are used); gates come from win.     */
 GPR_API int gpr_decide_resident(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
 /* device pointers of the resident planes (for generators / inspection); power may be NULL */

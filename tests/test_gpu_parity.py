@@ -318,8 +318,9 @@ def test_batch_entry_point(variant, engines, oracle_c):
                (r.n_series, r.n_candidates, r.n_decisions), exp)
 
 
+@pytest.mark.parametrize("block_index", [False, True], ids=["rescan", "block-index"])
 @pytest.mark.parametrize("variant", VARIANTS)
-def test_resident_window_ring(variant, engines, oracle_c):
+def test_resident_window_ring(variant, block_index, engines, oracle_c):
     """daemon mode: append columns tick by tick into the HBM ring, rescan, compare with the
     oracle on the window a fresh range query would have returned"""
     eng = engines[variant]
@@ -327,7 +328,7 @@ def test_resident_window_ring(variant, engines, oracle_c):
     total = 900
     full = oracle_c.synth_fill(seed, 0, 0, P, G, total)       # one long history
     fullw = oracle_c.synth_fill(seed, 1, 0, P, G, total)
-    eng.resident_init(P, G, T, power_plane=True)
+    eng.resident_init(P, G, T, power_plane=True, block_index=block_index)
     W = (P + 31) // 32
     db = np.zeros(W, np.uint32)
     cb = np.zeros(W, np.uint32)
@@ -345,6 +346,31 @@ def test_resident_window_ring(variant, engines, oracle_c):
         winw[:, :, : t - lo] = fullw[:, :, lo:t]
         exp = oracle_c.decide(win, winw, power_threshold=150.0)
         _check(db, cb, (r.n_series, r.n_candidates, r.n_decisions), exp, sm)
+
+
+@pytest.mark.parametrize("T", [64, 100, 240, 7200])
+def test_block_index_rebuild_after_direct_writes(T, engines, oracle_c):
+    """GPR_F_BLOCK_INDEX: the index follows gpr_append by itself and gpr_resident_reindex after the
+    caller filled the planes directly; deciding on it equals deciding on the full rows"""
+    eng = engines["tma"]
+    seed, P, G = 0x5EED0005, 300, 4
+    eng.resident_init(P, G, T, block_index=True)
+    u_ptr, _, ld = eng.resident_planes()
+    assert ld == T
+    eng.synth_fill(seed, 0, u_ptr, 0, P, G, T)            # written behind the library's back ...
+    eng.resident_reindex()                                # ... so the index must be rebuilt
+    W = (P + 31) // 32
+    db, cb, sm = np.zeros(W, np.uint32), np.zeros(W, np.uint32), np.zeros((P, G), np.float32)
+    r = eng.decide_ptr(None, 0, 0, 0, db, candidate_bits=cb, series_max=sm, in_kind=0, out_kind=0, resident=True)
+    full = oracle_c.synth_fill(seed, 0, 0, P, G, T)
+    _check(db, cb, (r.n_series, r.n_candidates, r.n_decisions), oracle_c.decide(full), sm)
+    # overwrite the burst of a few series through gpr_append: their block maxima must drop again
+    n_new = min(T, 70)
+    cols = np.zeros((P, G, n_new), np.float32)
+    eng.append(cols)
+    full = np.concatenate([full[:, :, n_new:], cols], axis=2) if n_new < T else cols
+    r = eng.decide_ptr(None, 0, 0, 0, db, candidate_bits=cb, series_max=sm, in_kind=0, out_kind=0, resident=True)
+    _check(db, cb, (r.n_series, r.n_candidates, r.n_decisions), oracle_c.decide(full), sm)
 
 
 def test_error_paths(engines):

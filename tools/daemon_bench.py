@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--samples", type=int, default=7200)
     ap.add_argument("--new", type=int, default=180)
     ap.add_argument("--ticks", type=int, default=5)
-    ap.add_argument("--check", action="store_true", help="compare the last tick with the CPU oracle (slow)")
+    ap.add_argument("--index", action="store_true", help="GPR_F_BLOCK_INDEX: decide on 64-sample block maxima")
     a = ap.parse_args()
     P, G, T, n_new = a.pods, a.gpus_per_pod, a.samples, a.new
     seed = 0x5EED0005
@@ -44,9 +44,10 @@ def main():
         dist.all_gather_object(handles, eng.p2p_init(rank, world, P))
         eng.p2p_attach(handles)
     t0 = time.perf_counter()
-    eng.resident_init(P, G, T)
+    eng.resident_init(P, G, T, block_index=a.index)
     u_ptr, _, ld = eng.resident_planes()
     eng.synth_fill(seed, 0, u_ptr, rank * P, P, G, T)   # the history a first full range query would load
+    eng.resident_reindex()
     torch.cuda.synchronize()
     init_s = time.perf_counter() - t0
     # the columns of the next ticks, staged in pinned host memory like an ingest thread would
@@ -79,7 +80,7 @@ def main():
         eng.close()
         return
     out = {"config": f"{world} GPU(s) x [{P} pods x {G} x {T} resident ({bytes_scan / 1e9:.1f} GB)], {n_new} new columns/tick",
-           "n_gpus": world,
+           "n_gpus": world, "block_index": bool(a.index),
            "init_fill_s": init_s, "ingest_ms": ing, "ingest_h2d_bytes": int(cols.nbytes),
            "ingest_GBps": cols.nbytes / ing / 1e6, "decide_ms": dec, "kernel_ms": ker,
            "rescan_GBps": bytes_scan / ker / 1e6, "tick_ms": ing + dec,
