@@ -141,8 +141,16 @@ void finish_shape(Window& w, const IngestOptions& opt, int64_t newest, int64_t m
   if (with_power) w.power.assign(cells, nan);
 }
 
+// timestamp in whole seconds; anything that is not a sane epoch time maps to "far outside any window"
+constexpr int64_t kBadTs = std::numeric_limits<int64_t>::min() / 4;
+inline int64_t ts_seconds(double t) {
+  if (!(t > -4e12 && t < 4e12)) return kBadTs;  // also NaN
+  return (int64_t)std::llround(t);
+}
+
 // column of timestamp ts, or -1 when it lies outside (t_end - N, t_end]
 inline int64_t column_of(const Window& w, int64_t ts) {
+  if (ts > w.t_end || ts < w.t_end - (int64_t)w.T * w.step - w.step) return -1;
   const int64_t back = (w.t_end - ts + w.step / 2) / w.step;  // 0 = newest column
   if (ts > w.t_end || back < 0 || back >= (int64_t)w.T) return -1;
   return (int64_t)w.T - 1 - back;
@@ -199,7 +207,12 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
       (is_power ? pseries : useries).push_back(RawSeries{p, slot, &vals});
       int64_t prev = kNoTs;
       for (const Json& tv : vals.items()) {
-        const int64_t ts = (int64_t)std::llround(tv[0].as_number());
+        // a sample is exactly [ <unix time>, "<value>" ]; anything else is a malformed response
+        // (both paths reject it, the tick then counts as a query failure, main.rs:310-321)
+        if (!tv.is_array() || tv.size() != 2 || !tv[0].is_number())
+          throw std::runtime_error("matrix response: sample is not [time, value]");
+        const int64_t ts = ts_seconds(tv[0].as_number());
+        if (ts == kBadTs) continue;
         newest = std::max(newest, ts);
         if (prev != kNoTs && ts > prev) min_step = std::min(min_step, ts - prev);
         prev = ts;
@@ -216,7 +229,7 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
       float* row = plane.data() + ((size_t)rs.pod * w.G + rs.slot) * w.T;
       for (const Json& tv : rs.values->items()) {
         ++w.stats.samples_in;
-        const int64_t col = column_of(w, (int64_t)std::llround(tv[0].as_number()));
+        const int64_t col = column_of(w, ts_seconds(tv[0].as_number()));
         if (col < 0) {
           ++w.stats.samples_out_of_window;
           continue;
@@ -514,7 +527,8 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
       for (const TextSeries& ts : list) {
         int64_t prev = kNoTs;
         for_each_sample(ts.vb, ts.ve, [&](double t, double) {
-          const int64_t ti = (int64_t)std::llround(t);
+          const int64_t ti = ts_seconds(t);
+          if (ti == kBadTs) return;
           newest = std::max(newest, ti);
           if (prev != kNoTs && ti > prev) min_step = std::min(min_step, ti - prev);
           prev = ti;
@@ -541,7 +555,7 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
         float* row = plane.data() + ((size_t)ts.pod * w.G + ts.slot) * w.T;
         for_each_sample(ts.vb, ts.ve, [&](double t, double v) {
           ++n_in;
-          const int64_t col = column_of(w, (int64_t)std::llround(t));
+          const int64_t col = column_of(w, ts_seconds(t));
           if (col < 0) {
             ++n_out;
             return;
@@ -552,10 +566,21 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
       IngestStats& s = st[(size_t)tid];
       s.samples_in += n_in, s.samples_out_of_window += n_out, s.tiny_values_clamped += n_tiny;
     };
+    // a malformed sample array must surface as an exception on the caller's thread, not terminate()
+    std::vector<std::string> errors((size_t)n_threads);
+    auto guarded = [&](int tid, bool sole_pass) {
+      try {
+        work(tid, sole_pass);
+      } catch (const std::exception& e) {
+        errors[(size_t)tid] = e.what();
+      }
+    };
     std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t, true);
-    work(0, true);
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(guarded, t, true);
+    guarded(0, true);
     for (std::thread& t : th) t.join();
+    for (const std::string& e : errors)
+      if (!e.empty()) throw std::runtime_error(e);
     work(0, false);  // duplicates of one group: sequential, order-independent merge
     for (const IngestStats& s : st) {
       w.stats.samples_in += s.samples_in;
