@@ -309,6 +309,7 @@ def run_cuda(args):
     value = samples_per_step / (ms_per_step * 1e-3)
 
     e2e_s_per_step, e2e_ok, e2e_steps = float("nan"), True, 0
+    e2e_u8 = None
     h_u = h_e = None
     if not profiling_only:
         # ---- timed region 2: end to end through gpr_decide() with pinned HOST buffers ----------------
@@ -337,6 +338,33 @@ def run_cuda(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s_per_step = float(t.item()) / e2e_steps
         barrier()
+
+        # ---- extra: the same call with the window in the compact wire format (GPR_FMT_U8B, one
+        # byte per sample; DCGM_FI_DEV_GPU_UTIL is an integer percentage) — reported beside `e2e`,
+        # never instead of it
+        if world == 1:
+            h_u8 = eng.host_array((P, G, T), np.uint8)
+            np.copyto(h_u8, np.where(np.isnan(h_u), 0, h_u + 1), casting="unsafe")
+            h_bits8 = eng.host_array((max(W_out, 1),), np.uint32)
+
+            def e2e_u8_step():
+                return eng.decide_ptr(h_u8, P, G, T, h_bits8, eligible=h_e, in_kind=0, out_kind=0,
+                                      blocking=True, util_format=g.ffi.GPR_FMT_U8B)
+
+            for _ in range(3):
+                e2e_u8_step()
+            u8_ok = bool(np.array_equal(h_bits8[:n_words_mine], gpu_bits))
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_u8_step()
+            torch.cuda.synchronize()
+            dt8 = (time.perf_counter() - t0) / e2e_steps
+            e2e_u8 = {"value": samples_per_step / dt8, "unit": UNIT, "pod_decisions_per_sec": PODS / dt8,
+                      "ms_per_step": dt8 * 1e3, "steps": e2e_steps,
+                      "h2d_bytes_per_step": int(h_u8.nbytes + h_e.nbytes), "d2h_bytes_per_step": int(W_out * 4 + 24),
+                      "api": "gpr_decide(ctx, window{mem_kind=HOST, util_format=GPR_FMT_U8B}, result{HOST})",
+                      "matches_device_path": u8_ok}
+            e2e_ok = e2e_ok and u8_ok
 
     # ---- extra: daemon steady state (--daemon-mode, --check-interval 180 s): the window stays
     # resident in HBM, a tick moves only the 180 new columns per series across PCIe and rescans.
@@ -401,6 +429,7 @@ def run_cuda(args):
                     "matches_device_path": e2e_ok},
             "single_decision_us": single_decision_us,
             "e2e_resident": resident,
+            "e2e_u8": e2e_u8,
             "gpu_launches": int(launches), "clocks": clocks,
             "parity": "unchecked (no cpu_baseline leg in this run; see tests/ -m gpu)",
             "device": eng.device_info()["name"],

@@ -282,7 +282,12 @@ int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok, bool pdl) {
       tma_smem_bytes(tma_layout(ctx, rp.T, ctx->tma_warps), ctx->tma_warps) > kTmaSmemBudget)
     variant = GPR_KERNEL_LDG;  // a tuning override (GPR_TMA_WARPS / GPR_TMA_CHUNK) that does not fit
   cudaError_t e;
-  if (variant == GPR_KERNEL_TMA) {
+  if (rp.util_u8) {  // biased-byte util plane: one kernel, any alignment (the power plane stays f32)
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctx->ldg_ctas_per_sm);
+    const uint32_t need = (rp.total_rows + kLdgWarps - 1) / kLdgWarps;
+    grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, need));
+    e = launch_ex(gpr::k_reduce_u8<kLdgWarps, 4>, grid, kLdgWarps * 32, 0, ctx->stream, pdl, rp);
+  } else if (variant == GPR_KERNEL_TMA) {
     const int nw = ctx->tma_warps;
     uint32_t grid = (uint32_t)ctx->sm_count;
     grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, (rp.total_rows + nw - 1) / nw));
@@ -302,13 +307,13 @@ int launch_reduce(gpr_ctx* ctx, gpr::ReduceParams& rp, bool tma_ok, bool pdl) {
   return GPR_OK;
 }
 
-int copy_rows_h2d(gpr_ctx* ctx, float* dst, const float* src, size_t n_rows, uint32_t T,
-                  uint64_t ld, cudaStream_t s) {
+int copy_rows_h2d(gpr_ctx* ctx, void* dst, const void* src, size_t n_rows, uint32_t T,
+                  uint64_t ld, size_t esize, cudaStream_t s) {
   if (n_rows == 0) return GPR_OK;
   if (ld == T) {
-    CU(cudaMemcpyAsync(dst, src, n_rows * (size_t)T * 4u, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dst, src, n_rows * (size_t)T * esize, cudaMemcpyHostToDevice, s));
   } else {
-    CU(cudaMemcpy2DAsync(dst, (size_t)T * 4u, src, (size_t)ld * 4u, (size_t)T * 4u, n_rows,
+    CU(cudaMemcpy2DAsync(dst, (size_t)T * esize, src, (size_t)ld * esize, (size_t)T * esize, n_rows,
                          cudaMemcpyHostToDevice, s));
   }
   return GPR_OK;
@@ -333,6 +338,9 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   const float* util = win->util;
   const float* power = win->power;
   int in_kind = win->mem_kind;
+  const bool u8 = !resident && win->util_format == GPR_FMT_U8B;
+  if (!resident && win->util_format != GPR_FMT_F32 && win->util_format != GPR_FMT_U8B)
+    return fail(ctx, GPR_E_INVALID, "bad util_format %u", win->util_format);
   if (resident) {
     if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
     P = ctx->res_P, G = ctx->res_G, T = ctx->res_T, ld = T;
@@ -510,6 +518,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
     rp.seg[0] = gpr::Segment{util, masks, smax_dev, S, 0u};
     rp.seg[1] = gpr::Segment{power, masks + P, nullptr, use_power ? S : 0u, 1u};
     rp.total_rows = S + (use_power ? S : 0u);
+    rp.util_u8 = u8 ? 1u : 0u;
     const bool tma_ok = (T % 4u) == 0 && (ld % 4u) == 0 && aligned16(util) &&
                         (!use_power || aligned16(power));
     if (P > 0) {
@@ -529,21 +538,27 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
     ctx->last_was_reduce = false;
     CU(cudaEventRecord(ctx->ev_join, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));
-    const size_t pod_bytes = (size_t)G * T * 4u * (use_power ? 2u : 1u);
+    const size_t usize = u8 ? 1u : 4u;  // bytes per util sample on the wire and in the staging plane
+    const size_t pod_bytes = (size_t)G * T * (usize + (use_power ? 4u : 0u));
     uint32_t chunk_pods = (uint32_t)std::max<size_t>(1, ctx->chunk_bytes / std::max<size_t>(pod_bytes, 1));
     uint32_t n_chunks = P ? (P + chunk_pods - 1) / chunk_pods : 0;
     rp.ld = T;  // staging is dense
+    rp.util_u8 = u8 ? 1u : 0u;
     const bool tma_ok = (T % 4u) == 0;
+    const char* util_bytes = reinterpret_cast<const char*>(util);
+    char* stage_bytes = reinterpret_cast<char*>(ctx->d_util_stage);
     for (uint32_t c = 0; c < n_chunks; ++c) {
       const uint32_t p0 = c * chunk_pods, p1 = std::min(P, p0 + chunk_pods);
       const size_t row0 = (size_t)p0 * G, n_rows = (size_t)(p1 - p0) * G;
-      float* du = ctx->d_util_stage + row0 * T;
-      if ((rc = copy_rows_h2d(ctx, du, util + row0 * ld, n_rows, T, ld, ctx->copy_stream)) != GPR_OK)
+      float* du = reinterpret_cast<float*>(stage_bytes + row0 * T * usize);
+      if ((rc = copy_rows_h2d(ctx, du, util_bytes + row0 * ld * usize, n_rows, T, ld, usize,
+                              ctx->copy_stream)) != GPR_OK)
         return rc;
       float* dp = nullptr;
       if (use_power) {
         dp = ctx->d_power_stage + row0 * T;
-        if ((rc = copy_rows_h2d(ctx, dp, power + row0 * ld, n_rows, T, ld, ctx->copy_stream)) != GPR_OK)
+        if ((rc = copy_rows_h2d(ctx, dp, power + row0 * ld, n_rows, T, ld, 4u, ctx->copy_stream)) !=
+            GPR_OK)
           return rc;
       }
       cudaEvent_t ev = ctx->ev_chunk[c % kMaxChunkEvents];

@@ -91,6 +91,7 @@ struct ReduceParams {
   float thr;          // smallest f32 >= (double) power threshold
   const unsigned long long* done;  // scratch-set guard, see wait_scratch_free
   unsigned long long need;
+  uint32_t util_u8;   // seg[0] rows are biased bytes (GPR_FMT_U8B), k_reduce_u8 only
 };
 
 #ifdef GPR_TIMELINE
@@ -431,6 +432,95 @@ __global__ void __launch_bounds__(WARPS * 32) k_reduce_ldg(ReduceParams p) {
   }
   TL_MARK(1);
   TL_MARK(2);
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce over biased bytes (GPR_FMT_U8B): 0 = no sample, b = value b - 1
+// ------------------------------------------------------------------------------------------
+// Same question, one byte per sample.  With the bias the whole row folds with OR: the window max
+// is 0 exactly when the OR of every byte of the row is 0x01 (some sample present, none above 0),
+// and no sample is present when it is 0x00 - one LOP3 per 8 bytes, so the kernel stays bound by
+// memory, not by emulated byte-SIMD max.  The true maximum (series_max) is only folded when the
+// caller asked for it.  Rows may start at any byte: byte head to 16-byte alignment, 128-bit
+// body, byte tail; absent (0) is the identity of both OR and max, so predicated-off loads are 0.
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// returns the window max as the f32 the other kernels would have produced (NaN = no sample);
+// without want_max any positive maximum is reported as 1.0f (only `== 0` is consumed)
+template <int U>
+__device__ __forceinline__ float row_max_u8(const uint8_t* __restrict__ row, uint32_t T, int lane,
+                                            bool want_max) {
+  uint32_t acc = 0, m4 = 0;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+  uint32_t head = (uint32_t)((16u - (a & 15u)) & 15u);
+  if (head > T) head = T;
+  uint32_t hb = 0, tb = 0;  // one head byte and one tail byte per lane (at most 15 of each)
+  if ((uint32_t)lane < head) hb = __ldg(row + lane);
+  const uint4* __restrict__ v = reinterpret_cast<const uint4*>(row + head);
+  const uint32_t nv = (T - head) >> 4;
+  for (uint32_t i = lane; i < nv; i += 32u * U) {
+    uint4 x[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint32_t k = i + 32u * j;
+      x[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (k < nv) x[j] = ldg_stream_u4(v + k);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      acc |= (x[j].x | x[j].y) | (x[j].z | x[j].w);
+      if (want_max) m4 = __vmaxu4(__vmaxu4(m4, x[j].x), __vmaxu4(__vmaxu4(x[j].y, x[j].z), x[j].w));
+    }
+  }
+  const uint32_t done = head + nv * 16u;
+  if (done + lane < T) tb = __ldg(row + done + lane);
+  acc |= hb | tb;
+  acc |= acc >> 16;
+  acc |= acc >> 8;
+  acc = __reduce_or_sync(0xffffffffu, acc & 0xffu);
+  if (acc == 0u) return nan_f();   // no sample in the window
+  if (acc == 1u) return 0.0f;      // samples present, none above 0
+  if (!want_max) return 1.0f;
+  m4 = __vmaxu4(m4, max(hb, tb));  // head / tail bytes are plain values: byte lane 0
+  uint32_t m = max(max(m4 & 0xffu, (m4 >> 8) & 0xffu), max((m4 >> 16) & 0xffu, m4 >> 24));
+  m = __reduce_max_sync(0xffffffffu, m);
+  return (float)(m - 1u);
+}
+
+template <int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32) k_reduce_u8(ReduceParams p) {
+  __shared__ unsigned int s_next;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  const uint32_t n_mine = cta_row_count(p.total_rows);
+  if (threadIdx.x == 0) s_next = WARPS;
+  __syncthreads();
+  uint32_t j = warp;
+  bool scratch_ok = false;
+  while (j < n_mine) {
+    uint32_t seg, local;
+    const float* frow = row_ptr(p, blockIdx.x + j * gridDim.x, seg, local);
+    float m;
+    if (seg == 0u && p.util_u8) {
+      const uint8_t* row = reinterpret_cast<const uint8_t*>(p.seg[0].base) + (size_t)local * p.ld;
+      m = row_max_u8<U>(row, p.T, lane, p.seg[0].smax != nullptr);
+    } else {
+      m = row_max_ldg<U>(frow, p.T, lane);
+    }
+    if (lane == 0) {
+      if (!scratch_ok) wait_scratch_free(p), scratch_ok = true;
+      publish_row(p, seg, local, m);
+      j = atomicAdd(&s_next, 1u);
+    }
+    j = __shfl_sync(0xffffffffu, j, 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -49,6 +49,22 @@ class Decision:
         return np.flatnonzero(flat)
 
 
+def to_biased_u8(util: np.ndarray) -> np.ndarray:
+    """f32 window (NaN = no sample) -> GPR_FMT_U8B bytes (0 = no sample, b = value + 1).  Raises if a
+    sample is not an integer in 0..254 (DCGM_FI_DEV_GPU_UTIL is an integer percentage)."""
+    util = np.asarray(util, dtype=np.float32)
+    present = ~np.isnan(util)
+    v = np.where(present, util, 0.0)
+    if not np.all((v >= 0) & (v <= 254) & (v == np.floor(v))):
+        raise ValueError("window is not representable in GPR_FMT_U8B (integers 0..254 or NaN)")
+    return np.where(present, v + 1, 0).astype(np.uint8)
+
+
+def from_biased_u8(b: np.ndarray) -> np.ndarray:
+    b = np.asarray(b, dtype=np.uint8)
+    return np.where(b == 0, np.float32("nan"), b.astype(np.float32) - 1).astype(np.float32)
+
+
 def _ptr(x) -> Optional[int]:
     """numpy array / torch tensor / int address / None -> address."""
     if x is None:
@@ -115,8 +131,9 @@ class IdleEngine:
 
     # ---- hot path ---------------------------------------------------------------------------
     def _window(self, util, power, eligible, created_ts, cutoff_ts, P, G, T, row_stride,
-                power_threshold, mem_kind) -> ffi.gpr_window:
+                power_threshold, mem_kind, util_format: int = ffi.GPR_FMT_F32) -> ffi.gpr_window:
         w = ffi.gpr_window()
+        w.util_format = util_format
         w.struct_size = C.sizeof(ffi.gpr_window)
         w.mem_kind = mem_kind
         w.util, w.power = _ptr(util), _ptr(power)
@@ -132,8 +149,10 @@ class IdleEngine:
                cutoff_ts: int = 0, power_threshold: Optional[float] = 0.0,
                want_candidates: bool = True, want_series_max: bool = False,
                world: int = 1) -> Decision:
-        """Blocking decision over a HOST window ``util[P, G, T]`` (float32, NaN = no sample)."""
-        util = np.ascontiguousarray(util, dtype=np.float32)
+        """Blocking decision over a HOST window ``util[P, G, T]`` (float32, NaN = no sample; or
+        uint8 in the biased byte format GPR_FMT_U8B, see :func:`to_biased_u8`)."""
+        fmt = ffi.GPR_FMT_U8B if getattr(util, "dtype", None) == np.uint8 else ffi.GPR_FMT_F32
+        util = np.ascontiguousarray(util, dtype=np.uint8 if fmt else np.float32)
         if util.ndim != 3:
             raise ValueError("util must be [pods, gpus, samples]")
         P, G, T = util.shape
@@ -146,7 +165,7 @@ class IdleEngine:
         if created_ts is not None:
             created_ts = np.ascontiguousarray(created_ts, dtype=np.int64)
         w = self._window(util, power, eligible, created_ts, cutoff_ts, P, G, T, 0,
-                         power_threshold, ffi.GPR_MEM_HOST)
+                         power_threshold, ffi.GPR_MEM_HOST, fmt)
         W = (P + 31) // 32 * world
         dbits = np.zeros(max(W, 1), dtype=np.uint32)
         cbits = np.zeros(max(W, 1), dtype=np.uint32) if want_candidates else None
@@ -163,11 +182,12 @@ class IdleEngine:
                    created_ts=None, cutoff_ts: int = 0, power_threshold: Optional[float] = 0.0,
                    candidate_bits=None, series_max=None, row_stride: int = 0,
                    in_kind: int = ffi.GPR_MEM_DEVICE, out_kind: int = ffi.GPR_MEM_DEVICE,
-                   blocking: bool = True, resident: bool = False) -> ffi.gpr_result:
+                   blocking: bool = True, resident: bool = False,
+                   util_format: int = ffi.GPR_FMT_F32) -> ffi.gpr_result:
         """Raw-pointer form (device tensors, pinned host buffers).  With ``blocking=False`` the
         call only enqueues; counters in the returned struct are valid after :meth:`sync`."""
         w = self._window(util, power, eligible, created_ts, cutoff_ts, P, G, T, row_stride,
-                         power_threshold, in_kind)
+                         power_threshold, in_kind, util_format)
         r = ffi.gpr_result()
         r.struct_size = C.sizeof(ffi.gpr_result)
         r.out_mem_kind = out_kind
@@ -191,7 +211,8 @@ class IdleEngine:
         for i, kw in enumerate(calls):
             w = self._window(kw["util"], kw.get("power"), kw.get("eligible"), kw.get("created_ts"),
                              kw.get("cutoff_ts", 0), kw["P"], kw["G"], kw["T"], kw.get("row_stride", 0),
-                             kw.get("power_threshold", 0.0), kw.get("in_kind", ffi.GPR_MEM_DEVICE))
+                             kw.get("power_threshold", 0.0), kw.get("in_kind", ffi.GPR_MEM_DEVICE),
+                             kw.get("util_format", ffi.GPR_FMT_F32))
             C.memmove(C.byref(wins, i * C.sizeof(ffi.gpr_window)), C.byref(w), C.sizeof(ffi.gpr_window))
             r = ress[i]
             r.struct_size = C.sizeof(ffi.gpr_result)

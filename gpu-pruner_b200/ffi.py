@@ -17,6 +17,7 @@ ERROR_NAMES = {
 }
 GPR_MEM_HOST, GPR_MEM_DEVICE = 0, 1
 GPR_KERNEL_AUTO, GPR_KERNEL_LDG, GPR_KERNEL_TMA = 0, 1, 2
+GPR_FMT_F32, GPR_FMT_U8B = 0, 1
 GPR_F_POWER_PLANE = 0x1
 GPR_F_BLOCK_INDEX = 0x2
 GPR_UNIQUE_ID_BYTES = 128
@@ -39,7 +40,7 @@ class gpr_window(C.Structure):
         ("eligible", C.c_void_p), ("created_ts", C.c_void_p),
         ("cutoff_ts", C.c_int64),
         ("n_pods", C.c_uint32), ("n_gpus", C.c_uint32), ("n_samples", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("util_format", C.c_uint32),
         ("row_stride", C.c_uint64), ("power_threshold", C.c_double),
     ]
 

@@ -77,6 +77,17 @@ enum {
   GPR_KERNEL_TMA = 2   /* cp.async.bulk (TMA) rows into an mbarrier-guarded smem ring     */
 };
 
+/* ---- sample format of gpr_window.util (gpr_window.util_format) ----------------------------
+ * DCGM_FI_DEV_GPU_UTIL is an integer percentage, so a caller that parses the range query itself
+ * can hand the window over at one byte per sample: a quarter of the PCIe / HBM bytes of the f32
+ * layout and the same verdict.  The power plane and the resident ring stay f32.               */
+enum {
+  GPR_FMT_F32 = 0,  /* f32, NaN = no sample                                               */
+  GPR_FMT_U8B = 1   /* biased u8: 0 = no sample, b in 1..255 = sample value b - 1 (0..254);
+                       a zero-filled buffer is an all-absent window, like a NaN-filled f32 one;
+                       `util` then points at bytes and row_stride counts bytes               */
+};
+
 /* ---- gpr_config.flags ---------------------------------------------------------------- */
 #define GPR_F_POWER_PLANE 0x1u /* reserve staging for the power plane (host windows)      */
 #define GPR_F_BLOCK_INDEX 0x2u /* gpr_resident_init: keep the max of every 64-sample block of the
@@ -103,7 +114,8 @@ typedef struct gpr_config {
  * One window = the range-vector result laid out densely.
  *
  *   n_gpus          series slots per pod, 1..32 (a pod cannot span nodes; GPR_E_UNSUPPORTED above).
- *   util[p][g][t]   f32, t fastest; NaN = "no sample" (stale / absent / scrape gap).
+ *   util[p][g][t]   f32, t fastest; NaN = "no sample" (stale / absent / scrape gap); or biased
+ *                   bytes when util_format = GPR_FMT_U8B (cast the pointer).
  *                   Restates DCGM_FI_DEV_GPU_UTIL{pod != ""}[Nm]   (query.promql.j2:16-20)
  *   power[p][g][t]  f32 or NULL.  Restates DCGM_FI_DEV_POWER_USAGE{...}[Nm]
  *                   (query.promql.j2:39-42).  Used only if power_threshold is "truthy".
@@ -128,7 +140,7 @@ typedef struct gpr_window {
   uint32_t n_pods;
   uint32_t n_gpus;
   uint32_t n_samples;
-  uint32_t reserved0;
+  uint32_t util_format;    /* GPR_FMT_*; ignored by gpr_decide_resident (the ring is f32)   */
   uint64_t row_stride;
   double power_threshold;
 } gpr_window;

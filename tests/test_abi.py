@@ -8,6 +8,7 @@ import subprocess
 import sys
 import textwrap
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -108,3 +109,17 @@ def test_product_package_never_imports_the_oracle():
                 assert m is None, f"{os.path.join(dp, f)} uses the oracle: {m.group(0)!r}"
     out = subprocess.run(["ldd", os.path.join(pkg, "libgpr.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_biased_u8_helpers_round_trip():
+    """GPR_FMT_U8B: 0 = no sample, b = value + 1; only integer samples 0..254 are representable"""
+    import gpu_pruner_b200 as g
+    u = np.array([[[0, np.nan, 100, 254, 1]]], np.float32)
+    b = g.to_biased_u8(u)
+    assert b.dtype == np.uint8 and b.tolist() == [[[1, 0, 101, 255, 2]]]
+    back = g.from_biased_u8(b)
+    assert np.array_equal(np.isnan(back), np.isnan(u)) and np.array_equal(np.nan_to_num(back), np.nan_to_num(u))
+    for bad in (0.5, -1.0, 255.0, np.inf):
+        with pytest.raises(ValueError):
+            g.to_biased_u8(np.array([bad], np.float32))
+    assert (g.ffi.GPR_FMT_F32, g.ffi.GPR_FMT_U8B) == (0, 1)
