@@ -10,7 +10,7 @@ import torch  # noqa: E402
 import gpu_pruner_b200 as g  # noqa: E402
 
 
-def run(variant, P, G, T, iters, rot, power=False):
+def run(variant, P, G, T, iters, rot, power=False, u8=False):
     eng = g.IdleEngine(device=0, kernel=variant)
     wins = []
     for i in range(rot):
@@ -20,12 +20,15 @@ def run(variant, P, G, T, iters, rot, power=False):
         if power:
             w = torch.empty((P, G, T), dtype=torch.float32, device="cuda:0")
             eng.synth_fill(0x5EED0002 + i, 1, w, 0, P, G, T)
+        if u8:   # GPR_FMT_U8B: 0 = no sample, b = value + 1
+            u = torch.where(torch.isnan(u), torch.zeros_like(u), u + 1).to(torch.uint8)
         wins.append((u, w))
+    fmt = g.ffi.GPR_FMT_U8B if u8 else g.ffi.GPR_FMT_F32
     db = torch.zeros((P + 31) // 32, dtype=torch.int32, device="cuda:0")
     torch.cuda.synchronize()
     for i in range(5):
         eng.decide_ptr(wins[i % rot][0], P, G, T, db, power=wins[i % rot][1], power_threshold=150.0 if power else 0.0,
-                       blocking=False)
+                       blocking=False, util_format=fmt)
     eng.sync()
     best = 1e9
     tot = 0.0
@@ -34,13 +37,13 @@ def run(variant, P, G, T, iters, rot, power=False):
         eng.timer_begin()
         for i in range(iters):
             eng.decide_ptr(wins[i % rot][0], P, G, T, db, power=wins[i % rot][1],
-                           power_threshold=150.0 if power else 0.0, blocking=False)
+                           power_threshold=150.0 if power else 0.0, blocking=False, util_format=fmt)
         ms = eng.timer_end()
         eng.sync()
         best = min(best, ms / iters)
         tot += ms / iters
-    nbytes = 4.0 * P * G * T * (2 if power else 1)
-    print(f"{variant:4s} P={P} G={G} T={T} power={int(power)} rot={rot}: best {best*1e3:8.2f} us/step  "
+    nbytes = (1.0 if u8 else 4.0) * P * G * T + (4.0 * P * G * T if power else 0.0)
+    print(f"{'u8' if u8 else variant:4s} P={P} G={G} T={T} power={int(power)} rot={rot}: best {best*1e3:8.2f} us/step  "
           f"avg {tot/reps*1e3:8.2f} us  -> {nbytes/best/1e6:8.1f} GB/s (best)  "
           f"{P/best/1e3:8.2f} Mdecisions/s", flush=True)
     eng.close()
@@ -53,9 +56,15 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--shape", default="", help="P,G,T,rot (overrides --configs)")
     ap.add_argument("--power", action="store_true")
+    ap.add_argument("--u8", action="store_true", help="windows in the biased-byte format (one kernel, --variants ignored)")
     a = ap.parse_args()
     shapes = {"c2": (10000, 4, 1800, 6), "c3": (100000, 8, 3600, 2), "c4": (250000, 4, 1800, 2),
               "c5s": (312500, 4, 7200, 1)}
+    if a.u8:
+        for c in a.configs.split(","):
+            P, G, T, rot = shapes[c]
+            run("auto", P, G, T, a.iters if c == "c2" else max(10, a.iters // 5), rot * 3, u8=True)
+        sys.exit(0)
     if a.shape:
         P, G, T, rot = map(int, a.shape.split(","))
         for v in a.variants.split(","):
