@@ -40,6 +40,9 @@ struct Window {
   std::vector<PodEntry> pods;
   std::vector<float> util;            // [P][G][T], NaN = no sample
   std::vector<float> power;           // empty, or [P][G][T]
+  // device-resident planes (ingest_matrix_device): util / power above are empty then
+  const float* d_util = nullptr;
+  const float* d_power = nullptr;
   IngestStats stats;
 };
 

@@ -1,0 +1,229 @@
+#include "ingest_device.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "ingest_internal.hpp"
+
+namespace gph {
+
+using namespace detail;
+
+namespace {
+
+struct NotCompact {  // the response is not in the one encoding the device scan understands
+  std::string why;
+};
+
+struct DevSeries {
+  uint32_t pod, slot;
+  uint64_t begin, end;  // gpr_text_span.begin / .end
+};
+
+struct TextPlan {
+  int slot = 0;                    // resident text slot on the device
+  const std::string* text = nullptr;
+  std::vector<DevSeries> series;   // placed series, in text order
+};
+
+const char kHead[] = "{\"status\":\"success\",\"data\":{\"resultType\":\"matrix\",\"result\":[";
+const char kMetric[] = "{\"metric\":";
+
+bool starts_with(const std::string& s, size_t at, const char* lit) {
+  const size_t n = strlen(lit);
+  return at + n <= s.size() && memcmp(s.data() + at, lit, n) == 0;
+}
+
+size_t skip_trailing_ws(const std::string& s, size_t at) {
+  while (at < s.size() && (s[at] == ' ' || s[at] == '\n' || s[at] == '\r' || s[at] == '\t')) ++at;
+  return at;
+}
+
+// Walk the series of one response using the device's marker lists; labels -> rows through `asg`.
+void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool is_power, bool is_prof) {
+  const std::string& t = *plan.text;
+  std::vector<uint64_t> opens, closes;
+  dev.scan(plan.slot, t.data(), t.size(), &opens, &closes);
+  std::sort(opens.begin(), opens.end());
+  std::sort(closes.begin(), closes.end());
+
+  size_t at;
+  bool bare;
+  if (starts_with(t, 0, kHead)) at = sizeof kHead - 1, bare = false;
+  else if (starts_with(t, 0, "[")) at = 1, bare = true;
+  else throw NotCompact{"response does not start with the compact success/matrix header"};
+
+  size_t walked = 0;
+  if (at < t.size() && t[at] == ']') {
+    ++at;  // empty result
+  } else {
+    while (true) {
+      if (!starts_with(t, at, kMetric) || at + sizeof kMetric - 1 >= t.size() || t[at + sizeof kMetric - 1] != '{')
+        throw NotCompact{"series does not start with {\"metric\":{"};
+      const size_t mb = at + sizeof kMetric - 1;  // '{' of the label map
+      auto vo = std::lower_bound(opens.begin(), opens.end(), (uint64_t)mb);
+      if (vo == opens.end()) throw NotCompact{"label map without a following \"values\" list"};
+      const size_t close_brace = (size_t)*vo;  // '}' of the label map
+      const size_t vb = close_brace + 12;      // first byte after `},"values":[`
+      if (vb >= t.size()) throw NotCompact{"truncated values list"};
+      size_t list_close;  // offset of the ']' closing the list
+      if (t[vb] == ']') {
+        list_close = vb;
+      } else {
+        if (t[vb] != '[') throw NotCompact{"values list does not start with a sample"};
+        auto vc = std::lower_bound(closes.begin(), closes.end(), (uint64_t)vb);
+        if (vc == closes.end()) throw NotCompact{"unterminated values list"};
+        list_close = (size_t)*vc + 2;
+      }
+      if (list_close + 1 >= t.size() || t[list_close + 1] != '}')
+        throw NotCompact{"series object has members after \"values\""};
+      // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON
+      // object ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and
+      // that no series without a "values" member was jumped over.  (A `},"values":[` inside a label
+      // value is impossible: a raw '"' ends a JSON string.)
+      Json metric;
+      try {
+        metric = Json::parse(t.substr(mb, close_brace + 1 - mb));
+      } catch (const std::exception& e) {
+        throw NotCompact{std::string("label map: ") + e.what()};
+      }
+      if (!metric.is_object()) throw NotCompact{"label map is not an object"};
+      ++walked;
+      ++w.stats.series_in;
+      if (list_close != vb) {  // an empty list is no element (as in the CPU paths)
+        uint32_t p, slot;
+        if (asg.assign(metric, is_power, is_prof, &p, &slot) == Assigner::Placed)
+          plan.series.push_back(DevSeries{p, slot, (uint64_t)vb, (uint64_t)list_close});
+      }
+      at = list_close + 2;  // past '}'
+      if (at < t.size() && t[at] == ',') {
+        ++at;
+        continue;
+      }
+      if (at < t.size() && t[at] == ']') {
+        ++at;
+        break;
+      }
+      throw NotCompact{"expected ',' or ']' after a series"};
+    }
+  }
+  if (walked != opens.size()) throw NotCompact{"values markers outside the series walk"};
+  if (!bare) {
+    if (!starts_with(t, at, "}}")) throw NotCompact{"response has members after \"result\""};
+    at += 2;
+  }
+  if (skip_trailing_ws(t, at) != t.size()) throw NotCompact{"trailing bytes after the response"};
+}
+
+}  // namespace
+
+Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std::string* prof,
+                            const std::string* power, const IngestOptions& opt, DeviceIngestReport* report) {
+  DeviceIngestReport local;
+  DeviceIngestReport& rep = report ? *report : local;
+  rep = DeviceIngestReport{};
+  auto cpu = [&](const std::string& why) {
+    rep.on_device = false, rep.reason = why;
+    Window w = ingest_matrix_text(util, prof, power, opt);
+    w.stats.warnings.push_back("device ingest not used: " + why);
+    return w;
+  };
+  if (opt.t_end <= 0 || opt.step <= 0) return cpu("window end / step not given (query.json)");
+
+  Window w;
+  Assigner asg(w);
+  TextPlan plans[3];  // prof, util, power — the order the CPU paths assign rows in
+  int n_plans = 0;
+  auto add = [&](const std::string* text, int slot) -> TextPlan* {
+    if (!text) return nullptr;
+    plans[n_plans].slot = slot, plans[n_plans].text = text;
+    return &plans[n_plans++];
+  };
+  TextPlan* pl_prof = add(prof, 0);
+  TextPlan* pl_util = add(&util, 1);
+  TextPlan* pl_power = add(power, 2);
+  try {
+    if (pl_prof) plan_text(dev, *pl_prof, asg, w, false, true);
+    plan_text(dev, *pl_util, asg, w, false, false);
+    if (pl_power) plan_text(dev, *pl_power, asg, w, true, false);
+  } catch (const NotCompact& e) {
+    return cpu(e.why);
+  }
+  finish_shape(w, opt, 0, 1, power != nullptr, /*allocate=*/false);  // t_end / step given: nothing to infer
+  const uint32_t n_rows = w.P * w.G;
+  if (n_rows == 0) {
+    rep.on_device = true;
+    return w;
+  }
+
+  // rows fed by more than one series are merged on the device (NaN-aware max), the rest stored
+  auto run_plane = [&](std::vector<TextPlan*> texts, int plane) {
+    std::vector<uint32_t> writers(n_rows, 0);
+    for (TextPlan* tp : texts)
+      for (const DevSeries& s : tp->series) ++writers[(size_t)s.pod * w.G + s.slot];
+    std::vector<std::vector<gpr_text_span>> spans(texts.size());
+    bool fill = true;
+    for (size_t k = 0; k < texts.size(); ++k) {
+      for (const DevSeries& s : texts[k]->series) {
+        gpr_text_span sp;
+        memset(&sp, 0, sizeof sp);
+        sp.begin = s.begin, sp.end = s.end, sp.row = s.pod * w.G + s.slot;
+        sp.flags = writers[sp.row] > 1 ? GPR_SPAN_SHARED : 0u;
+        spans[k].push_back(sp);
+      }
+      dev.parse(texts[k]->slot, spans[k], w.t_end, w.step, w.T, n_rows, plane, fill);
+      fill = false;
+      rep.spans += spans[k].size();
+    }
+    // rows the device gave up on: re-parse every series feeding them with the CPU walker
+    std::vector<uint8_t> dirty(n_rows, 0);
+    bool any_dirty = false;
+    for (const auto& list : spans)
+      for (const gpr_text_span& sp : list)
+        if (sp.flags & GPR_SPAN_HARD) dirty[sp.row] = 1, any_dirty = true, ++rep.hard_spans;
+    std::vector<std::vector<float>> rows;
+    std::vector<uint32_t> row_ids;
+    std::vector<int64_t> row_slot(any_dirty ? n_rows : 0, -1);
+    for (size_t k = 0; k < texts.size(); ++k) {
+      const std::string& t = *texts[k]->text;
+      for (const gpr_text_span& sp : spans[k]) {
+        if (!dirty[sp.row]) {
+          w.stats.samples_in += sp.n_in;
+          w.stats.samples_out_of_window += sp.n_oow;
+          w.stats.tiny_values_clamped += sp.n_tiny;
+          continue;
+        }
+        if (row_slot[sp.row] < 0) {
+          row_slot[sp.row] = (int64_t)rows.size();
+          rows.emplace_back(w.T, std::numeric_limits<float>::quiet_NaN());
+          row_ids.push_back(sp.row);
+        }
+        float* row = rows[(size_t)row_slot[sp.row]].data();
+        for_each_sample(t.data() + sp.begin - 1, t.data() + sp.end + 1, [&](double ts, double v) {
+          ++w.stats.samples_in;
+          const int64_t col = column_of(w, ts_seconds(ts));
+          if (col < 0) {
+            ++w.stats.samples_out_of_window;
+            return;
+          }
+          merge_cell(row[col], to_f32(v, &w.stats.tiny_values_clamped));
+        });
+      }
+    }
+    for (size_t i = 0; i < rows.size(); ++i) dev.patch_row(plane, row_ids[i], w.T, rows[i].data());
+    rep.rows_patched += rows.size();
+  };
+  std::vector<TextPlan*> util_texts;
+  if (pl_prof) util_texts.push_back(pl_prof);
+  util_texts.push_back(pl_util);
+  run_plane(util_texts, 0);
+  w.d_util = dev.plane(0);
+  if (pl_power) {
+    run_plane({pl_power}, 1);
+    w.d_power = dev.plane(1);
+  }
+  rep.on_device = true;
+  return w;
+}
+
+}  // namespace gph

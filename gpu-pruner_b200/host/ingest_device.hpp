@@ -1,0 +1,45 @@
+// ingest_device.hpp — the matrix wire format parsed ON THE GPU: the host keeps only what needs hashing
+// and strings (label maps -> tensor rows, ~1 % of the bytes); the sample lists go to the device as
+// text and land in the dense tensor in HBM (include/gpr.h, gpr_text_scan / gpr_text_parse).  The f32
+// window never exists on the host.  Result: the same Window as ingest_matrix_text() — shape, pods,
+// statistics — with `d_util` / `d_power` device planes instead of the host vectors, bit-identical
+// cell for cell (tests/test_text_device_cpu.py on an emulated device, tests/test_gpu_text.py on the GPU).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/gpr.h"
+#include "ingest.hpp"
+
+namespace gph {
+
+// What the orchestration needs from the device; implemented over libgpr.so in gpr_engine.cpp.
+class TextDevice {
+ public:
+  virtual ~TextDevice() = default;
+  // upload `text` into resident slot `slot` (0..2) and report the UNSORTED offsets of every
+  // `},"values":[` ('}' position) and `"]]` ('"' position)
+  virtual void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens,
+                    std::vector<uint64_t>* closes) = 0;
+  // parse the samples of `spans` (sorted by begin) of the text in `slot` into plane 0 (util) / 1 (power)
+  virtual void parse(int slot, std::vector<gpr_text_span>& spans, int64_t t_end, int64_t step, uint32_t T,
+                     uint32_t n_rows, int plane, bool fill) = 0;
+  virtual void patch_row(int plane, uint32_t row, uint32_t T, const float* data) = 0;
+  virtual const float* plane(int plane) = 0;
+};
+
+struct DeviceIngestReport {
+  bool on_device = false;        // false: the CPU text path produced the window (reason says why)
+  std::string reason;
+  uint64_t spans = 0, hard_spans = 0, rows_patched = 0;
+};
+
+// Needs opt.t_end > 0 and opt.step > 0 (the caller issued the range query, so it knows both);
+// otherwise, and for any response that is not in Prometheus' compact encoding, the CPU text path
+// runs instead and the returned Window carries host vectors as usual.
+Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std::string* prof,
+                            const std::string* power, const IngestOptions& opt,
+                            DeviceIngestReport* report = nullptr);
+
+}  // namespace gph

@@ -1,0 +1,414 @@
+// ingest_internal.hpp — pieces shared by the three ingest front ends (DOM reference path and threaded
+// text path in ingest.cpp, device path in ingest_device.cpp): label set -> (pod, slot) assignment,
+// window shape, time bucketing, and the CPU text walker for sample lists.  Not a public interface.
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+#include "ingest.hpp"
+
+namespace gph {
+namespace detail {
+
+
+const int64_t kNoTs = std::numeric_limits<int64_t>::min();
+
+// exported_<x> first, then <x> (lib.rs:158-175)
+inline const std::string* label(const Json& metric, const char* exported, const char* bare) {
+  const Json* j = metric.find(exported);
+  if (j && j->is_string()) return &j->as_string();
+  j = metric.find(bare);
+  if (j && j->is_string()) return &j->as_string();
+  return nullptr;
+}
+
+inline float to_f32(double x, uint64_t* clamped) {
+  float f = (float)x;
+  if (x != 0.0 && f == 0.0f && !std::isnan(x)) {  // below the f32 denormal range: keep it non-zero
+    f = std::copysign(std::numeric_limits<float>::denorm_min(), (float)(x < 0 ? -1.0 : 1.0));
+    ++*clamped;
+  }
+  return f;
+}
+
+// duplicates of one group: per-step max.  For the non-negative DCGM metrics the window max of that
+// is 0 exactly when every member's max is 0, i.e. when `sum by` of the maxima is 0.
+inline void merge_cell(float& cell, float v) {
+  cell = std::isnan(cell) ? v : (std::isnan(v) ? cell : std::max(cell, v));
+}
+
+// ---- label set -> (pod, slot): shared by the DOM and the text path -----------------------------------
+class Assigner {
+ public:
+  explicit Assigner(Window& w) : w_(w) {}
+  enum Result { Skipped, Shadowed, Placed };
+
+  Result assign(const Json& m, bool is_power, bool is_prof, uint32_t* pod_out, uint32_t* slot_out) {
+    const std::string* pod = label(m, "exported_pod", "pod");
+    const std::string* ns = label(m, "exported_namespace", "namespace");
+    const std::string* ctr = label(m, "exported_container", "container");
+    const Json* model = m.find("modelName");
+    // the selector demands pod != "" (query.promql.j2:11,17,40); a series that cannot be turned into
+    // PodMetricData is skipped with a log line (main.rs:423-428)
+    if (!pod || pod->empty() || !ns || (!is_power && (!ctr || !model || !model->is_string()))) {
+      ++w_.stats.series_skipped;
+      return Skipped;
+    }
+    auto key = std::make_pair(*pod, *ns);
+    auto it = pod_index_.find(key);
+    uint32_t p;
+    if (it == pod_index_.end()) {
+      p = (uint32_t)w_.pods.size();
+      pod_index_[key] = p;
+      w_.pods.push_back(PodEntry{*pod, *ns, {}, 0});
+      slot_index_.emplace_back();
+      pslot_index_.emplace_back();
+    } else {
+      p = it->second;
+    }
+    const std::string host = m["Hostname"].as_string(), gpu = m["gpu"].as_string();
+    const std::string mdl = model && model->is_string() ? model->as_string() : std::string();
+    // `sum by (Hostname, container, pod, namespace, gpu, modelName)` groups (query.promql.j2:9)
+    const std::string gkey = host + "\x1f" + (ctr ? *ctr : std::string()) + "\x1f" + gpu + "\x1f" + mdl;
+    uint32_t slot;
+    if (is_power) {
+      auto& idx = pslot_index_[p];
+      auto f = idx.find(gkey);
+      if (f == idx.end()) slot = idx[gkey] = w_.pods[p].power_slots++;
+      else slot = f->second, ++w_.stats.duplicates_merged;
+    } else {
+      auto& idx = slot_index_[p];
+      auto f = idx.find(gkey);
+      bool fresh = false;
+      if (f == idx.end()) {
+        slot = idx[gkey] = (uint32_t)w_.pods[p].slots.size();
+        GpuSlot g;
+        g.hostname = host, g.container = *ctr, g.gpu = gpu, g.model = mdl;
+        const Json* nt = m.find("node_type");
+        g.node_type = nt && nt->is_string() ? nt->as_string() : "unknown";  // lib.rs:176-179
+        g.from_prof = is_prof;
+        w_.pods[p].slots.push_back(g);
+        fresh = true;
+      } else {
+        slot = f->second;
+      }
+      // `A or B` (query.promql.j2:10-20) matches on the FULL label set: a UTIL element is dropped only
+      // if a PROF element with identical labels exists; series that differ in any other label both
+      // survive the `or` and are then folded together by `sum by`
+      std::vector<std::string> parts;
+      for (const Json::Member& kv : m.members())
+        if (kv.first != "__name__") parts.push_back(kv.first + "\x1f" + kv.second.as_string());
+      std::sort(parts.begin(), parts.end());
+      std::string sig;
+      for (const std::string& x : parts) sig += x + "\x1e";
+      std::vector<std::string>& ps = prof_sigs_[std::make_pair(p, slot)];
+      if (is_prof) {
+        ps.push_back(sig);
+        w_.pods[p].slots[slot].from_prof = true;
+      } else {
+        for (const std::string& x : ps)
+          if (x == sig) return Shadowed;
+      }
+      if (!fresh) ++w_.stats.duplicates_merged;
+    }
+    *pod_out = p, *slot_out = slot;
+    return Placed;
+  }
+
+ private:
+  Window& w_;
+  std::map<std::pair<std::string, std::string>, uint32_t> pod_index_;
+  std::vector<std::map<std::string, uint32_t>> slot_index_;   // per pod: group key -> util slot
+  std::vector<std::map<std::string, uint32_t>> pslot_index_;  // per pod: group key -> power slot
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<std::string>> prof_sigs_;
+};
+
+inline void finish_shape(Window& w, const IngestOptions& opt, int64_t newest, int64_t min_step, bool with_power,
+                         bool allocate = true) {
+  w.P = (uint32_t)w.pods.size();
+  uint32_t G = 1;
+  for (const PodEntry& pe : w.pods)
+    G = std::max<uint32_t>(G, std::max<uint32_t>((uint32_t)pe.slots.size(), pe.power_slots));
+  w.G = G;
+  w.step = opt.step > 0 ? opt.step : (min_step == std::numeric_limits<int64_t>::max() ? 1 : min_step);
+  w.t_end = opt.t_end > 0 ? opt.t_end : (newest == kNoTs ? 0 : newest);
+  const int64_t span = opt.duration_min * 60;
+  w.T = (uint32_t)std::max<int64_t>(1, span / w.step);  // (t_end - N, t_end] sampled every `step`
+  if (!allocate) return;  // device ingest: the planes live in HBM
+  const size_t cells = (size_t)w.P * w.G * w.T;
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  w.util.assign(cells, nan);
+  if (with_power) w.power.assign(cells, nan);
+}
+
+// timestamp in whole seconds; anything that is not a sane epoch time maps to "far outside any window"
+constexpr int64_t kBadTs = std::numeric_limits<int64_t>::min() / 4;
+inline int64_t ts_seconds(double t) {
+  if (!(t > -4e12 && t < 4e12)) return kBadTs;  // also NaN
+  return (int64_t)std::llround(t);
+}
+
+// column of timestamp ts, or -1 when it lies outside (t_end - N, t_end]
+inline int64_t column_of(const Window& w, int64_t ts) {
+  if (ts > w.t_end || ts < w.t_end - (int64_t)w.T * w.step - w.step) return -1;
+  const int64_t back = (w.t_end - ts + w.step / 2) / w.step;  // 0 = newest column
+  if (ts > w.t_end || back < 0 || back >= (int64_t)w.T) return -1;
+  return (int64_t)w.T - 1 - back;
+}
+
+// =====================================================================================================
+// text walker
+// =====================================================================================================
+
+struct Span {
+  const char *metric_b, *metric_e, *values_b, *values_e;  // values_b at '[', values_e one past the final ']'
+};
+
+[[noreturn]] inline void bad(const char* what) { throw std::runtime_error(std::string("matrix response: ") + what); }
+
+inline const char* skip_ws(const char* p, const char* e) {
+  while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+  return p;
+}
+
+// p at '"': returns one past the closing quote
+inline const char* skip_string(const char* p, const char* e) {
+  for (++p; p < e; ++p) {
+    if (*p == '\\') ++p;
+    else if (*p == '"') return p + 1;
+  }
+  bad("unterminated string");
+}
+
+// balanced skip of any JSON value
+inline const char* skip_value(const char* p, const char* e) {
+  p = skip_ws(p, e);
+  if (p >= e) bad("unexpected end");
+  if (*p == '"') return skip_string(p, e);
+  if (*p == '{' || *p == '[') {
+    int depth = 0;
+    for (; p < e; ++p) {
+      if (*p == '"') p = skip_string(p, e) - 1;
+      else if (*p == '{' || *p == '[') ++depth;
+      else if (*p == '}' || *p == ']') {
+        if (--depth == 0) return p + 1;
+      }
+    }
+    bad("unbalanced brackets");
+  }
+  while (p < e && *p != ',' && *p != '}' && *p != ']') ++p;
+  return p;
+}
+
+// first occurrence of "]]" in [p, e): eight bytes per step (a values array has a ']' every ~17 bytes,
+// which defeats memchr, and glibc's memmem manages ~1 GB/s on a 2-byte needle)
+inline const char* find_close2(const char* p, const char* e) {
+  const uint64_t pat = 0x5D5D5D5D5D5D5D5Dull;  // ']' x 8
+  const uint64_t lo = 0x0101010101010101ull, hi = 0x8080808080808080ull;
+  while (e - p >= 9) {
+    uint64_t a, b;
+    memcpy(&a, p, 8);
+    memcpy(&b, p + 1, 8);
+    const uint64_t xa = a ^ pat, xb = b ^ pat;
+    // zero bytes of x mark ']' — exact zero-byte detection (no false positives across bytes)
+    const uint64_t za = ~(((xa & ~hi) + ~hi) | xa) & hi, zb = ~(((xb & ~hi) + ~hi) | xb) & hi;
+    const uint64_t both = za & zb;
+    if (both) return p + (__builtin_ctzll(both) >> 3);
+    p += 8;
+    (void)lo;
+  }
+  for (; p + 1 < e; ++p)
+    if (p[0] == ']' && p[1] == ']') return p;
+  return nullptr;
+}
+
+// Walks the members of the object at p ('{').  `on_member(key_begin, key_len, value_ptr)` may consume
+// the value itself and return the position after it; returning nullptr means "skip it for me".
+// Returns the position after the closing '}'.
+template <typename F>
+const char* walk_object(const char* p, const char* e, F&& on_member) {
+  p = skip_ws(p, e);
+  if (p >= e || *p != '{') bad("expected object");
+  ++p;
+  while (true) {
+    p = skip_ws(p, e);
+    if (p < e && *p == '}') return p + 1;
+    if (p >= e || *p != '"') bad("expected member name");
+    const char* ks = p + 1;
+    const char* ke = skip_string(p, e) - 1;
+    p = skip_ws(ke + 1, e);
+    if (p >= e || *p != ':') bad("expected ':'");
+    p = skip_ws(p + 1, e);
+    const char* after = on_member(ks, (size_t)(ke - ks), p);
+    p = skip_ws(after ? after : skip_value(p, e), e);
+    if (p < e && *p == ',') { ++p; continue; }
+    if (p < e && *p == '}') return p + 1;
+    bad("expected ',' or '}'");
+  }
+}
+
+inline bool key_is(const char* ks, size_t kl, const char* name) {
+  return kl == strlen(name) && memcmp(ks, name, kl) == 0;
+}
+
+// the series of a result array starting at arr ('['); returns the position after its ']'
+inline const char* result_spans(const char* arr, const char* e, std::vector<Span>& out) {
+  const char* p = skip_ws(arr + 1, e);
+  while (true) {
+    if (p >= e) bad("unterminated result array");
+    if (*p == ']') return p + 1;
+    Span s{nullptr, nullptr, nullptr, nullptr};
+    p = walk_object(p, e, [&](const char* ks, size_t kl, const char* v) -> const char* {
+      if (key_is(ks, kl, "values") && v < e && *v == '[') {
+        // a values array holds nothing but [ts,"v"] pairs: it ends at the first "]]" (or is "[]"),
+        // so the bulk of the response is skipped with memmem instead of being walked
+        const char* in = skip_ws(v + 1, e);
+        const char* end;
+        if (in < e && *in == ']') {
+          end = in + 1;
+        } else {
+          const char* hit = find_close2(v, e);
+          if (!hit) bad("unterminated values array");
+          end = hit + 2;
+        }
+        s.values_b = v, s.values_e = end;
+        return end;
+      }
+      if (key_is(ks, kl, "metric")) {
+        const char* ve = skip_value(v, e);
+        s.metric_b = v, s.metric_e = ve;
+        return ve;
+      }
+      return nullptr;
+    });
+    out.push_back(s);
+    p = skip_ws(p, e);
+    if (p < e && *p == ',') p = skip_ws(p + 1, e);
+  }
+}
+
+inline std::vector<Span> series_spans(const std::string& text) {
+  const char* b = text.data();
+  const char* e = b + text.size();
+  const char* p = skip_ws(b, e);
+  std::vector<Span> out;
+  if (p < e && *p == '[') {  // bare result array
+    result_spans(p, e, out);
+    return out;
+  }
+  bool saw_result = false;
+  auto quoted = [&](const char* v) { return std::string(v + 1, skip_string(v, e) - 1); };
+  walk_object(p, e, [&](const char* ks, size_t kl, const char* v) -> const char* {
+    if (key_is(ks, kl, "status") && *v == '"' && quoted(v) != "success")
+      throw std::runtime_error("prometheus response status: " + quoted(v));
+    if (!key_is(ks, kl, "data")) return nullptr;
+    return walk_object(v, e, [&](const char* ks2, size_t kl2, const char* v2) -> const char* {
+      if (key_is(ks2, kl2, "resultType") && *v2 == '"' && quoted(v2) != "matrix")
+        throw std::runtime_error("expected matrix response from prometheus, got " + quoted(v2));
+      if (key_is(ks2, kl2, "result") && *v2 == '[') {
+        saw_result = true;
+        return result_spans(v2, e, out);
+      }
+      return nullptr;
+    });
+  });
+  if (!saw_result) bad("not a Prometheus matrix response");
+  return out;
+}
+
+// fast decimal: [-+]digits[.digits]; anything else (exponent, NaN, Inf) goes through strtod
+inline double parse_number(const char* p, const char* e, const char** end) {
+  const char* s = p;
+  bool neg = false;
+  if (p < e && (*p == '-' || *p == '+')) neg = *p == '-', ++p;
+  const char* d0 = p;
+  uint64_t ip = 0;
+  while (p < e && *p >= '0' && *p <= '9' && p - d0 < 18) ip = ip * 10 + (uint64_t)(*p - '0'), ++p;
+  if (p == d0 || (p < e && *p >= '0' && *p <= '9')) goto slow;
+  {
+    double v = (double)ip;
+    if (p < e && *p == '.') {
+      ++p;
+      const char* f0 = p;
+      uint64_t fp = 0;
+      while (p < e && *p >= '0' && *p <= '9' && p - f0 < 18) fp = fp * 10 + (uint64_t)(*p - '0'), ++p;
+      if (p < e && *p >= '0' && *p <= '9') goto slow;
+      static const double pow10[19] = {1,    1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,
+                                       1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18};
+      // exact only when both parts fit 53 bits; otherwise let strtod round correctly
+      if (ip > (1ull << 53) || fp > (1ull << 53) || (p - f0) > 15) goto slow;
+      v += (double)fp / pow10[p - f0];
+      if (ip != 0 && fp != 0) goto slow;  // sum of two roundings is not always correctly rounded
+    }
+    if (p < e && (*p == 'e' || *p == 'E')) goto slow;
+    *end = p;
+    return neg ? -v : v;
+  }
+slow : {
+  char buf[64];
+  size_t n = 0;
+  const char* q = s;
+  while (q < e && n + 1 < sizeof buf && *q != '"' && *q != ',' && *q != ']') buf[n++] = *q++;
+  buf[n] = 0;
+  char* ep = nullptr;
+  const double v = strtod(buf, &ep);
+  *end = s + (ep - buf);
+  return v;
+}
+}
+
+// walks [[ts,"v"],[ts,"v"],...] calling f(ts, value)
+template <typename F>
+void for_each_sample(const char* p, const char* e, F&& f) {
+  ++p;  // outer '['
+  while (true) {
+    p = skip_ws(p, e);
+    if (p >= e || *p == ']') return;
+    if (*p != '[') bad("expected [ts, value]");
+    p = skip_ws(p + 1, e);
+    const char* q;
+    const double ts = parse_number(p, e, &q);
+    if (q == p) bad("bad timestamp");
+    p = skip_ws(q, e);
+    if (p >= e || *p != ',') bad("expected ','");
+    p = skip_ws(p + 1, e);
+    double v;
+    if (p < e && *p == '"') {
+      v = parse_number(p + 1, e, &q);
+      if (q < e && *q != '"') {  // "NaN", "+Inf", ...
+        char buf[32];
+        size_t n = 0;
+        const char* r = p + 1;
+        while (r < e && *r != '"' && n + 1 < sizeof buf) buf[n++] = *r++;
+        buf[n] = 0;
+        v = strtod(buf, nullptr);
+        q = r;
+      }
+      p = q + 1;
+    } else {
+      v = parse_number(p, e, &q);
+      p = q;
+    }
+    p = skip_ws(p, e);
+    if (p >= e || *p != ']') bad("expected ']'");
+    ++p;
+    f(ts, v);
+    p = skip_ws(p, e);
+    if (p < e && *p == ',') ++p;
+  }
+}
+
+struct TextSeries {
+  uint32_t pod, slot;
+  const char *vb, *ve;
+  bool sole;  // the only series writing its tensor row
+};
+
+
+}  // namespace detail
+}  // namespace gph

@@ -264,6 +264,53 @@ GPR_API int gpr_synth_fill(gpr_ctx *ctx, uint64_t seed, int32_t plane, float *ds
 GPR_API int gpr_synth_eligible(gpr_ctx *ctx, uint64_t seed, uint8_t *dst, uint64_t pod_offset,
                        uint32_t n_pods);
 
+/* ---- device-side ingest of the range-query response TEXT ---------------------------------------
+ * The step before the hot path: Prometheus' matrix JSON (the shape gpu-pruner/src/bin/querytest.rs:41-53
+ * walks; series = label map + [[<unix time>, "<value>"], ...]) is parsed on the GPU straight into the
+ * dense tensor in HBM, so the f32 window never exists on the host.  Division of labour:
+ *   gpr_text_scan    uploads the text and reports where every sample list opens (`},"values":[`)
+ *                    and closes (`"]]`);
+ *   the caller       parses the label maps (~1 % of the bytes) and assigns every series its tensor
+ *                    row — label precedence of lib.rs:153-187, `sum by` groups of query.promql.j2:9
+ *                    (gpu-pruner_b200/host/ingest_device.cpp does this);
+ *   gpr_text_parse   parses all samples of the given spans into a context-owned plane
+ *                    [n_rows][n_samples] f32 (NaN = no sample), column = (t_end - ts) / step.
+ * The device parser is strict: anything but `[digits[.digits],"<short decimal>|NaN|+Inf|-Inf"]`,
+ * two samples of one series in one column, or time running backwards sets GPR_SPAN_HARD on the span;
+ * the caller re-parses the rows of hard spans on the CPU and overwrites them with gpr_memcpy, so the
+ * tensor is bit-identical to a CPU ingest for every input.
+ */
+typedef struct gpr_text_span {
+  uint64_t begin;    /* offset of the first byte after `"values":[` (a '[')                    */
+  uint64_t end;      /* offset of the ']' that closes the sample list                          */
+  uint32_t row;      /* destination row = pod * n_gpus + slot                                  */
+  uint32_t flags;    /* GPR_SPAN_SHARED in; GPR_SPAN_HARD out                                  */
+  uint32_t n_in;     /* out: samples parsed                                                    */
+  uint32_t n_oow;    /* out: samples outside (t_end - n_samples*step, t_end]                   */
+  uint32_t n_tiny;   /* out: non-zero values below the f32 denormal range, kept non-zero       */
+  uint32_t reserved;
+} gpr_text_span;
+#define GPR_SPAN_SHARED 1u /* several series feed this row: merge (NaN-aware max), do not store  */
+#define GPR_SPAN_HARD 2u   /* the device parser gave up on this span: re-parse its row on the CPU */
+#define GPR_TEXT_FILL 1u   /* gpr_text_parse: fill the plane with NaN first                      */
+
+/* Copy `n_bytes` of response text to the device (pinned host memory from gpr_host_alloc moves at
+ * full PCIe speed) and scan it.  Up to `cap` offsets are written to each of opens[] (position of the
+ * '}' of `},"values":[`) and closes[] (position of the '"' of `"]]`), UNSORTED; the true counts are
+ * returned in *n_opens / *n_closes (GPR_E_CAPACITY if either exceeds cap).  The text stays resident
+ * in the context for gpr_text_parse until the next gpr_text_scan.  Blocking.                      */
+GPR_API int gpr_text_scan(gpr_ctx *ctx, const char *text, uint64_t n_bytes, int32_t mem_kind,
+                          uint64_t *opens, uint64_t *closes, uint64_t cap, uint64_t *n_opens,
+                          uint64_t *n_closes);
+/* Parse the samples of spans[0..n_spans) (host array, sorted by begin, non-overlapping) of the resident
+ * text into plane `plane` (0 = util, 1 = power).  Out-fields of the spans are filled.  Blocking.   */
+GPR_API int gpr_text_parse(gpr_ctx *ctx, gpr_text_span *spans, uint32_t n_spans, int64_t t_end,
+                           int64_t step, uint32_t n_samples, uint32_t n_rows, int32_t plane,
+                           uint32_t flags);
+/* Device pointers of the planes (NULL if never parsed); valid until the next gpr_text_parse that has
+ * to grow them, or gpr_destroy.  Hand them to gpr_decide with mem_kind = GPR_MEM_DEVICE.           */
+GPR_API int gpr_text_planes(gpr_ctx *ctx, float **util, float **power);
+
 #ifdef __cplusplus
 }
 #endif

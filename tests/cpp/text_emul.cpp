@@ -1,0 +1,213 @@
+// TEST INFRASTRUCTURE.  Runs the device ingest (gpu-pruner_b200/host/ingest_device.cpp) on an EMULATED
+// device: the very functions the CUDA kernels call (gpu-pruner_b200/csrc/gpr_text.cuh, GPR_HD) executed
+// slice by slice on the CPU, with a sink that also checks the "every cell of a stored row is written at
+// most once" property the plain device stores rely on.  Each case directory (util.json [prof.json]
+// [power.json]) is ingested by the CPU text path and by the emulated device path; shape, pods,
+// statistics and every tensor cell must agree, or both must reject the input.
+//
+//   text_emul <t_end> <step> <duration_min> <case_dir>...
+// prints per case:  OK device=<0|1> spans=.. hard=.. patched=.. [reason]  |  REJECT  |  MISMATCH <what>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <stdexcept>
+#include <string>
+
+#include "../../gpu-pruner_b200/csrc/gpr_text.cuh"
+#include "ingest_device.hpp"
+
+using namespace gph;
+namespace tx = gpr::text;
+
+static_assert(sizeof(gpr_text_span) == sizeof(tx::Span), "gpr_text_span mirrors gpr::text::Span");
+
+namespace {
+
+class EmulDevice : public TextDevice {
+ public:
+  void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens,
+            std::vector<uint64_t>* closes) override {
+    std::vector<uint8_t>& t = text_[slot];
+    t.assign(n + tx::kTextPad, 0);
+    memcpy(t.data(), text, n);
+    n_[slot] = n;
+    struct Sink {
+      std::vector<uint64_t>*o, *c;
+      void values_open(uint64_t p) { o->push_back(p); }
+      void values_close(uint64_t p) { c->push_back(p); }
+    } sink{opens, closes};
+    const uint64_t slices = (n + tx::kScanBytes - 1) / tx::kScanBytes;
+    // reversed slice order: nothing may depend on the order threads run in
+    for (uint64_t s = slices; s-- > 0;) tx::scan_slice(t.data(), (uint64_t)n, s, sink);
+  }
+
+  void parse(int slot, std::vector<gpr_text_span>& spans, int64_t t_end, int64_t step, uint32_t T,
+             uint32_t n_rows, int plane, bool fill) override {
+    std::vector<float>& pl = plane_[plane];
+    if (fill) pl.assign((size_t)n_rows * T, tx::quiet_nan_f32());
+    if (pl.size() != (size_t)n_rows * T) throw std::logic_error("emul: plane shape changed without fill");
+    std::vector<uint8_t> stores(pl.size(), 0);
+    struct Sink {
+      std::vector<float>& pl;
+      std::vector<uint8_t>& stores;
+      tx::Span* sp;
+      uint32_t T;
+      void store(uint32_t row, uint32_t col, float v) {
+        pl[(size_t)row * T + col] = v;
+        if (stores[(size_t)row * T + col] < 255) ++stores[(size_t)row * T + col];
+      }
+      void merge(uint32_t row, uint32_t col, float v) {
+        float& c = pl[(size_t)row * T + col];
+        c = std::isnan(c) ? v : (std::isnan(v) ? c : (c < v ? v : c));
+      }
+      void hard(uint32_t s) { sp[s].flags |= tx::kSpanHard; }
+      void count(uint32_t s, uint32_t a, uint32_t b, uint32_t c) {
+        sp[s].n_in += a, sp[s].n_oow += b, sp[s].n_tiny += c;
+      }
+    } sink{pl, stores, reinterpret_cast<tx::Span*>(spans.data()), T};
+    const tx::Grid g{t_end, step, T, 0};
+    const uint8_t* t = text_[slot].data();
+    const uint64_t n = n_[slot];
+    const tx::Span* sp = reinterpret_cast<const tx::Span*>(spans.data());
+    const uint64_t slices = (n + tx::kParseBytes - 1) / tx::kParseBytes;
+    for (uint64_t s = slices; s-- > 0;) {
+      const uint32_t hint = tx::find_span(sp, (uint32_t)spans.size(), s * tx::kParseBytes);
+      tx::parse_slice(t, n, sp, (uint32_t)spans.size(), hint, s, g, sink);
+    }
+    // a cell stored twice by spans the device did not give up on would be a data race on the GPU
+    std::vector<uint8_t> row_hard(n_rows, 0);
+    for (const gpr_text_span& s : spans)
+      if (s.flags & GPR_SPAN_HARD) row_hard[s.row] = 1;
+    for (size_t i = 0; i < stores.size(); ++i)
+      if (stores[i] > 1 && !row_hard[i / T]) throw std::logic_error("emul: cell stored twice in a row not marked hard");
+  }
+
+  void patch_row(int plane, uint32_t row, uint32_t T, const float* data) override {
+    memcpy(plane_[plane].data() + (size_t)row * T, data, (size_t)T * sizeof(float));
+  }
+  const float* plane(int plane) override { return plane_[plane].data(); }
+
+ private:
+  std::vector<uint8_t> text_[3];
+  uint64_t n_[3] = {0, 0, 0};
+  std::vector<float> plane_[2];
+};
+
+bool slurp(const std::string& path, std::string* out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  out->assign((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  return true;
+}
+
+// value equality: NaN matches NaN (any payload), otherwise ==; `bits` additionally compares bit patterns
+bool same_plane(const float* a, const float* b, size_t n, bool bits, size_t* where) {
+  for (size_t i = 0; i < n; ++i) {
+    const bool na = std::isnan(a[i]), nb = std::isnan(b[i]);
+    bool ok = na == nb && (na || a[i] == b[i]);
+    if (ok && bits && !na) ok = memcmp(a + i, b + i, 4) == 0;
+    if (!ok) {
+      *where = i;
+      return false;
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 5) return 2;
+  IngestOptions o;
+  o.t_end = atoll(argv[1]), o.step = atoll(argv[2]), o.duration_min = atoll(argv[3]);
+  int bad = 0;
+  for (int i = 4; i < argc; ++i) {
+    const std::string dir = argv[i];
+    std::string util, prof, power;
+    if (!slurp(dir + "/util.json", &util)) {
+      printf("MISMATCH %s no util.json\n", dir.c_str());
+      ++bad;
+      continue;
+    }
+    const bool has_prof = slurp(dir + "/prof.json", &prof), has_power = slurp(dir + "/power.json", &power);
+    Window wc, wd;
+    bool ok_c = true, ok_d = true;
+    std::string err_c, err_d;
+    DeviceIngestReport rep;
+    EmulDevice dev;
+    try {
+      wc = ingest_matrix_text(util, has_prof ? &prof : nullptr, has_power ? &power : nullptr, o, 2);
+    } catch (const std::exception& e) {
+      ok_c = false, err_c = e.what();
+    }
+    try {
+      wd = ingest_matrix_device(dev, util, has_prof ? &prof : nullptr, has_power ? &power : nullptr, o, &rep);
+    } catch (const std::logic_error& e) {
+      printf("MISMATCH %s %s\n", dir.c_str(), e.what());
+      ++bad;
+      continue;
+    } catch (const std::exception& e) {
+      ok_d = false, err_d = e.what();
+    }
+    if (!ok_c || !ok_d) {
+      if (ok_c == ok_d) {
+        printf("REJECT %s device=%d\n", dir.c_str(), (int)rep.on_device);
+      } else {
+        printf("MISMATCH %s cpu %s / device %s\n", dir.c_str(), ok_c ? "ok" : err_c.c_str(),
+               ok_d ? "ok" : err_d.c_str());
+        ++bad;
+      }
+      continue;
+    }
+    std::string what;
+    if (wc.P != wd.P || wc.G != wd.G || wc.T != wd.T || wc.t_end != wd.t_end || wc.step != wd.step) what = "shape";
+    if (what.empty() && wc.pods.size() != wd.pods.size()) what = "pods";
+    for (size_t p = 0; what.empty() && p < wc.pods.size(); ++p) {
+      const PodEntry &a = wc.pods[p], &b = wd.pods[p];
+      if (a.name != b.name || a.ns != b.ns || a.slots.size() != b.slots.size() || a.power_slots != b.power_slots)
+        what = "pod " + a.name;
+      for (size_t s = 0; what.empty() && s < a.slots.size(); ++s)
+        if (a.slots[s].hostname != b.slots[s].hostname || a.slots[s].gpu != b.slots[s].gpu ||
+            a.slots[s].container != b.slots[s].container || a.slots[s].model != b.slots[s].model ||
+            a.slots[s].node_type != b.slots[s].node_type || a.slots[s].from_prof != b.slots[s].from_prof)
+          what = "slot of " + a.name;
+    }
+    const IngestStats &sa = wc.stats, &sb = wd.stats;
+    if (what.empty() && (sa.series_in != sb.series_in || sa.series_skipped != sb.series_skipped ||
+                         sa.samples_in != sb.samples_in || sa.samples_out_of_window != sb.samples_out_of_window ||
+                         sa.duplicates_merged != sb.duplicates_merged ||
+                         sa.tiny_values_clamped != sb.tiny_values_clamped)) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "stats in %llu/%llu oow %llu/%llu tiny %llu/%llu series %llu/%llu",
+               (unsigned long long)sa.samples_in, (unsigned long long)sb.samples_in,
+               (unsigned long long)sa.samples_out_of_window, (unsigned long long)sb.samples_out_of_window,
+               (unsigned long long)sa.tiny_values_clamped, (unsigned long long)sb.tiny_values_clamped,
+               (unsigned long long)sa.series_in, (unsigned long long)sb.series_in);
+      what = buf;
+    }
+    if (what.empty()) {
+      const size_t cells = (size_t)wc.P * wc.G * wc.T;
+      const float* du = rep.on_device ? wd.d_util : wd.util.data();
+      const float* dp = rep.on_device ? wd.d_power : (wd.power.empty() ? nullptr : wd.power.data());
+      size_t at = 0;
+      // rows merged from several series may differ in the sign of a zero (max is order-independent
+      // up to that); everything else is bit-exact
+      const bool bits = sa.duplicates_merged == 0;
+      if (cells && !same_plane(wc.util.data(), du, cells, bits, &at)) what = "util cell " + std::to_string(at);
+      if (what.empty() && !wc.power.empty() && (!dp || !same_plane(wc.power.data(), dp, cells, bits, &at)))
+        what = "power cell " + std::to_string(at);
+      if (what.empty() && wc.power.empty() && rep.on_device && wd.d_power) what = "unexpected power plane";
+    }
+    if (!what.empty()) {
+      printf("MISMATCH %s %s\n", dir.c_str(), what.c_str());
+      ++bad;
+    } else {
+      printf("OK %s device=%d spans=%llu hard=%llu patched=%llu %s\n", dir.c_str(), (int)rep.on_device,
+             (unsigned long long)rep.spans, (unsigned long long)rep.hard_spans,
+             (unsigned long long)rep.rows_patched, rep.reason.c_str());
+    }
+  }
+  return bad ? 1 : 0;
+}
