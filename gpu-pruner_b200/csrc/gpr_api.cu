@@ -24,6 +24,7 @@
 
 #include "gpr_kernels.cuh"
 #include "gpr_synth.cuh"
+#include "gpr_text_kernels.cuh"
 
 namespace {
 
@@ -150,6 +151,18 @@ struct gpr_ctx {
   uint32_t idx_ld = 0;      // padded to a multiple of 4 (TMA-able rows), padding stays NaN
   float* d_cols = nullptr;
   size_t cols_cap = 0;
+
+  // device-side ingest of response text (gpr_text_scan / gpr_text_parse)
+  uint8_t* d_text[3] = {nullptr, nullptr, nullptr};
+  size_t text_cap[3] = {0, 0, 0};
+  uint64_t text_n[3] = {0, 0, 0};
+  uint64_t* d_marks = nullptr;  // [2][marks_cap]
+  size_t marks_cap = 0;         // total entries (both lists)
+  unsigned long long* d_mark_counts = nullptr;
+  gpr::text::Span* d_spans = nullptr;
+  size_t spans_cap = 0;
+  float* d_tplane[2] = {nullptr, nullptr};
+  size_t tplane_cap[2] = {0, 0};
 
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -732,7 +745,9 @@ void gpr_destroy(gpr_ctx* ctx) {
                  ctx->d_masks[0],   ctx->d_masks[1],    ctx->d_bits,       ctx->d_gather,
                  ctx->d_smax,       ctx->d_acc,         ctx->d_tickets,    ctx->d_done,
                  ctx->d_flush,      ctx->d_res_util,    ctx->d_res_power,  ctx->d_cols,
-                 ctx->d_idx_util,   ctx->d_idx_power};
+                 ctx->d_idx_util,   ctx->d_idx_power,   ctx->d_text[0],    ctx->d_text[1],
+                 ctx->d_text[2],    ctx->d_marks,       ctx->d_mark_counts, ctx->d_spans,
+                 ctx->d_tplane[0],  ctx->d_tplane[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -1212,6 +1227,113 @@ int gpr_get_device_info(gpr_ctx* ctx, gpr_device_info* info) {
 }
 
 // ---- synthetic windows -----------------------------------------------------------------------------
+// ---- device-side ingest of the response text -------------------------------------------------------
+static_assert(sizeof(gpr_text_span) == sizeof(gpr::text::Span) && offsetof(gpr_text_span, row) == offsetof(gpr::text::Span, row) &&
+                  offsetof(gpr_text_span, n_tiny) == offsetof(gpr::text::Span, n_tiny),
+              "gpr_text_span mirrors gpr::text::Span");
+static_assert(GPR_SPAN_SHARED == gpr::text::kSpanShared && GPR_SPAN_HARD == gpr::text::kSpanHard, "span flags");
+
+int gpr_text_scan(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes, int32_t mem_kind,
+                  uint64_t* opens, uint64_t* closes, uint64_t cap, uint64_t* n_opens, uint64_t* n_closes) {
+  if (!ctx) return GPR_E_INVALID;
+  NvtxRange nvtx_range("gpr_text_scan");
+  if (slot < 0 || slot > 2) return fail(ctx, GPR_E_INVALID, "text slot %d (0..2)", slot);
+  if ((!text && n_bytes) || !n_opens || !n_closes || (cap && (!opens || !closes)))
+    return fail(ctx, GPR_E_INVALID, "text / output arrays are NULL");
+  if (mem_kind != GPR_MEM_HOST && mem_kind != GPR_MEM_DEVICE) return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", mem_kind);
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_text[slot], &ctx->text_cap[slot], (size_t)n_bytes + gpr::text::kTextPad)) != GPR_OK)
+    return rc;
+  if ((rc = grow(ctx, &ctx->d_marks, &ctx->marks_cap, (size_t)2 * cap + 2)) != GPR_OK) return rc;
+  if (!ctx->d_mark_counts) CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_mark_counts), 2 * sizeof(unsigned long long)));
+  uint8_t* d = ctx->d_text[slot];
+  if (n_bytes)
+    CU(cudaMemcpyAsync(d, text, n_bytes, mem_kind == GPR_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  CU(cudaMemsetAsync(d + n_bytes, 0, gpr::text::kTextPad, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_mark_counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  ctx->text_n[slot] = n_bytes;
+  ctx->last_was_reduce = false;
+  unsigned long long counts[2] = {0, 0};
+  if (n_bytes) {
+    const uint64_t slices = (n_bytes + gpr::text::kScanBytes - 1) / gpr::text::kScanBytes;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((slices + 255) / 256, (uint64_t)ctx->sm_count * 32);
+    gpr::text::k_text_scan<<<grid, 256, 0, ctx->stream>>>(d, n_bytes, ctx->d_marks, ctx->d_marks + cap,
+                                                           ctx->d_mark_counts, cap);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(counts, ctx->d_mark_counts, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *n_opens = counts[0], *n_closes = counts[1];
+  const uint64_t no = std::min<uint64_t>(counts[0], cap), nc = std::min<uint64_t>(counts[1], cap);
+  if (no) CU(cudaMemcpyAsync(opens, ctx->d_marks, no * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nc) CU(cudaMemcpyAsync(closes, ctx->d_marks + cap, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (counts[0] > cap || counts[1] > cap)
+    return fail(ctx, GPR_E_CAPACITY, "%llu / %llu markers, room for %llu: call again with a larger cap", counts[0],
+                counts[1], (unsigned long long)cap);
+  return GPR_OK;
+}
+
+int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_spans, int64_t t_end, int64_t step,
+                   uint32_t n_samples, uint32_t n_rows, int32_t plane, uint32_t flags) {
+  if (!ctx) return GPR_E_INVALID;
+  NvtxRange nvtx_range("gpr_text_parse");
+  if (slot < 0 || slot > 2 || plane < 0 || plane > 1) return fail(ctx, GPR_E_INVALID, "bad slot %d / plane %d", slot, plane);
+  if (!ctx->d_text[slot]) return fail(ctx, GPR_E_STATE, "no text in slot %d (gpr_text_scan)", slot);
+  if (n_spans && !spans) return fail(ctx, GPR_E_INVALID, "spans is NULL");
+  if (step <= 0 || n_samples == 0) return fail(ctx, GPR_E_INVALID, "step and n_samples must be > 0");
+  const uint64_t n = ctx->text_n[slot];
+  for (uint32_t i = 0; i < n_spans; ++i) {
+    if (spans[i].begin > spans[i].end || spans[i].end > n || spans[i].row >= n_rows ||
+        (i && spans[i].begin < spans[i - 1].end))
+      return fail(ctx, GPR_E_INVALID, "span %u is out of order, out of the text or out of the plane", i);
+    spans[i].flags &= GPR_SPAN_SHARED;
+    spans[i].n_in = spans[i].n_oow = spans[i].n_tiny = 0;
+  }
+  CU(cudaSetDevice(ctx->device));
+  const size_t cells = (size_t)n_rows * n_samples;
+  int rc;
+  const size_t cap_before = ctx->tplane_cap[plane];
+  if ((rc = grow(ctx, &ctx->d_tplane[plane], &ctx->tplane_cap[plane], cells + 4)) != GPR_OK) return rc;
+  if (ctx->tplane_cap[plane] != cap_before && !(flags & GPR_TEXT_FILL))
+    return fail(ctx, GPR_E_STATE, "plane %d had to grow: the first parse of a window must pass GPR_TEXT_FILL", plane);
+  if ((rc = grow(ctx, &ctx->d_spans, &ctx->spans_cap, (size_t)n_spans + 1)) != GPR_OK) return rc;
+  ctx->last_was_reduce = false;
+  float* pl = ctx->d_tplane[plane];
+  if ((flags & GPR_TEXT_FILL) && cells) {
+    const uint64_t n_vec = (cells + 3) / 4;  // the plane is allocated with 4 cells of slack
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_vec + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    gpr::text::k_text_fill_nan<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(pl), n_vec);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  if (n_spans && n) {
+    CU(cudaMemcpyAsync(ctx->d_spans, spans, (size_t)n_spans * sizeof(gpr_text_span), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    const uint64_t slices = (n + gpr::text::kParseBytes - 1) / gpr::text::kParseBytes;
+    const uint64_t blocks = (slices + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(ctx, GPR_E_CAPACITY, "text too large");
+    const gpr::text::Grid g{t_end, step, n_samples, 0u};
+    gpr::text::k_text_parse<<<(uint32_t)blocks, 256, 0, ctx->stream>>>(ctx->d_text[slot], n, ctx->d_spans, n_spans, g, pl);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(spans, ctx->d_spans, (size_t)n_spans * sizeof(gpr_text_span), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+int gpr_text_planes(gpr_ctx* ctx, float** util, float** power) {
+  if (!ctx) return GPR_E_INVALID;
+  if (util) *util = ctx->d_tplane[0];
+  if (power) *power = ctx->d_tplane[1];
+  return GPR_OK;
+}
+
 int gpr_synth_fill(gpr_ctx* ctx, uint64_t seed, int32_t plane, float* dst, uint64_t pod_offset,
                    uint32_t n_pods, uint32_t n_gpus, uint32_t n_samples, uint64_t row_stride) {
   if (!ctx) return GPR_E_INVALID;

@@ -29,6 +29,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GPR_HD __host__ __device__ __forceinline__
@@ -234,19 +235,35 @@ template <typename Sink>
 GPR_HD void scan_slice(const uint8_t* __restrict__ t, uint64_t n, uint64_t slice, Sink& sink) {
   const uint64_t b = slice * kScanBytes;
   if (b >= n) return;
-  const uint64_t e = b + kScanBytes < n ? b + kScanBytes : n;
-  for (uint64_t p = b; p < e; ++p) {
-    const uint8_t c = t[p];
+  // the slice's 16 bytes plus 4 of look-ahead live in registers (the text is padded, so reading
+  // past n is safe; `t` is 16-byte aligned and slices are 16 bytes, so the vector load is aligned)
+  uint32_t w[5];
+#if defined(__CUDA_ARCH__)
+  const uint4 x = *reinterpret_cast<const uint4*>(t + b);
+  w[0] = x.x, w[1] = x.y, w[2] = x.z, w[3] = x.w;
+  w[4] = *reinterpret_cast<const uint32_t*>(t + b + 16);
+#else
+  memcpy(w, t + b, sizeof w);
+#endif
+#define GPR_TEXT_BYTE(k) ((w[(k) >> 2] >> (((k)&3) * 8)) & 0xffu)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < (int)kScanBytes; ++k) {
+    const uint64_t p = b + (uint64_t)k;
+    if (p >= n) break;
+    const uint32_t c = GPR_TEXT_BYTE(k);
     if (c == '"') {
-      if (t[p + 1] == ']' && t[p + 2] == ']') sink.values_close(p);
+      if (GPR_TEXT_BYTE(k + 1) == ']' && GPR_TEXT_BYTE(k + 2) == ']') sink.values_close(p);
     } else if (c == '}') {
-      // },"values":[
+      // },"values":[   (rare: once per series, plus the '}' that end label maps)
       if (t[p + 1] == ',' && t[p + 2] == '"' && t[p + 3] == 'v' && t[p + 4] == 'a' && t[p + 5] == 'l' &&
           t[p + 6] == 'u' && t[p + 7] == 'e' && t[p + 8] == 's' && t[p + 9] == '"' && t[p + 10] == ':' &&
           t[p + 11] == '[')
         sink.values_open(p);
     }
   }
+#undef GPR_TEXT_BYTE
 }
 
 // ---- the parse pass: one slice of kParseBytes ----------------------------------------------------------------

@@ -335,6 +335,45 @@ class IdleEngine:
                 "cc": (info.cc_major, info.cc_minor), "l2_bytes": info.l2_bytes,
                 "hbm_bytes": info.hbm_bytes}
 
+    # ---- device-side ingest of the response text ------------------------------------------------
+    SPAN_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("row", "<u4"), ("flags", "<u4"),
+                           ("n_in", "<u4"), ("n_oow", "<u4"), ("n_tiny", "<u4"), ("reserved", "<u4")])
+
+    def text_scan(self, text, slot: int = 0, n_bytes: Optional[int] = None, mem_kind: int = ffi.GPR_MEM_HOST):
+        """Upload response text (bytes, or a pinned uint8 array from :meth:`host_array`) into ``slot`` and
+        return the sorted offsets of every ``},"values":[`` and ``"]]``."""
+        if isinstance(text, (bytes, bytearray)):
+            buf = np.frombuffer(text, dtype=np.uint8)
+        else:
+            buf = text
+        n = int(buf.size if n_bytes is None else n_bytes)
+        cap = max(1024, n // 256)
+        while True:
+            opens = np.empty(cap, np.uint64)
+            closes = np.empty(cap, np.uint64)
+            no, nc = C.c_uint64(0), C.c_uint64(0)
+            rc = self._lib.gpr_text_scan(self._h, slot, _ptr(buf), n, mem_kind, _ptr(opens), _ptr(closes), cap,
+                                         C.byref(no), C.byref(nc))
+            if rc == ffi.GPR_E_CAPACITY:
+                cap = int(max(no.value, nc.value)) + 16
+                continue
+            self._check(rc)
+            return np.sort(opens[:no.value]), np.sort(closes[:nc.value])
+
+    def text_parse(self, spans: np.ndarray, t_end: int, step: int, T: int, n_rows: int, slot: int = 0,
+                   plane: int = 0, fill: bool = True) -> np.ndarray:
+        """Parse the samples of ``spans`` (structured array of SPAN_DTYPE, sorted by begin) of the text in
+        ``slot`` into the context's plane; returns the spans with their out-fields filled."""
+        spans = np.ascontiguousarray(spans, dtype=self.SPAN_DTYPE)
+        self._check(self._lib.gpr_text_parse(self._h, slot, _ptr(spans), len(spans), int(t_end), int(step), int(T),
+                                             int(n_rows), plane, ffi.GPR_TEXT_FILL if fill else 0))
+        return spans
+
+    def text_planes(self):
+        u, w = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.gpr_text_planes(self._h, C.byref(u), C.byref(w)))
+        return u.value, w.value
+
     def synth_fill(self, seed: int, plane: int, dst, pod_offset: int, P: int, G: int, T: int,
                    row_stride: int = 0):
         self._check(self._lib.gpr_synth_fill(self._h, seed, plane, _ptr(dst), pod_offset, P, G, T,

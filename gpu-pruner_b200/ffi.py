@@ -62,6 +62,15 @@ class gpr_device_info(C.Structure):
     ]
 
 
+class gpr_text_span(C.Structure):
+    _fields_ = [
+        ("begin", C.c_uint64), ("end", C.c_uint64), ("row", C.c_uint32), ("flags", C.c_uint32),
+        ("n_in", C.c_uint32), ("n_oow", C.c_uint32), ("n_tiny", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+GPR_SPAN_SHARED, GPR_SPAN_HARD, GPR_TEXT_FILL = 1, 2, 1
+
 _P = C.c_void_p
 # name -> (restype, argtypes); must list every symbol include/gpr.h declares
 PROTOTYPES = {
@@ -93,6 +102,11 @@ PROTOTYPES = {
     "gpr_flush_l2": (C.c_int, [_P]),
     "gpr_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "gpr_get_device_info": (C.c_int, [_P, C.POINTER(gpr_device_info)]),
+    "gpr_text_scan": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, C.c_int32, _P, _P, C.c_uint64,
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gpr_text_parse": (C.c_int, [_P, C.c_int32, _P, C.c_uint32, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
+                                 C.c_int32, C.c_uint32]),
+    "gpr_text_planes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "gpr_synth_fill": (C.c_int, [_P, C.c_uint64, C.c_int32, _P, C.c_uint64, C.c_uint32,
                                  C.c_uint32, C.c_uint32, C.c_uint64]),
     "gpr_synth_eligible": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_uint32]),

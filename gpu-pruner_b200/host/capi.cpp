@@ -355,3 +355,51 @@ GPH_API int gph_run_tick(const char* args, int n, const unsigned* candidate_bits
     return put(std::string("{\"ok\":false,\"error\":\"") + gph::json_escape(e.what()) + "\"}", out, cap);
   }
 }
+
+// Synthetic range-query response in Prometheus' compact encoding, written at memory speed (for the
+// ingest benchmarks: P pods x G GPUs, n samples each ending at t_end, DCGM-like integer percentages with
+// ~60 % idle series).  Returns the number of bytes written, or -needed if `cap` is too small.
+GPH_API long long gph_synth_response(unsigned P, unsigned G, unsigned n, long long t_end, unsigned long long seed,
+                                     char* out, long long cap) {
+  auto mix = [](unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+  };
+  const long long need = 64 + (long long)P * G * (260 + (long long)n * 19);
+  if (!out || cap < need) return -need;
+  char* p = out;
+  auto lit = [&](const char* s) {
+    const size_t k = strlen(s);
+    memcpy(p, s, k), p += k;
+  };
+  auto num = [&](unsigned long long v) {
+    char tmp[24];
+    int k = 0;
+    do tmp[k++] = (char)('0' + v % 10), v /= 10; while (v);
+    while (k) *p++ = tmp[--k];
+  };
+  lit("{\"status\":\"success\",\"data\":{\"resultType\":\"matrix\",\"result\":[");
+  for (unsigned pod = 0; pod < P; ++pod)
+    for (unsigned g = 0; g < G; ++g) {
+      if (pod || g) *p++ = ',';
+      lit("{\"metric\":{\"__name__\":\"DCGM_FI_DEV_GPU_UTIL\",\"Hostname\":\"node-"), num(pod % 512);
+      lit("\",\"UUID\":\"GPU-"), num(pod), *p++ = '-', num(g);
+      lit("\",\"device\":\"nvidia"), num(g), lit("\",\"exported_container\":\"main\",\"exported_namespace\":\"ns-");
+      num(pod % 64), lit("\",\"exported_pod\":\"pod-"), num(pod), lit("\",\"gpu\":\""), num(g);
+      lit("\",\"instance\":\"10.0.0.1:9400\",\"job\":\"dcgm\",\"modelName\":\"NVIDIA B200\"},\"values\":[");
+      const unsigned long long hs = mix(seed ^ ((unsigned long long)pod * G + g));
+      const bool idle = hs % 100 < 60;
+      for (unsigned i = 0; i < n; ++i) {
+        if (i) *p++ = ',';
+        *p++ = '[', num((unsigned long long)(t_end - (long long)n + 1 + i)), lit(",\"");
+        const unsigned long long hc = mix(hs ^ i);
+        num(idle ? 0 : ((hc >> 10) & 1 ? 1 + (hc >> 11) % 100 : 0));
+        lit("\"]");
+      }
+      lit("]}");
+    }
+  lit("]}}");
+  return (long long)(p - out);
+}

@@ -56,7 +56,8 @@ bool file_exists(const std::string& p) {
 // file://DIR with util.json [prof.json] [power.json] [query.json = {"end": ts, "step": s}]
 class FileSource : public WindowSource {
  public:
-  explicit FileSource(std::string dir) : dir_(std::move(dir)) {}
+  FileSource(std::string dir, TextIngestor* ingestor, const Logger* log)
+      : dir_(std::move(dir)), ingestor_(ingestor), log_(log) {}
   Window fetch(const Cli& args) override {
     const std::string up = dir_ + "/util.json";
     if (!file_exists(up)) throw std::runtime_error("Failed to run query! " + up + " not found");
@@ -79,11 +80,33 @@ class FileSource : public WindowSource {
       opt.t_end = (int64_t)meta["end"].as_number(0);
       opt.step = (int64_t)meta["step"].as_number(0);
     }
-    return ingest_matrix_text(util, pprof, ppower, opt);
+    if (!ingestor_) return ingest_matrix_text(util, pprof, ppower, opt);
+    std::string note;
+    Window w = ingestor_->ingest(args, util, pprof, ppower, opt, &note);
+    if (log_ && !note.empty()) log_->info(note);
+    return w;
   }
 
  private:
   std::string dir_;
+  TextIngestor* ingestor_;
+  const Logger* log_;
+};
+
+class CpuTextIngestor : public TextIngestor {
+ public:
+  Window ingest(const Cli&, const std::string& util, const std::string* prof, const std::string* power,
+                const IngestOptions& opt, std::string* note) override {
+    const auto t0 = std::chrono::steady_clock::now();
+    Window w = ingest_matrix_text(util, prof, power, opt);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (note) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "Device ingest not used (GPR_INGEST=cpu): CPU text parser, %.1f ms", ms);
+      *note = buf;
+    }
+    return w;
+  }
 };
 
 class UnsupportedSource : public WindowSource {
@@ -100,8 +123,10 @@ class UnsupportedSource : public WindowSource {
 
 }  // namespace
 
-std::unique_ptr<WindowSource> make_window_source(const std::string& url) {
-  if (url.rfind("file://", 0) == 0) return std::make_unique<FileSource>(url.substr(7));
+std::unique_ptr<TextIngestor> make_cpu_text_ingestor() { return std::make_unique<CpuTextIngestor>(); }
+
+std::unique_ptr<WindowSource> make_window_source(const std::string& url, TextIngestor* ingestor, const Logger* log) {
+  if (url.rfind("file://", 0) == 0) return std::make_unique<FileSource>(url.substr(7), ingestor, log);
   return std::make_unique<UnsupportedSource>(url);
 }
 
@@ -164,7 +189,7 @@ TickResult Controller::run_query_and_scale(const Window& w) {
   if (P > 0) {
     VerdictRequest rq;
     rq.window = &w;
-    rq.power_on = !w.power.empty() && args_.power_threshold && *args_.power_threshold != 0.0;
+    rq.power_on = (!w.power.empty() || w.d_power) && args_.power_threshold && *args_.power_threshold != 0.0;
     rq.power_threshold = rq.power_on ? *args_.power_threshold : 0.0;
     rq.eligible = kube_ ? eligible.data() : nullptr;
     rq.created_ts = kube_ ? created.data() : nullptr;

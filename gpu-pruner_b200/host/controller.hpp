@@ -74,10 +74,20 @@ struct Verdict {
   uint64_t n_series = 0, n_candidates = 0, n_decisions = 0;
   double kernel_ms = 0;
 };
+// Turns the raw range-query responses into a Window.  Default: the threaded CPU text parser
+// (ingest_matrix_text).  The product engine also offers one that parses the text on the GPU straight
+// into HBM (ingest_device.hpp); selected with GPR_INGEST=gpu.
+class TextIngestor {
+ public:
+  virtual ~TextIngestor() = default;
+  virtual Window ingest(const Cli& args, const std::string& util, const std::string* prof, const std::string* power,
+                        const IngestOptions& opt, std::string* note) = 0;
+};
 class VerdictEngine {
  public:
   virtual ~VerdictEngine() = default;
   virtual bool decide(const VerdictRequest& rq, Verdict* out, std::string* error) = 0;
+  virtual TextIngestor* text_ingestor() { return nullptr; }   // device-side ingest, if the engine has one
 };
 std::unique_ptr<VerdictEngine> make_gpr_engine();   // gpr_engine.cpp (links libgpr.so)
 
@@ -87,7 +97,11 @@ class WindowSource {
   virtual ~WindowSource() = default;
   virtual Window fetch(const Cli& args) = 0;   // throws std::runtime_error on failure
 };
-std::unique_ptr<WindowSource> make_window_source(const std::string& url);
+// The default CPU text parser behind the TextIngestor interface, reporting its time the way the device
+// ingestor does (GPR_INGEST=cpu; used to compare the two on the same fixtures).
+std::unique_ptr<TextIngestor> make_cpu_text_ingestor();
+std::unique_ptr<WindowSource> make_window_source(const std::string& url, TextIngestor* ingestor = nullptr,
+                                                 const Logger* log = nullptr);
 
 class Controller {
  public:

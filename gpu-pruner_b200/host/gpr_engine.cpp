@@ -1,37 +1,61 @@
 // gpr_engine.cpp — the product VerdictEngine: libgpr.so (include/gpr.h), CUDA on sm_100a.
 // There is no other implementation in the product; without a CUDA device every tick fails and is
 // counted like a failed Prometheus query in the reference (main.rs:310-321).
+//
+// The same object is the product's TextDevice / TextIngestor (GPR_INGEST=gpu): the response text is
+// parsed on the GPU straight into HBM and the decision runs on those device planes — the f32 window
+// never crosses PCIe, only the text does (once).
+#include <chrono>
 #include <cstring>
+#include <stdexcept>
 
 #include "../../include/gpr.h"
 #include "controller.hpp"
+#include "ingest_device.hpp"
 
 namespace gph {
 namespace {
 
-class GprVerdictEngine : public VerdictEngine {
+class GprVerdictEngine : public VerdictEngine, public TextIngestor, private TextDevice {
  public:
   ~GprVerdictEngine() override {
-    if (ctx_) gpr_destroy(ctx_);
+    if (ctx_) {
+      if (d_elig_) gpr_device_free(ctx_, d_elig_);
+      if (d_created_) gpr_device_free(ctx_, d_created_);
+      if (h_text_) gpr_host_free(ctx_, h_text_);
+      gpr_destroy(ctx_);
+    }
   }
 
+  TextIngestor* text_ingestor() override { return this; }
+
+  // ---- VerdictEngine --------------------------------------------------------------------------------
   bool decide(const VerdictRequest& rq, Verdict* out, std::string* error) override {
     const Window& w = *rq.window;
-    if (!ensure(w, rq.power_on, rq.gpu_device, error)) return false;
+    const bool on_device = w.d_util != nullptr;
+    if (on_device ? !ensure_ctx(rq.gpu_device, error) : !ensure(w, rq.power_on, rq.gpu_device, error)) return false;
     const uint32_t W = (w.P + 31) / 32;
     out->decision_bits.assign(W, 0), out->candidate_bits.assign(W, 0);
     out->series_max.assign((size_t)w.P * w.G, 0.f);
     gpr_window win;
     memset(&win, 0, sizeof win);
     win.struct_size = sizeof win;
-    win.mem_kind = GPR_MEM_HOST;
-    win.util = w.util.data();
-    win.power = rq.power_on ? w.power.data() : nullptr;
     win.power_threshold = rq.power_on ? rq.power_threshold : 0.0;
-    win.eligible = rq.eligible;
-    win.created_ts = rq.created_ts;
     win.cutoff_ts = rq.cutoff_ts;
     win.n_pods = w.P, win.n_gpus = w.G, win.n_samples = w.T;
+    if (on_device) {
+      // planes are in HBM already (device ingest); mem_kind covers the gates too, so they follow
+      win.mem_kind = GPR_MEM_DEVICE;
+      win.util = w.d_util;
+      win.power = rq.power_on ? w.d_power : nullptr;
+      if (!upload_gates(rq, w.P, &win, error)) return false;
+    } else {
+      win.mem_kind = GPR_MEM_HOST;
+      win.util = w.util.data();
+      win.power = rq.power_on ? w.power.data() : nullptr;
+      win.eligible = rq.eligible;
+      win.created_ts = rq.created_ts;
+    }
     gpr_result res;
     memset(&res, 0, sizeof res);
     res.struct_size = sizeof res;
@@ -49,19 +73,132 @@ class GprVerdictEngine : public VerdictEngine {
     return true;
   }
 
+  // ---- TextIngestor ---------------------------------------------------------------------------------
+  Window ingest(const Cli& args, const std::string& util, const std::string* prof, const std::string* power,
+                const IngestOptions& opt, std::string* note) override {
+    std::string error;
+    if (!ensure_ctx(args.gpu_device, &error)) throw std::runtime_error("Failed to run query! " + error);
+    const auto t0 = std::chrono::steady_clock::now();
+    DeviceIngestReport rep;
+    Window w = ingest_matrix_device(*this, util, prof, power, opt, &rep);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (note) {
+      char buf[320];
+      if (rep.on_device)
+        snprintf(buf, sizeof buf,
+                 "Device ingest: %llu series lists parsed on the GPU into a %ux%ux%u window in %.1f ms "
+                 "(%llu re-parsed on the CPU, %llu rows patched)",
+                 (unsigned long long)rep.spans, w.P, w.G, w.T, ms, (unsigned long long)rep.hard_spans,
+                 (unsigned long long)rep.rows_patched);
+      else
+        snprintf(buf, sizeof buf, "Device ingest not used (%s): CPU text parser, %.1f ms", rep.reason.c_str(), ms);
+      *note = buf;
+    }
+    return w;
+  }
+
  private:
+  // ---- TextDevice over libgpr -------------------------------------------------------------------------
+  void check(int rc, const char* what) {
+    if (rc != GPR_OK) throw std::runtime_error(std::string(what) + " (" + std::to_string(rc) + "): " + gpr_last_error(ctx_));
+  }
+  void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens, std::vector<uint64_t>* closes) override {
+    // stage through pinned memory: a pageable source would move at a fraction of PCIe speed
+    if (n > h_text_cap_) {
+      if (h_text_) gpr_host_free(ctx_, h_text_), h_text_ = nullptr, h_text_cap_ = 0;
+      check(gpr_host_alloc(ctx_, n + n / 8 + 4096, &h_text_), "pinned text buffer");
+      h_text_cap_ = n + n / 8 + 4096;
+    }
+    if (n) memcpy(h_text_, text, n);
+    uint64_t cap = n / 256 + 4096, no = 0, nc = 0;
+    while (true) {
+      opens->resize(cap), closes->resize(cap);
+      const int rc = gpr_text_scan(ctx_, slot, static_cast<const char*>(h_text_), n, GPR_MEM_HOST, opens->data(),
+                                   closes->data(), cap, &no, &nc);
+      if (rc == GPR_E_CAPACITY) {
+        cap = std::max(no, nc) + 16;
+        continue;
+      }
+      check(rc, "gpr_text_scan");
+      break;
+    }
+    opens->resize(no), closes->resize(nc);
+  }
+  void parse(int slot, std::vector<gpr_text_span>& spans, int64_t t_end, int64_t step, uint32_t T, uint32_t n_rows,
+             int plane, bool fill) override {
+    check(gpr_text_parse(ctx_, slot, spans.data(), (uint32_t)spans.size(), t_end, step, T, n_rows, plane,
+                         fill ? GPR_TEXT_FILL : 0u),
+          "gpr_text_parse");
+  }
+  void patch_row(int plane, uint32_t row, uint32_t T, const float* data) override {
+    float *u = nullptr, *p = nullptr;
+    check(gpr_text_planes(ctx_, &u, &p), "gpr_text_planes");
+    float* base = plane == 0 ? u : p;
+    check(gpr_memcpy(ctx_, base + (size_t)row * T, data, (size_t)T * sizeof(float), GPR_MEM_DEVICE, GPR_MEM_HOST),
+          "row patch");
+  }
+  const float* plane(int plane) override {
+    float *u = nullptr, *p = nullptr;
+    check(gpr_text_planes(ctx_, &u, &p), "gpr_text_planes");
+    return plane == 0 ? u : p;
+  }
+
+  // ---- context ------------------------------------------------------------------------------------------
+  bool upload_gates(const VerdictRequest& rq, uint32_t P, gpr_window* win, std::string* error) {
+    if (P > gate_cap_) {
+      if (d_elig_) gpr_device_free(ctx_, d_elig_), d_elig_ = nullptr;
+      if (d_created_) gpr_device_free(ctx_, d_created_), d_created_ = nullptr;
+      const size_t cap = (size_t)P + P / 4 + 64;
+      if (gpr_device_alloc(ctx_, cap, &d_elig_) != GPR_OK ||
+          gpr_device_alloc(ctx_, cap * sizeof(int64_t), &d_created_) != GPR_OK) {
+        *error = std::string("idle engine: gate buffers: ") + gpr_last_error(ctx_);
+        return false;
+      }
+      gate_cap_ = cap;
+    }
+    int rc = GPR_OK;
+    if (rq.eligible && P) {
+      rc = gpr_memcpy(ctx_, d_elig_, rq.eligible, P, GPR_MEM_DEVICE, GPR_MEM_HOST);
+      win->eligible = static_cast<const uint8_t*>(d_elig_);
+    }
+    if (rc == GPR_OK && rq.created_ts && P) {
+      rc = gpr_memcpy(ctx_, d_created_, rq.created_ts, (size_t)P * sizeof(int64_t), GPR_MEM_DEVICE, GPR_MEM_HOST);
+      win->created_ts = static_cast<const int64_t*>(d_created_);
+    }
+    if (rc != GPR_OK) {
+      *error = std::string("idle engine: gate upload: ") + gpr_last_error(ctx_);
+      return false;
+    }
+    return true;
+  }
+
+  // a context without host-window staging is enough for device-resident windows
+  bool ensure_ctx(int device, std::string* error) {
+    if (ctx_) return true;
+    return create(0, 1, 1, false, device, error);
+  }
   bool ensure(const Window& w, bool need_power, int device, std::string* error) {
     const uint64_t cells = (uint64_t)w.P * w.G * w.T;
     if (ctx_ && cells <= cap_cells_ && (!need_power || cap_power_)) return true;
-    if (ctx_) gpr_destroy(ctx_), ctx_ = nullptr;
+    drop();
+    // head-room so that a growing cluster does not re-create the context every tick
+    return create(w.P + w.P / 4 > 64 ? w.P + w.P / 4 : 64, w.G ? w.G : 1, w.T ? w.T : 1, need_power, device, error);
+  }
+  void drop() {
+    if (!ctx_) return;
+    if (d_elig_) gpr_device_free(ctx_, d_elig_), d_elig_ = nullptr;
+    if (d_created_) gpr_device_free(ctx_, d_created_), d_created_ = nullptr;
+    if (h_text_) gpr_host_free(ctx_, h_text_), h_text_ = nullptr;
+    gate_cap_ = 0, h_text_cap_ = 0;
+    gpr_destroy(ctx_), ctx_ = nullptr;
+  }
+  bool create(uint32_t max_pods, uint32_t max_gpus, uint32_t max_samples, bool need_power, int device,
+              std::string* error) {
     gpr_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg;
     cfg.device = device;
-    // head-room so that a growing cluster does not re-create the context every tick
-    cfg.max_pods = w.P + w.P / 4 > 64 ? w.P + w.P / 4 : 64;
-    cfg.max_gpus = w.G ? w.G : 1;
-    cfg.max_samples = w.T ? w.T : 1;
+    cfg.max_pods = max_pods, cfg.max_gpus = max_gpus, cfg.max_samples = max_samples;
     cfg.flags = need_power ? GPR_F_POWER_PLANE : 0;
     const int rc = gpr_create(&cfg, &ctx_);
     if (rc != GPR_OK) {
@@ -73,9 +210,15 @@ class GprVerdictEngine : public VerdictEngine {
     cap_power_ = need_power;
     return true;
   }
+
   gpr_ctx* ctx_ = nullptr;
   uint64_t cap_cells_ = 0;
   bool cap_power_ = false;
+  void* d_elig_ = nullptr;
+  void* d_created_ = nullptr;
+  size_t gate_cap_ = 0;
+  void* h_text_ = nullptr;
+  size_t h_text_cap_ = 0;
 };
 
 }  // namespace

@@ -298,15 +298,16 @@ typedef struct gpr_text_span {
  * full PCIe speed) and scan it.  Up to `cap` offsets are written to each of opens[] (position of the
  * '}' of `},"values":[`) and closes[] (position of the '"' of `"]]`), UNSORTED; the true counts are
  * returned in *n_opens / *n_closes (GPR_E_CAPACITY if either exceeds cap).  The text stays resident
- * in the context for gpr_text_parse until the next gpr_text_scan.  Blocking.                      */
-GPR_API int gpr_text_scan(gpr_ctx *ctx, const char *text, uint64_t n_bytes, int32_t mem_kind,
-                          uint64_t *opens, uint64_t *closes, uint64_t cap, uint64_t *n_opens,
-                          uint64_t *n_closes);
-/* Parse the samples of spans[0..n_spans) (host array, sorted by begin, non-overlapping) of the resident
- * text into plane `plane` (0 = util, 1 = power).  Out-fields of the spans are filled.  Blocking.   */
-GPR_API int gpr_text_parse(gpr_ctx *ctx, gpr_text_span *spans, uint32_t n_spans, int64_t t_end,
-                           int64_t step, uint32_t n_samples, uint32_t n_rows, int32_t plane,
-                           uint32_t flags);
+ * in the context's slot `slot` (0..2: a tick has up to three responses — PROF, UTIL, POWER) for
+ * gpr_text_parse until the next gpr_text_scan of that slot.  Blocking.                           */
+GPR_API int gpr_text_scan(gpr_ctx *ctx, int32_t slot, const char *text, uint64_t n_bytes,
+                          int32_t mem_kind, uint64_t *opens, uint64_t *closes, uint64_t cap,
+                          uint64_t *n_opens, uint64_t *n_closes);
+/* Parse the samples of spans[0..n_spans) (host array, sorted by begin, non-overlapping) of the text in
+ * `slot` into plane `plane` (0 = util, 1 = power).  Out-fields of the spans are filled.  Blocking.  */
+GPR_API int gpr_text_parse(gpr_ctx *ctx, int32_t slot, gpr_text_span *spans, uint32_t n_spans,
+                           int64_t t_end, int64_t step, uint32_t n_samples, uint32_t n_rows,
+                           int32_t plane, uint32_t flags);
 /* Device pointers of the planes (NULL if never parsed); valid until the next gpr_text_parse that has
  * to grow them, or gpr_destroy.  Hand them to gpr_decide with mem_kind = GPR_MEM_DEVICE.           */
 GPR_API int gpr_text_planes(gpr_ctx *ctx, float **util, float **power);

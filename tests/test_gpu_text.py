@@ -1,0 +1,297 @@
+"""GPU: the device-side ingest — Prometheus matrix JSON parsed by CUDA kernels straight into the tensor in
+HBM (include/gpr.h gpr_text_scan / gpr_text_parse, gpu-pruner_b200/csrc/gpr_text*.cuh) — against the CPU
+text ingest of the same bytes (gpu-pruner_b200/host/ingest.cpp through libgprhost.so): every tensor cell,
+the per-span statistics and the hard-span flags; then the whole product path (gpu-pruner binary with
+GPR_INGEST=gpu) against the same binary with the CPU ingest.  The same parser core runs on an emulated
+device in tests/test_text_device_cpu.py."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import hostlib as H
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+T_END = 1_700_000_000
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import gpu_pruner_b200 as g
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; the engine has no CPU fallback")
+    e = g.IdleEngine(device=0)
+    yield e
+    e.close()
+
+
+def _labels(p, g):
+    return {"__name__": "DCGM_FI_DEV_GPU_UTIL", "Hostname": f"node-{p % 7}", "gpu": str(g), "modelName": "NVIDIA B200",
+            "exported_pod": f"pod-{p}", "exported_namespace": f"ns-{p % 3}", "exported_container": "main",
+            "UUID": f"GPU-{p}-{g}", "note": 'tricky "]] },\\"values\\":[ bytes'}
+
+
+def _response(P, G, T, rng, values, n_samples=None, frac=False):
+    """series in (pod, gpu) order so that tensor row == series index on both paths"""
+    parts = []
+    for p in range(P):
+        for g in range(G):
+            n = T if n_samples is None else n_samples(p, g)
+            ts = np.arange(T_END - n + 1, T_END + 1)
+            vals = rng.choice(values, size=n)
+            if frac:
+                body = ",".join(f'[{t}.{int(rng.integers(0, 400)):03d},"{v}"]' for t, v in zip(ts, vals))
+            else:
+                body = ",".join(f'[{t},"{v}"]' for t, v in zip(ts, vals))
+            parts.append('{"metric":' + json.dumps(_labels(p, g), separators=(",", ":")) + ',"values":[' + body + "]}")
+    return ('{"status":"success","data":{"resultType":"matrix","result":[' + ",".join(parts) + "]}}").encode()
+
+
+def _cpu_ingest(text, duration_min, step=1):
+    """raw bytes -> (util[P,G,T], meta) through the CPU text path of libgprhost.so"""
+    lib = H.lib()
+    H.ingest_mode(0)
+    dims = (C.c_uint * 3)()
+    meta = C.create_string_buffer(1 << 22)
+    rc = lib.gph_ingest(text, None, None, C.c_longlong(duration_min), C.c_longlong(step), C.c_longlong(T_END), dims,
+                        None, None, meta, 1 << 22)
+    assert rc == 0, meta.value[:300]
+    P, G, T = dims[0], dims[1], dims[2]
+    u = np.zeros((P, G, T), np.float32)
+    rc = lib.gph_ingest(text, None, None, C.c_longlong(duration_min), C.c_longlong(step), C.c_longlong(T_END), dims,
+                        u.ctypes.data_as(C.c_void_p), None, meta, 1 << 22)
+    assert rc == 0
+    return u, json.loads(meta.value.decode())
+
+
+def _spans_from_markers(text, opens, closes, eng):
+    """what ingest_device.cpp does, reduced to 'row = series index'"""
+    spans = np.zeros(len(opens), eng.SPAN_DTYPE)
+    for i, o in enumerate(opens):
+        vb = int(o) + 12
+        if text[vb:vb + 1] == b"]":
+            spans[i]["begin"] = spans[i]["end"] = vb
+        else:
+            c = int(closes[np.searchsorted(closes, vb)])
+            spans[i]["begin"], spans[i]["end"] = vb, c + 2
+        spans[i]["row"] = i
+    return spans
+
+
+def _plane(eng, n_rows, T, plane=0):
+    ptr = eng.text_planes()[plane]
+    out = np.empty((n_rows, T), np.float32)
+    eng.memcpy(out, ptr, out.nbytes, 0, 1)
+    return out
+
+
+def _same(a, b):
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def test_marker_scan_finds_exactly_the_list_delimiters(eng):
+    rng = np.random.default_rng(1)
+    text = _response(37, 3, 50, rng, ["0", "7", "NaN"], n_samples=lambda p, g: [0, 1, 50][(p + g) % 3])
+    opens, closes = eng.text_scan(text)
+    exp_o = np.array([m.start() for m in re.finditer(rb'\},"values":\[', text)], np.uint64)
+    exp_c = np.array([m.start() for m in re.finditer(rb'"\]\]', text)], np.uint64)
+    assert len(exp_o) == 37 * 3
+    assert np.array_equal(opens, exp_o) and np.array_equal(closes, exp_c)
+
+
+@pytest.mark.parametrize("P,G,n,dur", [(1, 1, 1, 1), (5, 2, 60, 1), (7, 3, 75, 1), (64, 4, 180, 3), (300, 4, 1800, 30),
+                                       (33, 1, 7200, 120)])
+def test_parse_matches_cpu_ingest_on_plain_dcgm_values(P, G, n, dur, eng):
+    """n samples per series into a window of dur*60 one-second columns"""
+    rng = np.random.default_rng(P + n)
+    vals = [str(v) for v in range(0, 101)] + ["0"] * 300 + ["NaN"] * 5
+    text = _response(P, G, n, rng, vals)
+    W = dur * 60
+    u_cpu, meta = _cpu_ingest(text, dur)
+    assert u_cpu.shape == (P, G, W)
+    opens, closes = eng.text_scan(text)
+    spans = _spans_from_markers(text, opens, closes, eng)
+    out = eng.text_parse(spans, T_END, 1, W, P * G)
+    assert not np.any(out["flags"] & 2), "plain integer samples must not need the CPU"
+    assert int(out["n_in"].sum()) == P * G * n and int(out["n_oow"].sum()) == P * G * max(0, n - W)
+    assert int(out["n_oow"].sum()) == meta["samples_out_of_window"]
+    got = _plane(eng, P * G, W).reshape(P, G, W)
+    assert _same(got, u_cpu)
+    assert np.array_equal(np.isnan(got), np.isnan(u_cpu))
+
+
+def test_decimals_fractional_timestamps_and_out_of_window_samples(eng):
+    rng = np.random.default_rng(5)
+    vals = ["0", "0.5", "12.25", "1e2", "1E1", "-0", "+3", "Inf", "+Inf", "-Inf", "NaN", "149.99", "0.001", "99.9"]
+    P, G, T = 40, 2, 90
+    # series longer than the 60 s window: the oldest 30 samples fall out
+    text = _response(P, G, T, rng, vals, frac=True)
+    u_cpu, meta = _cpu_ingest(text, 1)
+    opens, closes = eng.text_scan(text)
+    spans = _spans_from_markers(text, opens, closes, eng)
+    out = eng.text_parse(spans, T_END, 1, 60, P * G)
+    got = _plane(eng, P * G, 60).reshape(P, G, 60)
+    hard = (out["flags"] & 2) != 0
+    ok_rows = ~hard.reshape(P, G)
+    assert ok_rows.sum() > P * G // 2          # fractional stamps that collide in one column go to the CPU
+    assert _same(got[ok_rows], u_cpu[ok_rows])
+    assert int(out["n_in"][~hard].sum()) == int((~hard).sum()) * T
+    assert int(out["n_oow"][~hard].sum()) >= int((~hard).sum()) * 28
+    assert meta["samples_out_of_window"] >= int(out["n_oow"][~hard].sum())
+
+
+def test_values_outside_the_exact_fast_path_mark_the_span_hard(eng):
+    rng = np.random.default_rng(9)
+    P, G, T = 30, 1, 40
+    parts, expect_hard = [], []
+    for p in range(P):
+        awkward = ["0.30000000000000004", "1e-50", "123456789012345678", "1e23", "0x10", "", "1.", ".5", "nan"][p % 9]
+        bad_at = int(rng.integers(0, T)) if p % 2 else -1
+        body = ",".join(f'[{T_END - T + 1 + i},"{awkward if i == bad_at else "0"}"]' for i in range(T))
+        parts.append('{"metric":' + json.dumps(_labels(p, 0), separators=(",", ":")) + ',"values":[' + body + "]}")
+        expect_hard.append(bad_at >= 0)
+    text = ('{"status":"success","data":{"resultType":"matrix","result":[' + ",".join(parts) + "]}}").encode()
+    opens, closes = eng.text_scan(text)
+    spans = _spans_from_markers(text, opens, closes, eng)
+    out = eng.text_parse(spans, T_END, 1, T, P)
+    assert [bool(f & 2) for f in out["flags"]] == expect_hard
+    got = _plane(eng, P, T)
+    assert np.all(got[~np.array(expect_hard)] == 0.0)
+
+
+def test_shared_rows_merge_and_second_parse_without_fill(eng):
+    """two series feeding one row (a `sum by` duplicate): NaN-aware max, whatever the thread order"""
+    T = 50
+    a = [("NaN" if i % 5 == 0 else str(i % 7)) for i in range(T)]
+    b = [("NaN" if i % 3 == 0 else str((i * 3) % 11)) for i in range(T)]
+    def ser(vals, uuid):
+        body = ",".join(f'[{T_END - T + 1 + i},"{v}"]' for i, v in enumerate(vals))
+        return '{"metric":' + json.dumps(dict(_labels(0, 0), UUID=uuid), separators=(",", ":")) + ',"values":[' + body + "]}"
+    text = ('{"status":"success","data":{"resultType":"matrix","result":[' + ser(a, "x") + "," + ser(b, "y") + "]}}").encode()
+    opens, closes = eng.text_scan(text)
+    spans = _spans_from_markers(text, opens, closes, eng)
+    spans["row"] = 0
+    spans["flags"] = 1      # GPR_SPAN_SHARED
+    eng.text_parse(spans, T_END, 1, T, 1)
+    fa = np.array([np.nan if v == "NaN" else float(v) for v in a], np.float32)
+    fb = np.array([np.nan if v == "NaN" else float(v) for v in b], np.float32)
+    exp = np.fmax(fa, fb)
+    assert _same(_plane(eng, 1, T)[0], exp)
+    u_cpu, _ = _cpu_ingest(text, 1)
+    assert _same(u_cpu[0, 0, -T:], exp)
+    # a second text into the same plane without refilling it (PROF first, then UTIL)
+    text2 = ('{"status":"success","data":{"resultType":"matrix","result":[' + ser(["9"] * T, "z") + "]}}").encode()
+    o2, c2 = eng.text_scan(text2, slot=1)
+    sp2 = _spans_from_markers(text2, o2, c2, eng)
+    sp2["flags"] = 1
+    eng.text_parse(sp2, T_END, 1, T, 1, slot=1, fill=False)
+    assert np.all(_plane(eng, 1, T)[0] == 9.0)
+
+
+def test_parsed_planes_feed_the_decision_kernels(eng, oracle_c):
+    """text -> HBM tensor -> verdict without the window ever existing on the host"""
+    rng = np.random.default_rng(21)
+    P, G, T = 200, 4, 120
+    vals = ["0"] * 50 + ["0", "3", "100", "NaN"]
+    def n_samples(p, g):
+        return [T, T, T // 2, 0][(p * 3 + g) % 4]
+    text = _response(P, G, T, rng, vals, n_samples=n_samples)
+    opens, closes = eng.text_scan(text)
+    spans = _spans_from_markers(text, opens, closes, eng)
+    # empty lists are not elements: the CPU ingest gives those (pod, gpu) no slot; emulate its row layout
+    # by keeping 'row = pod * G + gpu' only for this all-pods-present layout
+    keep = spans["begin"] != spans["end"]
+    u_dev_rows = P * G
+    eng.text_parse(spans[keep], T_END, 1, T, u_dev_rows)
+    ptr = eng.text_planes()[0]
+    db = torch.zeros((P + 31) // 32, dtype=torch.int32, device="cuda:0")
+    cb = torch.zeros((P + 31) // 32, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
+    r = eng.decide_ptr(ptr, P, G, T, db, candidate_bits=cb)
+    got = _plane(eng, P * G, T).reshape(P, G, T)
+    exp = oracle_c.decide(got)
+    assert np.array_equal(db.cpu().numpy().view(np.uint32), exp["decision_bits"])
+    assert (r.n_series, r.n_candidates, r.n_decisions) == (exp["n_series"], exp["n_candidates"], exp["n_decisions"])
+    assert 0 < r.n_decisions < P
+
+
+def test_error_paths(eng):
+    import gpu_pruner_b200 as g
+    text = _response(2, 1, 5, np.random.default_rng(0), ["0"])
+    opens, closes = eng.text_scan(text)
+    spans = _spans_from_markers(text, opens, closes, eng)
+    for mutate in (lambda s: s.__setitem__("row", 99), lambda s: s.__setitem__("end", len(text) + 50),
+                   lambda s: s["begin"].__setitem__(1, 1)):
+        bad = spans.copy()
+        mutate(bad)
+        with pytest.raises(g.GprError) as ei:
+            eng.text_parse(bad, T_END, 1, 5, 2)
+        assert ei.value.code == g.ffi.GPR_E_INVALID
+    with pytest.raises(g.GprError):
+        eng.text_parse(spans, T_END, 0, 5, 2)              # step must be > 0
+    with pytest.raises(g.GprError):
+        eng.text_parse(spans, T_END, 1, 5, 2, slot=2)      # nothing scanned into slot 2
+    o, c = eng.text_scan(b"")                             # empty text: no markers
+    assert len(o) == 0 and len(c) == 0
+
+
+# ---- the product path: gpu-pruner binary, GPR_INGEST=gpu vs the CPU ingest ------------------------------
+from hostworld import NOW, build_world  # noqa: E402
+
+
+def _run_bin(world, ingest, *extra):
+    tmp, prom, kube = world
+    out = tmp / f"patches-{ingest}.jsonl"
+    cmd = [H.BIN, "--prometheus-url", f"file://{prom}", "--kube-fixture", str(kube), "-t", "2", "-g", "300",
+           "--now", str(NOW), "--patch-out", str(out), "-l", "json", *extra]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, GPR_INGEST=ingest))
+    logs = [json.loads(l) for l in p.stderr.splitlines() if l.startswith("{")]
+    reqs = [json.loads(l) for l in out.read_text().splitlines()] if out.exists() else []
+    return p, logs, reqs
+
+
+def _strip(reqs):
+    """requests minus what differs run to run (event names are uuid4, timestamps are wall clock)"""
+    out = []
+    for r in reqs:
+        b = json.loads(json.dumps(r["body"]))
+        for k in ("metadata", "eventTime", "firstTimestamp", "lastTimestamp"):
+            if r["method"] == "POST":
+                b.pop(k, None)
+        if "metadata" in b and "annotations" in b["metadata"]:
+            b["metadata"]["annotations"] = sorted(b["metadata"]["annotations"])
+        out.append((r["method"], r["path"], json.dumps(b, sort_keys=True)))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("extra", [(), ("-r", "scale-down"), ("-r", "scale-down", "--power-threshold", "150")])
+def test_binary_with_device_ingest_behaves_like_the_cpu_ingest(extra, tmp_path):
+    world = build_world(tmp_path)
+    tmp, prom, kube = world
+    for name in ("util.json", "power.json"):      # Prometheus' compact encoding (the fixtures are pretty)
+        f = prom / name
+        f.write_text(json.dumps(json.loads(f.read_text()), separators=(",", ":")))
+    pc, logs_c, reqs_c = _run_bin(world, "cpu", *extra)
+    pg, logs_g, reqs_g = _run_bin(world, "gpu", *extra)
+    assert pc.returncode == 0 and pg.returncode == 0, pg.stderr
+    msgs_c = [l["fields"]["message"] for l in logs_c]
+    msgs_g = [l["fields"]["message"] for l in logs_g]
+    note = [m for m in msgs_g if m.startswith("Device ingest")]
+    assert note and "parsed on the GPU" in note[0], msgs_g[:6]
+    assert [m for m in msgs_g if not m.startswith("Device ingest")] == msgs_c
+    assert _strip(reqs_g) == _strip(reqs_c)
+
+
+def test_binary_falls_back_to_the_cpu_parser_for_other_encodings(tmp_path):
+    world = build_world(tmp_path)        # json.dumps default separators: not the compact encoding
+    pg, logs_g, _ = _run_bin(world, "gpu")
+    assert pg.returncode == 0
+    msgs = [l["fields"]["message"] for l in logs_g]
+    assert any(m.startswith("Device ingest not used") for m in msgs)
+    assert "Query returned 11 series across 10 unique pods" in msgs
