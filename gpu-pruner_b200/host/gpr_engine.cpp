@@ -22,7 +22,6 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     if (ctx_) {
       if (d_elig_) gpr_device_free(ctx_, d_elig_);
       if (d_created_) gpr_device_free(ctx_, d_created_);
-      if (h_text_) gpr_host_free(ctx_, h_text_);
       gpr_destroy(ctx_);
     }
   }
@@ -83,13 +82,14 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     Window w = ingest_matrix_device(*this, util, prof, power, opt, &rep);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (note) {
-      char buf[320];
+      char buf[480];
       if (rep.on_device)
         snprintf(buf, sizeof buf,
                  "Device ingest: %llu series lists parsed on the GPU into a %ux%ux%u window in %.1f ms "
-                 "(%llu re-parsed on the CPU, %llu rows patched)",
+                 "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, label maps %.1f, rows %.1f, "
+                 "parse %.1f ms)",
                  (unsigned long long)rep.spans, w.P, w.G, w.T, ms, (unsigned long long)rep.hard_spans,
-                 (unsigned long long)rep.rows_patched);
+                 (unsigned long long)rep.rows_patched, rep.scan_ms, rep.labels_ms, rep.assign_ms, rep.parse_ms);
       else
         snprintf(buf, sizeof buf, "Device ingest not used (%s): CPU text parser, %.1f ms", rep.reason.c_str(), ms);
       *note = buf;
@@ -103,18 +103,14 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     if (rc != GPR_OK) throw std::runtime_error(std::string(what) + " (" + std::to_string(rc) + "): " + gpr_last_error(ctx_));
   }
   void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens, std::vector<uint64_t>* closes) override {
-    // stage through pinned memory: a pageable source would move at a fraction of PCIe speed
-    if (n > h_text_cap_) {
-      if (h_text_) gpr_host_free(ctx_, h_text_), h_text_ = nullptr, h_text_cap_ = 0;
-      check(gpr_host_alloc(ctx_, n + n / 8 + 4096, &h_text_), "pinned text buffer");
-      h_text_cap_ = n + n / 8 + 4096;
-    }
-    if (n) memcpy(h_text_, text, n);
-    uint64_t cap = n / 256 + 4096, no = 0, nc = 0;
+    // The response sits in ordinary (pageable) memory: cudaMemcpy stages it through the driver's own
+    // pinned buffers.  Copying it into a pinned buffer of ours first costs a second pass over the text
+    // plus, the first time, the page-locking of that buffer — more than it saves for one use of the bytes.
+    // (A caller that receives the response straight into gpr_host_alloc memory gets full PCIe speed.)
+    uint64_t cap = n / 2048 + 4096, no = 0, nc = 0;  // a series is rarely shorter than 2 KB; retried if so
     while (true) {
       opens->resize(cap), closes->resize(cap);
-      const int rc = gpr_text_scan(ctx_, slot, static_cast<const char*>(h_text_), n, GPR_MEM_HOST, opens->data(),
-                                   closes->data(), cap, &no, &nc);
+      const int rc = gpr_text_scan(ctx_, slot, text, n, GPR_MEM_HOST, opens->data(), closes->data(), cap, &no, &nc);
       if (rc == GPR_E_CAPACITY) {
         cap = std::max(no, nc) + 16;
         continue;
@@ -188,8 +184,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     if (!ctx_) return;
     if (d_elig_) gpr_device_free(ctx_, d_elig_), d_elig_ = nullptr;
     if (d_created_) gpr_device_free(ctx_, d_created_), d_created_ = nullptr;
-    if (h_text_) gpr_host_free(ctx_, h_text_), h_text_ = nullptr;
-    gate_cap_ = 0, h_text_cap_ = 0;
+    gate_cap_ = 0;
     gpr_destroy(ctx_), ctx_ = nullptr;
   }
   bool create(uint32_t max_pods, uint32_t max_gpus, uint32_t max_samples, bool need_power, int device,
@@ -217,8 +212,6 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
   void* d_elig_ = nullptr;
   void* d_created_ = nullptr;
   size_t gate_cap_ = 0;
-  void* h_text_ = nullptr;
-  size_t h_text_cap_ = 0;
 };
 
 }  // namespace

@@ -1,7 +1,9 @@
 #include "ingest_device.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
+#include <thread>
 
 #include "ingest_internal.hpp"
 
@@ -39,13 +41,27 @@ size_t skip_trailing_ws(const std::string& s, size_t at) {
   return at;
 }
 
+double ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+struct SeriesLoc {
+  size_t mb, close_brace, vb, list_close;  // label map [mb, close_brace], list [vb, list_close]
+};
+
 // Walk the series of one response using the device's marker lists; labels -> rows through `asg`.
-void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool is_power, bool is_prof) {
+void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool is_power, bool is_prof,
+               DeviceIngestReport& rep) {
   const std::string& t = *plan.text;
   std::vector<uint64_t> opens, closes;
+  auto t0 = std::chrono::steady_clock::now();
   dev.scan(plan.slot, t.data(), t.size(), &opens, &closes);
+  rep.scan_ms += ms_since(t0);
+  t0 = std::chrono::steady_clock::now();
   std::sort(opens.begin(), opens.end());
   std::sort(closes.begin(), closes.end());
+  std::vector<SeriesLoc> locs;
+  locs.reserve(opens.size());
 
   size_t at;
   bool bare;
@@ -77,24 +93,8 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
       }
       if (list_close + 1 >= t.size() || t[list_close + 1] != '}')
         throw NotCompact{"series object has members after \"values\""};
-      // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON
-      // object ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and
-      // that no series without a "values" member was jumped over.  (A `},"values":[` inside a label
-      // value is impossible: a raw '"' ends a JSON string.)
-      Json metric;
-      try {
-        metric = Json::parse(t.substr(mb, close_brace + 1 - mb));
-      } catch (const std::exception& e) {
-        throw NotCompact{std::string("label map: ") + e.what()};
-      }
-      if (!metric.is_object()) throw NotCompact{"label map is not an object"};
+      locs.push_back(SeriesLoc{mb, close_brace, vb, list_close});
       ++walked;
-      ++w.stats.series_in;
-      if (list_close != vb) {  // an empty list is no element (as in the CPU paths)
-        uint32_t p, slot;
-        if (asg.assign(metric, is_power, is_prof, &p, &slot) == Assigner::Placed)
-          plan.series.push_back(DevSeries{p, slot, (uint64_t)vb, (uint64_t)list_close});
-      }
       at = list_close + 2;  // past '}'
       if (at < t.size() && t[at] == ',') {
         ++at;
@@ -113,6 +113,43 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
     at += 2;
   }
   if (skip_trailing_ws(t, at) != t.size()) throw NotCompact{"trailing bytes after the response"};
+
+  // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON
+  // object ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and that
+  // no series without a "values" member was jumped over.  (A `},"values":[` inside a label value is
+  // impossible: a raw '"' ends a JSON string.)  The maps are independent: parsed on all host cores.
+  std::vector<Json> metrics(locs.size());
+  {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_thr = std::min<size_t>(hw, std::max<size_t>(1, locs.size() / 256));
+    std::vector<std::string> errors(n_thr);
+    auto work = [&](size_t tid) {
+      try {
+        for (size_t i = tid; i < locs.size(); i += n_thr) {
+          metrics[i] = Json::parse(t.substr(locs[i].mb, locs[i].close_brace + 1 - locs[i].mb));
+          if (!metrics[i].is_object()) throw std::runtime_error("not an object");
+        }
+      } catch (const std::exception& e) {
+        errors[tid] = e.what();
+      }
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < n_thr; ++k) th.emplace_back(work, k);
+    work(0);
+    for (std::thread& x : th) x.join();
+    for (const std::string& e : errors)
+      if (!e.empty()) throw NotCompact{"label map: " + e};
+  }
+  rep.labels_ms += ms_since(t0);
+  t0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < locs.size(); ++i) {
+    ++w.stats.series_in;
+    if (locs[i].list_close == locs[i].vb) continue;  // an empty list is no element (as in the CPU paths)
+    uint32_t p, slot;
+    if (asg.assign(metrics[i], is_power, is_prof, &p, &slot) == Assigner::Placed)
+      plan.series.push_back(DevSeries{p, slot, (uint64_t)locs[i].vb, (uint64_t)locs[i].list_close});
+  }
+  rep.assign_ms += ms_since(t0);
 }
 
 }  // namespace
@@ -143,9 +180,9 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
   TextPlan* pl_util = add(&util, 1);
   TextPlan* pl_power = add(power, 2);
   try {
-    if (pl_prof) plan_text(dev, *pl_prof, asg, w, false, true);
-    plan_text(dev, *pl_util, asg, w, false, false);
-    if (pl_power) plan_text(dev, *pl_power, asg, w, true, false);
+    if (pl_prof) plan_text(dev, *pl_prof, asg, w, false, true, rep);
+    plan_text(dev, *pl_util, asg, w, false, false, rep);
+    if (pl_power) plan_text(dev, *pl_power, asg, w, true, false, rep);
   } catch (const NotCompact& e) {
     return cpu(e.why);
   }
@@ -171,7 +208,9 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
         sp.flags = writers[sp.row] > 1 ? GPR_SPAN_SHARED : 0u;
         spans[k].push_back(sp);
       }
+      const auto tp = std::chrono::steady_clock::now();
       dev.parse(texts[k]->slot, spans[k], w.t_end, w.step, w.T, n_rows, plane, fill);
+      rep.parse_ms += ms_since(tp);
       fill = false;
       rep.spans += spans[k].size();
     }
