@@ -9,6 +9,7 @@
 #include <cstring>
 #include <limits>
 #include <stdexcept>
+#include <unordered_map>
 
 #include "ingest.hpp"
 
@@ -59,7 +60,8 @@ class Assigner {
       ++w_.stats.series_skipped;
       return Skipped;
     }
-    auto key = std::make_pair(*pod, *ns);
+    key_.assign(std::to_string(pod->size())).append(1, ':').append(*pod).append(*ns);  // unambiguous (pod, ns)
+    const std::string& key = key_;
     auto it = pod_index_.find(key);
     uint32_t p;
     if (it == pod_index_.end()) {
@@ -100,19 +102,26 @@ class Assigner {
       // `A or B` (query.promql.j2:10-20) matches on the FULL label set: a UTIL element is dropped only
       // if a PROF element with identical labels exists; series that differ in any other label both
       // survive the `or` and are then folded together by `sum by`
-      std::vector<std::string> parts;
-      for (const Json::Member& kv : m.members())
-        if (kv.first != "__name__") parts.push_back(kv.first + "\x1f" + kv.second.as_string());
-      std::sort(parts.begin(), parts.end());
-      std::string sig;
-      for (const std::string& x : parts) sig += x + "\x1e";
-      std::vector<std::string>& ps = prof_sigs_[std::make_pair(p, slot)];
+      // (the signature is only built when a PROF series is involved: never for the usual UTIL-only tick)
+      auto signature = [&]() {
+        std::vector<std::string> parts;
+        for (const Json::Member& kv : m.members())
+          if (kv.first != "__name__") parts.push_back(kv.first + "\x1f" + kv.second.as_string());
+        std::sort(parts.begin(), parts.end());
+        std::string sig;
+        for (const std::string& x : parts) sig += x + "\x1e";
+        return sig;
+      };
       if (is_prof) {
-        ps.push_back(sig);
+        prof_sigs_[std::make_pair(p, slot)].push_back(signature());
         w_.pods[p].slots[slot].from_prof = true;
       } else {
-        for (const std::string& x : ps)
-          if (x == sig) return Shadowed;
+        auto ps = prof_sigs_.find(std::make_pair(p, slot));
+        if (ps != prof_sigs_.end()) {
+          const std::string sig = signature();
+          for (const std::string& x : ps->second)
+            if (x == sig) return Shadowed;
+        }
       }
       if (!fresh) ++w_.stats.duplicates_merged;
     }
@@ -122,7 +131,8 @@ class Assigner {
 
  private:
   Window& w_;
-  std::map<std::pair<std::string, std::string>, uint32_t> pod_index_;
+  std::unordered_map<std::string, uint32_t> pod_index_;
+  std::string key_;
   std::vector<std::map<std::string, uint32_t>> slot_index_;   // per pod: group key -> util slot
   std::vector<std::map<std::string, uint32_t>> pslot_index_;  // per pod: group key -> power slot
   std::map<std::pair<uint32_t, uint32_t>, std::vector<std::string>> prof_sigs_;

@@ -58,13 +58,13 @@ struct Parser {
     ++i;
     std::string out;
     while (true) {
+      // the run of plain characters up to the next quote or escape is appended in one piece
+      size_t j = i;
+      while (j < t.size() && t[j] != '"' && t[j] != '\\') ++j;
+      if (j > i) out.append(t, i, j - i), i = j;
       if (i >= t.size()) err("unterminated string");
       char c = t[i++];
       if (c == '"') break;
-      if (c != '\\') {
-        out += c;
-        continue;
-      }
       if (i >= t.size()) err("unterminated escape");
       char e = t[i++];
       switch (e) {
@@ -159,6 +159,7 @@ Json& Json::set(const std::string& key, Json v) {
       m.second = std::move(v);
       return m.second;
     }
+  if (o_.empty()) o_.reserve(16);  // label maps / small objects: no regrowth (a Member is ~200 bytes)
   o_.emplace_back(key, std::move(v));
   return o_.back().second;
 }
