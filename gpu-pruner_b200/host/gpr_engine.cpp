@@ -86,7 +86,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
       if (rep.on_device)
         snprintf(buf, sizeof buf,
                  "Device ingest: %llu series lists parsed on the GPU into a %ux%ux%u window in %.1f ms "
-                 "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, label maps %.1f, rows %.1f, "
+                 "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, series walk %.1f, labels->rows %.1f, "
                  "parse %.1f ms)",
                  (unsigned long long)rep.spans, w.P, w.G, w.T, ms, (unsigned long long)rep.hard_spans,
                  (unsigned long long)rep.rows_patched, rep.scan_ms, rep.labels_ms, rep.assign_ms, rep.parse_ms);

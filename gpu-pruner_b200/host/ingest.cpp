@@ -111,15 +111,20 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
   std::vector<TextSeries> useries, pseries;
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
 
+  FlatLabels flat;
   auto scan = [&](const std::string& text, bool is_power, bool is_prof) {
     for (const Span& s : series_spans(text)) {
       ++w.stats.series_in;
       if (!s.values_b || !s.metric_b) continue;
       const char* v = skip_ws(s.values_b + 1, s.values_e);
       if (v < s.values_e && *v == ']') continue;  // no sample in range: no element
-      const Json metric = Json::parse(std::string(s.metric_b, s.metric_e));
       uint32_t p, slot;
-      if (asg.assign(metric, is_power, is_prof, &p, &slot) != Assigner::Placed) continue;
+      if (flat.parse(s.metric_b, s.metric_e)) {  // Prometheus' own shape: read in place
+        if (asg.assign(flat, is_power, is_prof, &p, &slot) != Assigner::Placed) continue;
+      } else {
+        const Json metric = Json::parse(std::string(s.metric_b, s.metric_e));
+        if (asg.assign(metric, is_power, is_prof, &p, &slot) != Assigner::Placed) continue;
+      }
       (is_power ? pseries : useries).push_back(TextSeries{p, slot, s.values_b, s.values_e, true});
     }
   };

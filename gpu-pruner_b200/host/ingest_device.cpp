@@ -3,7 +3,6 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
-#include <thread>
 
 #include "ingest_internal.hpp"
 
@@ -113,41 +112,38 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
     at += 2;
   }
   if (skip_trailing_ws(t, at) != t.size()) throw NotCompact{"trailing bytes after the response"};
+  rep.labels_ms += ms_since(t0);
+  t0 = std::chrono::steady_clock::now();
 
   // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON
   // object ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and that
   // no series without a "values" member was jumped over.  (A `},"values":[` inside a label value is
-  // impossible: a raw '"' ends a JSON string.)  The maps are independent: parsed on all host cores.
-  std::vector<Json> metrics(locs.size());
-  {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t n_thr = std::min<size_t>(hw, std::max<size_t>(1, locs.size() / 256));
-    std::vector<std::string> errors(n_thr);
-    auto work = [&](size_t tid) {
+  // impossible: a raw '"' ends a JSON string.)  Prometheus' own shape — string values, no escapes —
+  // is read in place without allocating (FlatLabels); anything else goes through the DOM parser.
+  FlatLabels flat;
+  for (const SeriesLoc& loc : locs) {
+    const char* b = t.data() + loc.mb;
+    const char* e = t.data() + loc.close_brace + 1;
+    const bool element = loc.list_close != loc.vb;  // an empty list is no element (as in the CPU paths)
+    uint32_t p = 0, slot = 0;
+    Assigner::Result r = Assigner::Skipped;
+    if (flat.parse(b, e)) {
+      ++w.stats.series_in;
+      if (!element) continue;
+      r = asg.assign(flat, is_power, is_prof, &p, &slot);
+    } else {
+      Json metric;
       try {
-        for (size_t i = tid; i < locs.size(); i += n_thr) {
-          metrics[i] = Json::parse(t.substr(locs[i].mb, locs[i].close_brace + 1 - locs[i].mb));
-          if (!metrics[i].is_object()) throw std::runtime_error("not an object");
-        }
-      } catch (const std::exception& e) {
-        errors[tid] = e.what();
+        metric = Json::parse(std::string(b, e));
+      } catch (const std::exception& ex) {
+        throw NotCompact{std::string("label map: ") + ex.what()};
       }
-    };
-    std::vector<std::thread> th;
-    for (size_t k = 1; k < n_thr; ++k) th.emplace_back(work, k);
-    work(0);
-    for (std::thread& x : th) x.join();
-    for (const std::string& e : errors)
-      if (!e.empty()) throw NotCompact{"label map: " + e};
-  }
-  rep.labels_ms += ms_since(t0);
-  t0 = std::chrono::steady_clock::now();
-  for (size_t i = 0; i < locs.size(); ++i) {
-    ++w.stats.series_in;
-    if (locs[i].list_close == locs[i].vb) continue;  // an empty list is no element (as in the CPU paths)
-    uint32_t p, slot;
-    if (asg.assign(metrics[i], is_power, is_prof, &p, &slot) == Assigner::Placed)
-      plan.series.push_back(DevSeries{p, slot, (uint64_t)locs[i].vb, (uint64_t)locs[i].list_close});
+      if (!metric.is_object()) throw NotCompact{"label map is not an object"};
+      ++w.stats.series_in;
+      if (!element) continue;
+      r = asg.assign(metric, is_power, is_prof, &p, &slot);
+    }
+    if (r == Assigner::Placed) plan.series.push_back(DevSeries{p, slot, (uint64_t)loc.vb, (uint64_t)loc.list_close});
   }
   rep.assign_ms += ms_since(t0);
 }

@@ -33,8 +33,8 @@ struct DeviceIngestReport {
   bool on_device = false;        // false: the CPU text path produced the window (reason says why)
   std::string reason;
   uint64_t spans = 0, hard_spans = 0, rows_patched = 0;
-  // where the time went: device scan (text upload + marker scan), label maps (JSON, all host cores),
-  // row assignment (sequential), device parse (NaN fill + sample parse)
+  // where the time went: device scan (text upload + marker scan), series walk over the markers,
+  // label maps -> rows, device parse (NaN fill + sample parse)
   double scan_ms = 0, labels_ms = 0, assign_ms = 0, parse_ms = 0;
 };
 

@@ -9,7 +9,9 @@
 #include <cstring>
 #include <limits>
 #include <stdexcept>
+#include <string_view>
 #include <unordered_map>
+#include <vector>
 
 #include "ingest.hpp"
 
@@ -19,13 +21,82 @@ namespace detail {
 
 const int64_t kNoTs = std::numeric_limits<int64_t>::min();
 
+// ---- what the row assignment needs from a label map ------------------------------------------------------
+// Two interchangeable views: a parsed DOM object (any JSON), or FlatLabels — string_views straight into
+// the response text for the only shape Prometheus emits ({"k":"v",...}: string values, no escapes, no
+// whitespace, unique keys), built without a single allocation.  `str(key, &v)`: member present AND a
+// string; `each(f)`: f(key, value-or-"" ) over the members in text order.
+struct JsonMetric {
+  const Json& j;
+  bool str(std::string_view key, std::string_view* out) const {
+    const Json* m = j.find(std::string(key));
+    if (!m || !m->is_string()) return false;
+    *out = m->as_string();
+    return true;
+  }
+  template <typename F>
+  void each(F&& f) const {
+    for (const Json::Member& kv : j.members()) f(std::string_view(kv.first), std::string_view(kv.second.as_string()));
+  }
+};
+
+struct FlatLabels {
+  std::vector<std::pair<std::string_view, std::string_view>> kv;
+  bool str(std::string_view key, std::string_view* out) const {
+    for (const auto& m : kv)
+      if (m.first == key) {
+        *out = m.second;
+        return true;
+      }
+    return false;
+  }
+  template <typename F>
+  void each(F&& f) const {
+    for (const auto& m : kv) f(m.first, m.second);
+  }
+  // [b, e) must be exactly {"k":"v","k":"v",...}; false = use the DOM parser (escapes, non-string values,
+  // whitespace, control characters, duplicate keys, or not a label map at all)
+  bool parse(const char* b, const char* e) {
+    kv.clear();
+    const char* p = b;
+    if (p >= e || *p != '{') return false;
+    ++p;
+    if (p < e && *p == '}') return p + 1 == e;
+    while (true) {
+      std::string_view k, v;
+      if (!quoted(p, e, &k) || p >= e || *p != ':') return false;
+      ++p;
+      if (!quoted(p, e, &v)) return false;
+      for (const auto& m : kv)
+        if (m.first == k) return false;
+      kv.emplace_back(k, v);
+      if (p < e && *p == ',') {
+        ++p;
+        continue;
+      }
+      return p + 1 == e && *p == '}';
+    }
+  }
+
+ private:
+  static bool quoted(const char*& p, const char* e, std::string_view* out) {
+    if (p >= e || *p != '"') return false;
+    const char* s = ++p;
+    while (p < e && *p != '"') {
+      if (*p == '\\' || (unsigned char)*p < 0x20) return false;
+      ++p;
+    }
+    if (p >= e) return false;
+    *out = std::string_view(s, (size_t)(p - s));
+    ++p;
+    return true;
+  }
+};
+
 // exported_<x> first, then <x> (lib.rs:158-175)
-inline const std::string* label(const Json& metric, const char* exported, const char* bare) {
-  const Json* j = metric.find(exported);
-  if (j && j->is_string()) return &j->as_string();
-  j = metric.find(bare);
-  if (j && j->is_string()) return &j->as_string();
-  return nullptr;
+template <typename M>
+inline bool label(const M& metric, std::string_view exported, std::string_view bare, std::string_view* out) {
+  return metric.str(exported, out) || metric.str(bare, out);
 }
 
 inline float to_f32(double x, uint64_t* clamped) {
@@ -50,49 +121,54 @@ class Assigner {
   enum Result { Skipped, Shadowed, Placed };
 
   Result assign(const Json& m, bool is_power, bool is_prof, uint32_t* pod_out, uint32_t* slot_out) {
-    const std::string* pod = label(m, "exported_pod", "pod");
-    const std::string* ns = label(m, "exported_namespace", "namespace");
-    const std::string* ctr = label(m, "exported_container", "container");
-    const Json* model = m.find("modelName");
+    return assign(JsonMetric{m}, is_power, is_prof, pod_out, slot_out);
+  }
+
+  template <typename M>
+  Result assign(const M& m, bool is_power, bool is_prof, uint32_t* pod_out, uint32_t* slot_out) {
+    std::string_view pod, ns, ctr, model, host, gpu;
+    const bool has_pod = label(m, "exported_pod", "pod", &pod);
+    const bool has_ns = label(m, "exported_namespace", "namespace", &ns);
+    const bool has_ctr = label(m, "exported_container", "container", &ctr);
+    const bool has_model = m.str("modelName", &model);
     // the selector demands pod != "" (query.promql.j2:11,17,40); a series that cannot be turned into
     // PodMetricData is skipped with a log line (main.rs:423-428)
-    if (!pod || pod->empty() || !ns || (!is_power && (!ctr || !model || !model->is_string()))) {
+    if (!has_pod || pod.empty() || !has_ns || (!is_power && (!has_ctr || !has_model))) {
       ++w_.stats.series_skipped;
       return Skipped;
     }
-    key_.assign(std::to_string(pod->size())).append(1, ':').append(*pod).append(*ns);  // unambiguous (pod, ns)
-    const std::string& key = key_;
-    auto it = pod_index_.find(key);
+    key_.assign(std::to_string(pod.size())).append(1, ':').append(pod).append(ns);  // unambiguous (pod, ns)
+    auto it = pod_index_.find(key_);
     uint32_t p;
     if (it == pod_index_.end()) {
       p = (uint32_t)w_.pods.size();
-      pod_index_[key] = p;
-      w_.pods.push_back(PodEntry{*pod, *ns, {}, 0});
+      pod_index_[key_] = p;
+      w_.pods.push_back(PodEntry{std::string(pod), std::string(ns), {}, 0});
       slot_index_.emplace_back();
       pslot_index_.emplace_back();
     } else {
       p = it->second;
     }
-    const std::string host = m["Hostname"].as_string(), gpu = m["gpu"].as_string();
-    const std::string mdl = model && model->is_string() ? model->as_string() : std::string();
+    m.str("Hostname", &host), m.str("gpu", &gpu);   // absent / non-string: ""
     // `sum by (Hostname, container, pod, namespace, gpu, modelName)` groups (query.promql.j2:9)
-    const std::string gkey = host + "\x1f" + (ctr ? *ctr : std::string()) + "\x1f" + gpu + "\x1f" + mdl;
+    gkey_.assign(host).append(1, '\x1f').append(ctr).append(1, '\x1f').append(gpu).append(1, '\x1f').append(model);
     uint32_t slot;
     if (is_power) {
       auto& idx = pslot_index_[p];
-      auto f = idx.find(gkey);
-      if (f == idx.end()) slot = idx[gkey] = w_.pods[p].power_slots++;
+      auto f = idx.find(gkey_);
+      if (f == idx.end()) slot = idx[gkey_] = w_.pods[p].power_slots++;
       else slot = f->second, ++w_.stats.duplicates_merged;
     } else {
       auto& idx = slot_index_[p];
-      auto f = idx.find(gkey);
+      auto f = idx.find(gkey_);
       bool fresh = false;
       if (f == idx.end()) {
-        slot = idx[gkey] = (uint32_t)w_.pods[p].slots.size();
+        slot = idx[gkey_] = (uint32_t)w_.pods[p].slots.size();
         GpuSlot g;
-        g.hostname = host, g.container = *ctr, g.gpu = gpu, g.model = mdl;
-        const Json* nt = m.find("node_type");
-        g.node_type = nt && nt->is_string() ? nt->as_string() : "unknown";  // lib.rs:176-179
+        g.hostname = std::string(host), g.container = std::string(ctr), g.gpu = std::string(gpu);
+        g.model = std::string(model);
+        std::string_view nt;
+        g.node_type = m.str("node_type", &nt) ? std::string(nt) : "unknown";  // lib.rs:176-179
         g.from_prof = is_prof;
         w_.pods[p].slots.push_back(g);
         fresh = true;
@@ -105,8 +181,9 @@ class Assigner {
       // (the signature is only built when a PROF series is involved: never for the usual UTIL-only tick)
       auto signature = [&]() {
         std::vector<std::string> parts;
-        for (const Json::Member& kv : m.members())
-          if (kv.first != "__name__") parts.push_back(kv.first + "\x1f" + kv.second.as_string());
+        m.each([&](std::string_view k, std::string_view v) {
+          if (k != "__name__") parts.push_back(std::string(k) + "\x1f" + std::string(v));
+        });
         std::sort(parts.begin(), parts.end());
         std::string sig;
         for (const std::string& x : parts) sig += x + "\x1e";
@@ -132,7 +209,7 @@ class Assigner {
  private:
   Window& w_;
   std::unordered_map<std::string, uint32_t> pod_index_;
-  std::string key_;
+  std::string key_, gkey_;
   std::vector<std::map<std::string, uint32_t>> slot_index_;   // per pod: group key -> util slot
   std::vector<std::map<std::string, uint32_t>> pslot_index_;  // per pod: group key -> power slot
   std::map<std::pair<uint32_t, uint32_t>, std::vector<std::string>> prof_sigs_;
