@@ -20,6 +20,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "gpr_kernels.cuh"
@@ -163,6 +164,13 @@ struct gpr_ctx {
   size_t spans_cap = 0;
   float* d_tplane[2] = {nullptr, nullptr};
   size_t tplane_cap[2] = {0, 0};
+  // pageable text is staged through a small pinned ring by a few host threads (upload_pageable)
+  static constexpr int kUpThreads = 4, kUpSlots = 2;
+  static constexpr size_t kUpChunk = 4u << 20;
+  unsigned char* h_up_ring = nullptr;  // [kUpThreads][kUpSlots][kUpChunk], pinned
+  cudaStream_t up_stream[kUpThreads] = {};
+  cudaEvent_t up_event[kUpThreads][kUpSlots] = {};
+  int up_threads = kUpThreads;         // GPR_TEXT_UPLOAD_THREADS (0 = plain cudaMemcpy)
 
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -751,6 +759,12 @@ void gpr_destroy(gpr_ctx* ctx) {
   for (void* p : dev)
     if (p) cudaFree(p);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->h_up_ring) cudaFreeHost(ctx->h_up_ring);
+  for (int k = 0; k < gpr_ctx::kUpThreads; ++k) {
+    if (ctx->up_stream[k]) cudaStreamDestroy(ctx->up_stream[k]);
+    for (cudaEvent_t e : ctx->up_event[k])
+      if (e) cudaEventDestroy(e);
+  }
   cudaEvent_t evs[] = {ctx->ev_k0, ctx->ev_k1, ctx->ev_t0, ctx->ev_t1, ctx->ev_join};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
@@ -820,6 +834,7 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     CU(cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_done, 0, 2 * sizeof(unsigned long long)));
     c->pdl_enabled = env_int("GPR_PDL", 1) != 0;
+    c->up_threads = std::max(0, std::min((int)gpr_ctx::kUpThreads, env_int("GPR_TEXT_UPLOAD_THREADS", gpr_ctx::kUpThreads)));
     c->exchange_debug = env_int("GPR_DEBUG_EXCHANGE", 0);
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
                       (size_t)kSlots * 3 * sizeof(unsigned long long)));
@@ -1233,6 +1248,75 @@ static_assert(sizeof(gpr_text_span) == sizeof(gpr::text::Span) && offsetof(gpr_t
               "gpr_text_span mirrors gpr::text::Span");
 static_assert(GPR_SPAN_SHARED == gpr::text::kSpanShared && GPR_SPAN_HARD == gpr::text::kSpanHard, "span flags");
 
+// Host -> device copy of response text that sits in ordinary pageable memory.  A plain cudaMemcpy stages
+// it through the driver's single bounce buffer (measured 10.7 GB/s); here a few host threads copy
+// alternate 4 MB chunks into their own pinned double buffers and each enqueues its chunk on its own
+// stream, so the memcpy work is spread over cores and overlaps the DMA.  The context's stream then waits
+// for all of them.  Pinned / registered sources skip this and go down at PCIe speed.
+static int upload_text(gpr_ctx* ctx, uint8_t* dst, const char* src, uint64_t n, int32_t mem_kind) {
+  if (n == 0) return GPR_OK;
+  if (mem_kind == GPR_MEM_DEVICE) {
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return GPR_OK;
+  }
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  (void)cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind
+  constexpr int NT = gpr_ctx::kUpThreads, NS = gpr_ctx::kUpSlots;
+  constexpr size_t CH = gpr_ctx::kUpChunk;
+  const int nt = std::min<int>(ctx->up_threads, NT);
+  if (pinned || nt <= 0 || n < 4 * CH) {
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    return GPR_OK;
+  }
+  if (!ctx->h_up_ring) {
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_up_ring), (size_t)NT * NS * CH, cudaHostAllocDefault));
+    for (int k = 0; k < NT; ++k) {
+      CU(cudaStreamCreateWithFlags(&ctx->up_stream[k], cudaStreamNonBlocking));
+      for (int s = 0; s < NS; ++s) CU(cudaEventCreateWithFlags(&ctx->up_event[k][s], cudaEventDisableTiming));
+    }
+  }
+  // the destination may still be read by earlier work on the context's stream
+  CU(cudaEventRecord(ctx->ev_join, ctx->stream));
+  for (int k = 0; k < nt; ++k) CU(cudaStreamWaitEvent(ctx->up_stream[k], ctx->ev_join, 0));
+  const uint64_t n_chunks = (n + CH - 1) / CH;
+  cudaError_t errs[NT];
+  for (int k = 0; k < NT; ++k) errs[k] = cudaSuccess;
+  auto work = [&](int k) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    bool used[NS] = {};
+    int slot = 0;
+    for (uint64_t c = (uint64_t)k; c < n_chunks && e == cudaSuccess; c += (uint64_t)nt, slot = (slot + 1) % NS) {
+      unsigned char* buf = ctx->h_up_ring + ((size_t)k * NS + slot) * CH;
+      if (used[slot]) e = cudaEventSynchronize(ctx->up_event[k][slot]);  // its previous DMA has drained
+      if (e != cudaSuccess) break;
+      const uint64_t off = c * CH, len = std::min<uint64_t>(CH, n - off);
+      memcpy(buf, src + off, len);
+      e = cudaMemcpyAsync(dst + off, buf, len, cudaMemcpyHostToDevice, ctx->up_stream[k]);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->up_event[k][slot], ctx->up_stream[k]);
+      used[slot] = true;
+    }
+    errs[k] = e;
+  };
+  std::vector<std::thread> th;
+  int started = 1;  // share 0 runs on this thread
+  try {
+    th.reserve((size_t)nt);
+    for (int k = 1; k < nt; ++k) th.emplace_back(work, k), ++started;
+  } catch (...) {  // no thread to be had: nothing may cross the C ABI, the shares are done here instead
+  }
+  work(0);
+  for (std::thread& x : th) x.join();
+  for (int k = started; k < nt; ++k) work(k);
+  for (int k = 0; k < nt; ++k) CU(errs[k]);
+  // everything enqueued: the context's stream continues once every upload stream has drained
+  for (int k = 0; k < nt; ++k) {
+    CU(cudaEventRecord(ctx->up_event[k][0], ctx->up_stream[k]));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->up_event[k][0], 0));
+  }
+  return GPR_OK;
+}
+
 int gpr_text_scan(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes, int32_t mem_kind,
                   uint64_t* opens, uint64_t* closes, uint64_t cap, uint64_t* n_opens, uint64_t* n_closes) {
   if (!ctx) return GPR_E_INVALID;
@@ -1248,9 +1332,7 @@ int gpr_text_scan(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes
   if ((rc = grow(ctx, &ctx->d_marks, &ctx->marks_cap, (size_t)2 * cap + 2)) != GPR_OK) return rc;
   if (!ctx->d_mark_counts) CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_mark_counts), 2 * sizeof(unsigned long long)));
   uint8_t* d = ctx->d_text[slot];
-  if (n_bytes)
-    CU(cudaMemcpyAsync(d, text, n_bytes, mem_kind == GPR_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
-                       ctx->stream));
+  if ((rc = upload_text(ctx, d, text, n_bytes, mem_kind)) != GPR_OK) return rc;
   CU(cudaMemsetAsync(d + n_bytes, 0, gpr::text::kTextPad, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_mark_counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
   ctx->text_n[slot] = n_bytes;

@@ -221,6 +221,44 @@ def test_parsed_planes_feed_the_decision_kernels(eng, oracle_c):
     assert 0 < r.n_decisions < P
 
 
+def test_upload_paths_deliver_the_same_bytes(eng):
+    """pageable text goes up through a threaded pinned ring, pinned text and GPR_TEXT_UPLOAD_THREADS=0 through
+    plain copies: same markers, same tensor"""
+    import gpu_pruner_b200 as g
+    lib = H.lib()
+    lib.gph_synth_response.restype = C.c_longlong
+    P, G, n = 350, 4, 1800
+    need = -lib.gph_synth_response(P, G, n, C.c_longlong(T_END), C.c_ulonglong(3), None, C.c_longlong(0))
+    pinned = eng.host_array((need,), np.uint8)
+    k = lib.gph_synth_response(P, G, n, C.c_longlong(T_END), C.c_ulonglong(3), pinned.ctypes.data_as(C.c_char_p),
+                               C.c_longlong(need))
+    assert k > 40_000_000                      # well above the ring threshold, not a multiple of the chunk size
+    pageable = pinned[:k].tobytes()
+
+    def run(e, text, nbytes=None):
+        opens, closes = e.text_scan(text, n_bytes=nbytes)
+        spans = np.zeros(len(opens), e.SPAN_DTYPE)
+        spans["begin"] = opens + 12
+        spans["end"] = closes[np.searchsorted(closes, opens + 12)] + 2
+        spans["row"] = np.arange(len(opens))
+        out = e.text_parse(spans, T_END, 1, n, len(opens))
+        return opens, closes, out, _plane(e, len(opens), n)
+
+    o1, c1, s1, p1 = run(eng, pageable)
+    o2, c2, s2, p2 = run(eng, pinned, k)
+    os.environ["GPR_TEXT_UPLOAD_THREADS"] = "0"
+    try:
+        with g.IdleEngine(device=0) as plain:
+            o3, c3, s3, p3 = run(plain, pageable)
+    finally:
+        del os.environ["GPR_TEXT_UPLOAD_THREADS"]
+    assert len(o1) == P * G and np.array_equal(o1, o2) and np.array_equal(o1, o3)
+    assert np.array_equal(c1, c2) and np.array_equal(c1, c3)
+    assert int(s1["n_in"].sum()) == P * G * n and not np.any(s1["flags"] & 2)
+    assert np.array_equal(s1, s2) and np.array_equal(s1, s3)
+    assert np.array_equal(p1, p2) and np.array_equal(p1, p3) and not np.isnan(p1).any()
+
+
 def test_error_paths(eng):
     import gpu_pruner_b200 as g
     text = _response(2, 1, 5, np.random.default_rng(0), ["0"])
