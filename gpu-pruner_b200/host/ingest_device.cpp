@@ -1,3 +1,10 @@
+// ingest_device.cpp — host half of the device-side ingest (see ingest_device.hpp and
+// gpu-pruner_b200/csrc/gpr_text.cuh).  The wire shape is the matrix result that
+// /root/reference/gpu-pruner/src/bin/querytest.rs:41-53 walks; label precedence and defaults follow
+// PodMetricData::try_from (gpu-pruner/src/lib.rs:153-187) through the Assigner shared with ingest.cpp.
+// The device reports where sample lists open and close; this file walks the series with those offsets,
+// turns every label map into a tensor row, lets the device parse the samples, and re-parses on the CPU
+// the few rows the strict device parser declined.
 #include "ingest_device.hpp"
 
 #include <algorithm>
