@@ -32,13 +32,13 @@ int main(int argc, char** argv) {
   std::unique_ptr<gph::FixtureKubeApi> kube;
   if (cli.kube_fixture) kube = std::make_unique<gph::FixtureKubeApi>(*cli.kube_fixture);
   std::unique_ptr<gph::VerdictEngine> engine = gph::make_gpr_engine();   // libgpr.so; no CPU fallback
-  // GPR_INGEST=gpu: parse the response text on the GPU straight into HBM (ingest_device.hpp);
-  // default: the threaded CPU text parser, window uploaded by gpr_decide
+  // The response text is parsed on the GPU straight into HBM (ingest_device.hpp); responses that are not
+  // in Prometheus' compact encoding fall back to the CPU text parser by themselves.  GPR_INGEST=cpu forces
+  // the threaded CPU text parser (window uploaded by gpr_decide) for comparison.
   const char* ing = getenv("GPR_INGEST");
   std::unique_ptr<gph::TextIngestor> cpu_ingestor;
-  gph::TextIngestor* ingestor = nullptr;
-  if (ing && std::string(ing) == "gpu") ingestor = engine->text_ingestor();
-  else if (ing && std::string(ing) == "cpu") cpu_ingestor = gph::make_cpu_text_ingestor(), ingestor = cpu_ingestor.get();
+  gph::TextIngestor* ingestor = engine->text_ingestor();
+  if (ing && std::string(ing) == "cpu") cpu_ingestor = gph::make_cpu_text_ingestor(), ingestor = cpu_ingestor.get();
   std::unique_ptr<gph::WindowSource> src = gph::make_window_source(cli.prometheus_url, ingestor, &log);
   gph::Controller ctl(cli, kube.get(), engine.get(), log, gph::system_clock());
   return ctl.run(*src);

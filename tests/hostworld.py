@@ -44,7 +44,8 @@ def _series(pod, gpu, vals, t_end):
     return {"metric": lab, "values": [[t_end - (len(vals) - 1 - i), str(v)] for i, v in enumerate(vals)]}
 
 
-def build_world(tmp_path):
+def build_world(tmp_path, compact=True):
+    """compact=True: Prometheus' own encoding (no whitespace), which the device ingest parses on the GPU"""
     prom, kube = tmp_path / "prom", tmp_path / "kube"
     prom.mkdir()
     T = 120                                     # -t 2 minutes @ 1 s
@@ -72,8 +73,11 @@ def build_world(tmp_path):
         _write(kube, "pods", NS, _pod(name, owners, labels,
                                       age_s=60 if name == "young-0" else 7200,
                                       phase="Pending" if name == "pending-0" else "Running"))
-    (prom / "util.json").write_text(json.dumps({"status": "success", "data": {"resultType": "matrix", "result": util}}))
-    (prom / "power.json").write_text(json.dumps({"status": "success", "data": {"resultType": "matrix", "result": power}}))
+    sep = (",", ":") if compact else (", ", ": ")
+    (prom / "util.json").write_text(json.dumps({"status": "success", "data": {"resultType": "matrix", "result": util}},
+                                               separators=sep))
+    (prom / "power.json").write_text(json.dumps({"status": "success", "data": {"resultType": "matrix", "result": power}},
+                                                separators=sep))
     (prom / "query.json").write_text(json.dumps({"end": NOW, "step": 1}))
     _write(kube, "deployments", NS, _obj("web", "dep-web"))
     _write(kube, "deployments", NS, _obj("api", "dep-api"))

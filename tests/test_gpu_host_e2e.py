@@ -49,6 +49,7 @@ def test_dry_run_reports_the_same_roots_and_sends_nothing(world):
         "Dry-run: Would have sent [InferenceService] team-a:llm for scaledown"])
     # 11 idle series (hot-0 is idle too: no power clause without --power-threshold) across 10 unique pods
     assert "Query returned 11 series across 10 unique pods" in msgs
+    assert any(m.startswith("Device ingest: ") and "parsed on the GPU" in m for m in msgs)   # the default ingest
     assert any("Skipping team-a:young-0, created after the lookback window" in m for m in msgs)
     assert any("Skipping team-a:pending-0, it's still pending" in m for m in msgs)
     assert any("Skipping team-a:gone-0, pod no longer exists" in m for m in msgs)

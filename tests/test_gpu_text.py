@@ -312,9 +312,6 @@ def _strip(reqs):
 def test_binary_with_device_ingest_behaves_like_the_cpu_ingest(extra, tmp_path):
     world = build_world(tmp_path)
     tmp, prom, kube = world
-    for name in ("util.json", "power.json"):      # Prometheus' compact encoding (the fixtures are pretty)
-        f = prom / name
-        f.write_text(json.dumps(json.loads(f.read_text()), separators=(",", ":")))
     pc, logs_c, reqs_c = _run_bin(world, "cpu", *extra)
     pg, logs_g, reqs_g = _run_bin(world, "gpu", *extra)
     assert pc.returncode == 0 and pg.returncode == 0, pg.stderr
@@ -328,7 +325,7 @@ def test_binary_with_device_ingest_behaves_like_the_cpu_ingest(extra, tmp_path):
 
 
 def test_binary_falls_back_to_the_cpu_parser_for_other_encodings(tmp_path):
-    world = build_world(tmp_path)        # json.dumps default separators: not the compact encoding
+    world = build_world(tmp_path, compact=False)     # ", " / ": " separators: not the compact encoding
     pg, logs_g, _ = _run_bin(world, "gpu")
     assert pg.returncode == 0
     msgs = [l["fields"]["message"] for l in logs_g]
