@@ -358,6 +358,11 @@ inline const char* result_spans(const char* arr, const char* e, std::vector<Span
         const char* end;
         if (in < e && *in == ']') {
           end = in + 1;
+        } else if (in != v + 1) {
+          // whitespace right after the '[': an indented (pretty-printed) response, whose list does not
+          // end in a literal "]]" — walk it bracket by bracket instead (no server emits this; a proxy or a
+          // hand-made fixture may)
+          end = skip_value(v, e);
         } else {
           const char* hit = find_close2(v, e);
           if (!hit) bad("unterminated values array");

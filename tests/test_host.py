@@ -552,3 +552,43 @@ def test_text_ingest_throughput_smoke():
         assert u.shape == (300, 2, 600)
     H.ingest_mode(-1)
     assert times[0] < times[-1]
+
+
+def test_text_ingest_accepts_every_json_layout():
+    """compact (what Prometheus emits), spaced, and indented responses give the same tensor through the
+    text path as through the DOM parser — the byte-level shortcuts (SWAR search for the list end, in-place
+    label maps) must not make the parser pickier than JSON"""
+    import ctypes as C
+    import random
+    rng = random.Random(5)
+    t_end = 1_700_000_000
+    sers = []
+    for p in range(6):
+        for g in range(rng.randrange(1, 3)):
+            n = rng.choice([0, 1, 7, 60])
+            sers.append({"metric": lab_(rng, p, g),
+                         "values": [[t_end - n + 1 + i, rng.choice(["0", "5", "NaN", "0.5"])] for i in range(n)]})
+    resp = {"status": "success", "data": {"resultType": "matrix", "result": sers}}
+    layouts = {"compact": json.dumps(resp, separators=(",", ":")), "spaced": json.dumps(resp),
+               "indent1": json.dumps(resp, indent=1), "indent4": json.dumps(resp, indent=4),
+               "tabs": json.dumps(resp, indent="\t"), "crlf": json.dumps(resp, indent=2).replace("\n", "\r\n")}
+
+    def run(text, mode):
+        H.ingest_mode(mode)
+        dims = (C.c_uint * 3)()
+        meta = C.create_string_buffer(1 << 20)
+        u = np.zeros((6, 2, 60), np.float32)
+        rc = H.lib().gph_ingest(text.encode(), None, None, C.c_longlong(1), C.c_longlong(1), C.c_longlong(t_end), dims,
+                                u.ctypes.data_as(C.c_void_p), None, meta, 1 << 20)
+        assert rc == 0, (mode, meta.value[:200])
+        m = json.loads(meta.value.decode())
+        m.pop("ingest_ms", None)
+        return list(dims), u, m
+
+    ref = run(layouts["compact"], -1)
+    for name, text in layouts.items():
+        for mode in (-1, 1, 2):
+            dims, u, m = run(text, mode)
+            assert dims == ref[0] and np.array_equal(u.view(np.uint32), ref[1].view(np.uint32)), (name, mode)
+            assert m == ref[2], (name, mode)
+    H.ingest_mode(-1)

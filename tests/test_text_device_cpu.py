@@ -177,8 +177,13 @@ def test_anything_but_the_compact_encoding_falls_back_to_the_cpu_parser(driver, 
     empty = tmp_path / "empty"
     empty.mkdir()
     (empty / "util.json").write_text(_resp([]))
-    rc, lines = _run(driver, [pretty, bare, extra, swapped, hist, empty])
+    indented = tmp_path / "indented"
+    indented.mkdir()
+    (indented / "util.json").write_text(json.dumps({"status": "success", "data": {"resultType": "matrix", "result": [
+        {"metric": _labels(0, 0), "values": [[T_END - 1, "0"], [T_END, "4"]]}]}}, indent=2))
+    rc, lines = _run(driver, [pretty, bare, extra, swapped, hist, empty, indented])
     assert rc == 0, lines
+    assert lines[6].startswith("OK") and " device=0 " in lines[6]
     assert " device=0 " in lines[0] and " device=1 " in lines[1] and " device=0 " in lines[2]
     assert " device=0 " in lines[3] and " device=0 " in lines[4] and " device=1 " in lines[5]
     # and without end / step the device path is not attempted at all
