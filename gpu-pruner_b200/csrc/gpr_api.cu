@@ -134,8 +134,13 @@ struct gpr_ctx {
   size_t gather_cap = 0;
   float* d_smax = nullptr;
   size_t smax_cap = 0;
-  unsigned long long* h_counts = nullptr;  // pinned [kSlots][3]
+  unsigned long long* h_counts = nullptr;  // pinned [kSlots][4]: n_series, n_candidates, n_decisions,
+                                           // %globaltimer at completion; then [mark, error word]
+  unsigned long long* h_mark = nullptr;    // %globaltimer written by the last gpr_timer_begin
+  unsigned int* h_err = nullptr;           // raised by a kernel whose peer wait timed out
   std::vector<Pending> pending;
+  std::vector<uint64_t> stamps;            // completion stamps of the decisions retired by the last gpr_sync
+  unsigned long long rdv_seq = 0;          // rendezvous sequence number (same on all ranks)
 
   void* d_flush = nullptr;
   size_t flush_bytes = 0;
@@ -491,8 +496,10 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   // single-launch path: the last CTA stores the three counters straight into this call's
   // pinned (device-mapped, UVA) host slot, so no copy operation separates back-to-back steps
   const int slot = (int)ctx->pending.size();
-  unsigned long long* h_slot = ctx->h_counts + (size_t)slot * 3;
+  unsigned long long* h_slot = ctx->h_counts + (size_t)slot * 4;
   fp.counts = h_slot;
+  fp.stamp = h_slot + 3;
+  fp.err = ctx->h_err;
   fp.acc = ctx->d_acc + 3 * sset;
   fp.ticket = ctx->d_tickets + sset;
   fp.done = ctx->d_done + sset;
@@ -598,7 +605,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       ctx->uses[sset]++;
     }
   }
-  if (P == 0) h_slot[0] = h_slot[1] = h_slot[2] = 0;  // slot is not in flight
+  if (P == 0) h_slot[0] = h_slot[1] = h_slot[2] = h_slot[3] = 0;  // slot is not in flight
 
   // ---- the one collective: allgather of the packed bitmap over NVLink ----------------------
   if ((comm && !fused) || host_out || !async) ctx->last_was_reduce = false;  // something follows
@@ -649,13 +656,21 @@ int sync_impl(gpr_ctx* ctx) {
     ctx->masks_dirty = true;
     return fail(ctx, GPR_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
   }
+  ctx->stamps.clear();
   for (const Pending& p : ctx->pending) {
-    const unsigned long long* c = ctx->h_counts + (size_t)p.slot * 3;
+    const unsigned long long* c = ctx->h_counts + (size_t)p.slot * 4;
     p.res->n_series = c[0];
     p.res->n_candidates = c[1];
     p.res->n_decisions = c[2];
+    ctx->stamps.push_back(c[3]);
   }
   ctx->pending.clear();
+  if (*ctx->h_err) {
+    *ctx->h_err = 0;
+    ctx->masks_dirty = true;
+    return fail(ctx, GPR_E_STATE, "a peer rank never arrived at the bitmap exchange / rendezvous (waited %llu s); "
+                "the results of this batch are not global", gpr::kPeerTimeoutNs / 1000000000ull);
+  }
   return GPR_OK;
 }
 
@@ -837,8 +852,12 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     c->up_threads = std::max(0, std::min((int)gpr_ctx::kUpThreads, env_int("GPR_TEXT_UPLOAD_THREADS", gpr_ctx::kUpThreads)));
     c->exchange_debug = env_int("GPR_DEBUG_EXCHANGE", 0);
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
-                      (size_t)kSlots * 3 * sizeof(unsigned long long)));
+                      ((size_t)kSlots * 4 + 2) * sizeof(unsigned long long)));
+    memset(c->h_counts, 0, ((size_t)kSlots * 4 + 2) * sizeof(unsigned long long));
+    c->h_mark = c->h_counts + (size_t)kSlots * 4;
+    c->h_err = reinterpret_cast<unsigned int*>(c->h_mark + 1);
     c->pending.reserve(kSlots);
+    c->stamps.reserve(kSlots);
 
     c->variant = cfg->kernel_variant;
     if (const char* k = getenv("GPR_KERNEL")) {
@@ -1200,7 +1219,45 @@ int gpr_timer_begin(gpr_ctx* ctx) {
   if (!ctx) return GPR_E_INVALID;
   ctx->last_was_reduce = false;
   CU(cudaSetDevice(ctx->device));
+  // rendezvous first, then the start event: with an exchange attached the timed regions of all ranks
+  // begin within an NVLink round trip of each other, whatever the skew between their host threads
+  gpr::RendezvousParams q;
+  memset(&q, 0, sizeof q);
+  q.world = 1, q.rank = 0;
+  q.stamp = ctx->h_mark;
+  q.err = ctx->h_err;
+  if (ctx->p2p_ready && ctx->world > 1) {
+    q.world = ctx->world, q.rank = ctx->rank;
+    q.seq = ++ctx->rdv_seq;
+    for (int r = 0; r < ctx->world; ++r)
+      q.peer_flag[r] = reinterpret_cast<unsigned long long*>(ctx->p2p_peer[r]) + gpr::kMaxPeers + ctx->rank;
+    q.my_flags = reinterpret_cast<const unsigned long long*>(ctx->p2p_block) + gpr::kMaxPeers;
+  } else if (ctx->comm && ctx->world > 1) {
+    // NCCL only: a one-word allgather is the rendezvous
+    int rc = grow(ctx, &ctx->d_gather, &ctx->gather_cap, (size_t)ctx->world + 2);
+    if (rc != GPR_OK) return rc;
+    rc = grow(ctx, &ctx->d_bits, &ctx->bits_cap, 4);
+    if (rc != GPR_OK) return rc;
+    NC(g_nccl.AllGather(ctx->d_bits, ctx->d_gather, 1, ncclUint32, ctx->comm, ctx->stream));
+  }
+  gpr::k_rendezvous<<<1, 32, 0, ctx->stream>>>(q);
+  ctx->launches++;
+  CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_t0, ctx->stream));
+  return GPR_OK;
+}
+int gpr_step_stamps(gpr_ctx* ctx, uint64_t* ns, uint32_t cap, uint32_t* n, uint64_t* begin_ns) {
+  if (!ctx || !n) return GPR_E_INVALID;
+  *n = (uint32_t)ctx->stamps.size();
+  if (begin_ns) *begin_ns = *ctx->h_mark;
+  if (ns)
+    for (uint32_t i = 0; i < cap && i < *n; ++i) ns[i] = ctx->stamps[i];
+  return GPR_OK;
+}
+int gpr_p2p_debug(gpr_ctx* ctx, int32_t mode) {
+  if (!ctx) return GPR_E_INVALID;
+  if (mode < 0 || mode > 2) return fail(ctx, GPR_E_INVALID, "exchange debug mode %d (0..2)", mode);
+  ctx->exchange_debug = mode;
   return GPR_OK;
 }
 int gpr_timer_end(gpr_ctx* ctx, double* ms) {

@@ -78,8 +78,20 @@ struct FoldParams {
   unsigned long long step;               // exchange sequence number of this call (same on all ranks)
   uint32_t* out_dbits;                   // caller's global bitmaps on this device (may be null)
   uint32_t* out_cbits;
-  int exchange_debug;                    // 0 normal; developer timing switches: 1 = do not wait for the
+  int exchange_debug;                    // 0 normal; timing switches (gpr_p2p_debug): 1 = do not wait for the
                                          // peers, 2 = no push at all (results are then NOT global)
+  unsigned long long* stamp;             // host-mapped: %globaltimer (ns) when this decision completed
+  unsigned int* err;                     // host-mapped: set to 1 when a peer never showed up (see spin_until)
+};
+
+// One rank's view of the exchange block header, for the stand-alone rendezvous (gpr_timer_begin)
+struct RendezvousParams {
+  int world, rank;
+  unsigned long long* peer_flag[kMaxPeers];  // &rdv_flags[my_rank] on rank r
+  const unsigned long long* my_flags;        // local rdv_flags[world]
+  unsigned long long seq;
+  unsigned long long* stamp;                 // host-mapped, %globaltimer at release
+  unsigned int* err;
 };
 
 struct ReduceParams {
@@ -94,14 +106,14 @@ struct ReduceParams {
   uint32_t util_u8;   // seg[0] rows are biased bytes (GPR_FMT_U8B), k_reduce_u8 only
 };
 
-#ifdef GPR_TIMELINE
-// developer-only: per-CTA (smid, t_start, t_stream_end, t_exit) in ns, see tools/timeline.py
-__device__ unsigned long long g_timeline[4 * 4096];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef GPR_TIMELINE
+// developer-only: per-CTA (smid, t_start, t_stream_end, t_exit) in ns, see tools/timeline.py
+__device__ unsigned long long g_timeline[4 * 4096];
 __device__ __forceinline__ void tl_mark(int slot) {
   if (threadIdx.x == 0 && blockIdx.x < 4096) {
     if (slot == 0) {
@@ -147,6 +159,24 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Wait for a peer-written sequence number.  A peer that never arrives (crashed rank, a rank that
+// skipped a collective call) must not hang this GPU: after kPeerTimeoutNs the wait gives up, raises
+// the host-visible error word (gpr_sync then fails with GPR_E_STATE) and the kernel runs to completion.
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ void spin_until_sys(const unsigned long long* p, unsigned long long want,
+                                               unsigned int* err) {
+  if (ld_acquire_sys_u64(p) >= want) return;
+  const unsigned long long t0 = gtime();
+  unsigned int polls = 0;
+  while (ld_acquire_sys_u64(p) < want) {
+    __nanosleep(64);
+    if ((++polls & 1023u) == 0 && gtime() - t0 > kPeerTimeoutNs) {
+      if (err) *err = 1u;
+      return;
+    }
+  }
 }
 
 __device__ __forceinline__ float nan_f() { return __int_as_float(0x7fffffff); }
@@ -259,11 +289,12 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
       }
     }
   }
-  __threadfence_system();
+  // bar.sync orders every thread's peer stores before the flag threads' release (the release is
+  // cumulative at system scope), so one fence per peer instead of one per thread
   __syncthreads();
   if ((int)threadIdx.x < f.world && (int)threadIdx.x != f.rank && f.exchange_debug != 2) {
     st_release_sys_u64(f.peer_flag[threadIdx.x], f.step);             // "rank's words of step k are there"
-    while (f.exchange_debug == 0 && ld_acquire_sys_u64(f.my_flags + threadIdx.x) < f.step) __nanosleep(128);
+    if (f.exchange_debug == 0) spin_until_sys(f.my_flags + threadIdx.x, f.step, f.err);
   }
   __syncthreads();
   // assemble the caller's rank-major global bitmaps from the local gather buffer
@@ -321,9 +352,23 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
     f.counts[2] = __ldcg(&f.acc[2]);
     f.acc[0] = f.acc[1] = f.acc[2] = 0ull;
     *f.ticket = 0u;
+    if (f.stamp) *f.stamp = gtime();
     __threadfence();
     st_release_u64(f.done, f.need + 1ull);
   }
+}
+
+// Device-side rendezvous + time mark (gpr_timer_begin).  With an exchange attached every rank raises
+// its sequence number on every peer and waits for theirs, so the kernels that follow on each rank's
+// stream start within an NVLink round trip of each other instead of a host-launch skew apart.
+__global__ void __launch_bounds__(32) k_rendezvous(RendezvousParams q) {
+  const int t = threadIdx.x;
+  if (t < q.world && t != q.rank) {
+    st_release_sys_u64(q.peer_flag[t], q.seq);
+    spin_until_sys(q.my_flags + t, q.seq, q.err);
+  }
+  __syncwarp();
+  if (t == 0 && q.stamp) *q.stamp = gtime();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -319,6 +319,18 @@ class IdleEngine:
         self._check(self._lib.gpr_timer_end(self._h, C.byref(ms)))
         return ms.value
 
+    def step_stamps(self):
+        """(begin_ns, ns[]) — device %globaltimer at the last timer_begin and at the completion of every
+        decision retired by the last sync / blocking call"""
+        n, t0 = C.c_uint32(), C.c_uint64()
+        self._check(self._lib.gpr_step_stamps(self._h, None, 0, C.byref(n), C.byref(t0)))
+        out = np.zeros(max(n.value, 1), np.uint64)
+        self._check(self._lib.gpr_step_stamps(self._h, _ptr(out), n.value, C.byref(n), C.byref(t0)))
+        return int(t0.value), out[:n.value]
+
+    def p2p_debug(self, mode: int):
+        self._check(self._lib.gpr_p2p_debug(self._h, mode))
+
     def flush_l2(self):
         self._check(self._lib.gpr_flush_l2(self._h))
 

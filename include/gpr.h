@@ -227,6 +227,10 @@ GPR_API int gpr_comm_destroy(gpr_ctx *ctx);
 GPR_API int gpr_p2p_init(gpr_ctx *ctx, int rank, int world, uint32_t max_pods_per_rank,
                          void *handle64);
 GPR_API int gpr_p2p_attach(gpr_ctx *ctx, const void *handles /* world * 64 bytes */);
+/* Timing switch for attributing the cost of the fused exchange (bench.py's breakdown); all ranks must
+ * switch together.  0 = normal; 1 = push the words and flags but do not wait for the peers; 2 = no push
+ * at all.  In modes 1 and 2 the returned bitmaps are NOT global.                                    */
+GPR_API int gpr_p2p_debug(gpr_ctx *ctx, int32_t mode);
 
 /* ---- memory helpers ------------------------------------------------------------------ */
 GPR_API int gpr_host_alloc(gpr_ctx *ctx, size_t bytes, void **out); /* pinned host memory         */
@@ -237,9 +241,20 @@ GPR_API int gpr_memcpy(gpr_ctx *ctx, void *dst, const void *src, size_t bytes,
                int32_t dst_kind, int32_t src_kind);          /* blocking                   */
 
 /* ---- measurement support ------------------------------------------------------------- */
-/* CUDA events on the context's stream: begin; ...enqueue...; end -> elapsed ms.           */
+/* CUDA events on the context's stream: begin; ...enqueue...; end -> elapsed ms.
+ * gpr_timer_begin first enqueues a device-side rendezvous: with a fused exchange attached
+ * (gpr_p2p_attach) every rank's stream waits, on the GPU, until all ranks have reached their
+ * gpr_timer_begin, so the timed regions of all ranks start within an NVLink round trip of each other
+ * whatever the skew between the host threads (with gpr_comm_init only, a one-word ncclAllGather plays
+ * that role).  It is therefore COLLECTIVE when world > 1: all ranks must call it in lock-step.     */
 GPR_API int gpr_timer_begin(gpr_ctx *ctx);
 GPR_API int gpr_timer_end(gpr_ctx *ctx, double *ms);
+/* Per-decision completion times: ns[i] = the device's %globaltimer (nanoseconds) at which the i-th of
+ * the decisions retired by the most recent gpr_sync / blocking call finished (bitmap complete, exchange
+ * included); *begin_ns = the same clock at the release of the last gpr_timer_begin.  *n = number of
+ * decisions retired (may exceed cap).  Differences of consecutive stamps are the per-step device times
+ * SURVEY.md §8(d) asks the median of.                                                              */
+GPR_API int gpr_step_stamps(gpr_ctx *ctx, uint64_t *ns, uint32_t cap, uint32_t *n, uint64_t *begin_ns);
 /* writes > L2-size bytes so the next launch starts with a cold L2                          */
 GPR_API int gpr_flush_l2(gpr_ctx *ctx);
 /* number of kernels this context has launched since creation                               */

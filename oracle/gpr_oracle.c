@@ -19,10 +19,14 @@
  * per element.  Plain scalar C, no intrinsics: this is also "the reference CPU loop" timed
  * as the baseline.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE /* sched_getaffinity / pthread_setaffinity_np for the timed baseline's pool */
+#endif
 #include "gpr_oracle.h"
 
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -125,6 +129,7 @@ typedef struct {
   /* synthetic streaming mode */
   int synth, use_power, use_elig;
   uint64_t seed, pod_offset;
+  void *aux; /* other job kinds run through the same pool (gpo_synth_fill) */
 } job_t;
 
 static void *decide_job(void *arg) {
@@ -158,13 +163,39 @@ static struct {
 } g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
             NULL, NULL, 0, 0, 0, 0, NULL, NULL};
 
+/* Optional pinning for the timed baseline (gpo_pool_pin): worker i stays on the i-th CPU this
+ * process may run on, so the pages a worker first touches in gpo_synth_fill are the ones the same
+ * worker streams in gpo_decide_mt (same pod split), whatever the box's NUMA layout. */
+static volatile int g_pin = 0;
+
+static void pin_self(int id) {
+  cpu_set_t allowed, one;
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+  const int n = CPU_COUNT(&allowed);
+  if (n <= 0) return;
+  int want = id % n, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c) {
+    if (!CPU_ISSET(c, &allowed)) continue;
+    if (seen++ == want) {
+      CPU_ZERO(&one);
+      CPU_SET(c, &one);
+      pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+      return;
+    }
+  }
+}
+
+void gpo_pool_pin(int on) { g_pin = on ? 1 : 0; }
+
 static void *pool_worker(void *arg) {
   const int id = *(int *)arg; /* 1-based */
   unsigned long seen = 0;
+  int pinned = 0;
   pthread_mutex_lock(&g_pool.mu);
   for (;;) {
     while (g_pool.gen == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
     seen = g_pool.gen;
+    if (g_pin && !pinned) pin_self(id), pinned = 1;
     if (id < g_pool.n_jobs) {
       job_t *job = &g_pool.jobs[id];
       void *(*fn)(void *) = g_pool.fn;
@@ -324,7 +355,7 @@ typedef struct {
 } fill_job_t;
 
 static void *fill_job(void *arg) {
-  fill_job_t *j = (fill_job_t *)arg;
+  fill_job_t *j = (fill_job_t *)((job_t *)arg)->aux;
   for (uint32_t p = j->p0; p < j->p1; ++p)
     for (uint32_t g = 0; g < j->G; ++g) {
       const uint64_t local = (uint64_t)p * j->G + g;
@@ -338,24 +369,25 @@ int gpo_synth_fill(int n_threads, uint64_t seed, int plane, float *dst, uint64_t
                    uint32_t P, uint32_t G, uint32_t T, uint64_t ld) {
   if (n_threads < 1) n_threads = 1;
   if (ld == 0) ld = T;
-  fill_job_t *jobs = (fill_job_t *)calloc((size_t)n_threads, sizeof(fill_job_t));
-  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
-  if (!jobs || !th) {
-    free(jobs), free(th);
+  /* same pool and same pod split as gpo_decide_mt: with pinned workers every page is first touched by
+   * the thread that later streams it */
+  job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
+  fill_job_t *fj = (fill_job_t *)calloc((size_t)n_threads, sizeof(fill_job_t));
+  if (!jobs || !fj) {
+    free(jobs), free(fj);
     return -1;
   }
   for (int i = 0; i < n_threads; ++i) {
-    fill_job_t *j = &jobs[i];
+    fill_job_t *j = &fj[i];
     j->seed = seed, j->pod_offset = pod_offset, j->ld = ld, j->plane = plane, j->dst = dst;
     j->G = G, j->T = T;
-    j->p0 = (uint32_t)((uint64_t)P * i / n_threads);
-    j->p1 = (uint32_t)((uint64_t)P * (i + 1) / n_threads);
+    j->p0 = split32(P, n_threads, i);
+    j->p1 = split32(P, n_threads, i + 1);
+    jobs[i].aux = j;
   }
-  for (int i = 1; i < n_threads; ++i) pthread_create(&th[i], NULL, fill_job, &jobs[i]);
-  fill_job(&jobs[0]);
-  for (int i = 1; i < n_threads; ++i) pthread_join(th[i], NULL);
-  free(jobs), free(th);
-  return 0;
+  const int rc = run_jobs(jobs, n_threads, fill_job);
+  free(jobs), free(fj);
+  return rc;
 }
 
 int gpo_synth_eligible(uint64_t seed, uint8_t *dst, uint64_t pod_offset, uint32_t P) {
@@ -426,6 +458,9 @@ int gpo_decide_synth(int n_threads, uint64_t seed, uint64_t pod_offset, uint32_t
 }
 
 int gpo_hardware_threads(void) {
+  cpu_set_t allowed; /* the CPUs this process may actually use (cgroup / taskset aware) */
+  if (sched_getaffinity(0, sizeof allowed, &allowed) == 0 && CPU_COUNT(&allowed) > 0)
+    return CPU_COUNT(&allowed);
   long n = sysconf(_SC_NPROCESSORS_ONLN);
   return n > 0 ? (int)n : 1;
 }

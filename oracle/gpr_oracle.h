@@ -60,7 +60,11 @@ int gpo_decide_synth(int n_threads, uint64_t seed, uint64_t pod_offset, uint32_t
                      int use_elig, uint32_t *decision_bits, uint32_t *candidate_bits,
                      uint64_t counts[3]);
 
+/* CPUs this process may run on (affinity-mask aware) */
 int gpo_hardware_threads(void);
+/* Timed baseline only: pin pool worker i to the i-th allowed CPU (takes effect at each worker's next
+ * job), so that windows filled by gpo_synth_fill are NUMA-local to the thread that reduces them. */
+void gpo_pool_pin(int on);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,8 @@ def load() -> C.CDLL:
         lib.gpo_decide_synth.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                          C.c_uint32, C.c_int, C.c_double, C.c_int, _P, _P, _P]
         lib.gpo_hardware_threads.restype = C.c_int
+        lib.gpo_pool_pin.restype = None
+        lib.gpo_pool_pin.argtypes = [C.c_int]
         _lib = lib
     return _lib
 
@@ -122,6 +124,11 @@ def decide_synth(seed, pod_offset, P, G, T, use_power=False, power_threshold=0.0
     W = (P + 31) // 32
     return {"decision_bits": dbits[:W], "candidate_bits": cbits[:W], "n_series": int(counts[0]),
             "n_candidates": int(counts[1]), "n_decisions": int(counts[2])}
+
+
+def pool_pin(on: bool = True):
+    """timed baseline only: pin the pool's workers to distinct CPUs (see gpr_oracle.h)"""
+    load().gpo_pool_pin(1 if on else 0)
 
 
 def hardware_threads() -> int:

@@ -55,6 +55,16 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
         eng.decide_ptr(u, P, G, T, db2, eligible=e, blocking=False)
     eng.sync()
     assert torch.equal(db, db2)
+    # the collective timer: device-side rendezvous, then per-decision completion stamps
+    eng.timer_begin()
+    for it in range(5):
+        eng.decide_ptr(u, P, G, T, db2, eligible=e, blocking=False)
+    ms = eng.timer_end()
+    eng.sync()
+    t0, st = eng.step_stamps()
+    assert len(st) == 5 and t0 > 0 and int(st[0]) > t0 and np.all(np.diff(st.astype(np.int64)) > 0)
+    assert 0 < (int(st[-1]) - t0) / 1e6 <= ms * 1.5 + 0.1
+    assert torch.equal(db, db2)
     np.save(os.path.join(out_dir, f"d_{rank}.npy"), db.cpu().numpy().view(np.uint32))
     np.save(os.path.join(out_dir, f"c_{rank}.npy"), cb.cpu().numpy().view(np.uint32))
     np.save(os.path.join(out_dir, f"n_{rank}.npy"), np.array([r.n_series, r.n_candidates, r.n_decisions]))

@@ -500,3 +500,33 @@ def test_memory_and_timing_helpers(engines):
     before = eng.launch_count()
     eng.decide(np.zeros((3, 1, 4), np.float32))
     assert eng.launch_count() >= before + 2          # one reduce + one fold
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_step_stamps(variant, engines):
+    """gpr_step_stamps: one %globaltimer completion stamp per retired decision, increasing, after the mark
+    of gpr_timer_begin, consistent with the CUDA-event time of the same region"""
+    import gpu_pruner_b200 as g
+    eng = engines[variant]
+    P, G, T = 2048, 4, 600
+    u, _, e = _synth_device(eng, 4242, P, G, T, False)
+    db = torch.zeros(P // 32, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
+    batch = eng.make_batch([dict(util=u, eligible=e, P=P, G=G, T=T, decision_bits=db)] * 16)
+    eng.decide_batch_async(batch)
+    eng.sync()
+    eng.timer_begin()
+    eng.decide_batch_async(batch)
+    ms = eng.timer_end()
+    eng.sync()
+    t0, st = eng.step_stamps()
+    assert len(st) == 16 and t0 > 0
+    d = np.diff(np.concatenate([np.array([t0], np.uint64), st]).astype(np.int64))
+    assert np.all(d > 0)
+    assert abs(d.sum() / 1e6 - ms) < 0.25 * ms + 0.05
+    # a blocking call retires exactly one decision
+    eng.decide_ptr(u, P, G, T, db, eligible=e)
+    assert len(eng.step_stamps()[1]) == 1
+    with pytest.raises(g.GprError):
+        eng.p2p_debug(7)
+    eng.p2p_debug(0)
