@@ -105,6 +105,7 @@ struct gpr_ctx {
   int tma_warps = 16;
   int tma_chunk_bytes = 8192;
   size_t chunk_bytes = 32u << 20;
+  int parse_ctas_per_sm = 6;   // k_text_parse: 4 warps and 37 KB of shared memory per CTA (GPR_PARSE_CTAS)
 
   // capacity for host windows
   uint32_t max_pods = 0, max_gpus = 0, max_samples = 0;
@@ -408,9 +409,10 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
     return fail(ctx, GPR_E_STATE, "too many outstanding async results; call gpr_sync");
 
   if (host_in) {
-    if (P > ctx->max_pods || G > ctx->max_gpus || T > ctx->max_samples ||
-        (uint64_t)P * G * T > (uint64_t)ctx->max_pods * ctx->max_gpus * ctx->max_samples)
-      return fail(ctx, GPR_E_CAPACITY, "host window %ux%ux%u exceeds capacity %ux%ux%u", P, G, T,
+    // staging is dense, so only the number of cells matters: a window with one more GPU slot or a few more
+    // samples than the shape given at gpr_create still fits as long as the product does
+    if ((uint64_t)P * G * T > (uint64_t)ctx->max_pods * ctx->max_gpus * ctx->max_samples)
+      return fail(ctx, GPR_E_CAPACITY, "host window %ux%ux%u exceeds the staging capacity of %ux%ux%u cells", P, G, T,
                   ctx->max_pods, ctx->max_gpus, ctx->max_samples);
     if (use_power && !ctx->cap_power)
       return fail(ctx, GPR_E_CAPACITY, "power plane not reserved (GPR_F_POWER_PLANE)");
@@ -435,7 +437,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   }
   ctx->masks_dirty = false;
   uint32_t* const masks = ctx->d_masks[sset];
-  if ((rc = grow(ctx, &ctx->d_bits, &ctx->bits_cap, (size_t)2 * W + 2)) != GPR_OK) return rc;
+  if ((rc = grow(ctx, &ctx->d_bits, &ctx->bits_cap, (size_t)3 * W + 2)) != GPR_OK) return rc;
   if (comm && !fused &&
       (rc = grow(ctx, &ctx->d_gather, &ctx->gather_cap, (size_t)ctx->world * 2 * W + 2)) != GPR_OK)
     return rc;
@@ -477,6 +479,8 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   uint32_t* dbits_dev = direct_bits ? res->decision_bits : ctx->d_bits;
   uint32_t* cbits_dev = direct_bits ? res->candidate_bits
                                     : ((res->candidate_bits || comm) ? ctx->d_bits + W : nullptr);
+  // pods vetoed by the power clause: never exchanged (this rank's pods only)
+  uint32_t* vbits_dev = res->veto_bits ? (host_out ? ctx->d_bits + 2 * (size_t)W : res->veto_bits) : nullptr;
   uint32_t* my_gather = nullptr;  // local gather buffer of this call (fused exchange)
   if (fused) {
     my_gather = reinterpret_cast<uint32_t*>(ctx->p2p_block + ctx->p2p_gather_off[sset]);
@@ -493,6 +497,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   fp.cutoff = win->cutoff_ts;
   fp.dbits = dbits_dev;
   fp.cbits = cbits_dev;
+  fp.vbits = vbits_dev;
   // single-launch path: the last CTA stores the three counters straight into this call's
   // pinned (device-mapped, UVA) host slot, so no copy operation separates back-to-back steps
   const int slot = (int)ctx->pending.size();
@@ -640,6 +645,8 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
                            ctx->stream));
     }
   }
+  if (res->veto_bits && host_out && W > 0)
+    CU(cudaMemcpyAsync(res->veto_bits, ctx->d_bits + 2 * (size_t)W, (size_t)W * 4u, cudaMemcpyDeviceToHost, ctx->stream));
   if (want_smax && host_out && S > 0)
     CU(cudaMemcpyAsync(res->series_max, ctx->d_smax, (size_t)S * 4u, cudaMemcpyDeviceToHost,
                        ctx->stream));
@@ -873,6 +880,7 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
       c->tma_warps = 16;
     c->tma_chunk_bytes = std::min(65536, std::max(512, env_int("GPR_TMA_CHUNK", 8192))) & ~15;
     c->chunk_bytes = (size_t)std::max(1, env_int("GPR_CHUNK_MB", 32)) << 20;  // sweep: profiles/README.md
+    c->parse_ctas_per_sm = std::max(1, std::min(8, env_int("GPR_PARSE_CTAS", 6)));
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kTmaSmemBudget));
     CU(cudaFuncSetAttribute(gpr::k_reduce_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1075,6 +1083,34 @@ int gpr_resident_planes(gpr_ctx* ctx, float** util, float** power, uint64_t* row
   if (power) *power = ctx->d_res_power;
   if (row_stride) *row_stride = ctx->res_T;
   return GPR_OK;
+}
+
+int gpr_resident_advance(gpr_ctx* ctx, uint32_t n_new) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
+  if (n_new == 0) return GPR_OK;
+  CU(cudaSetDevice(ctx->device));
+  ctx->last_was_reduce = false;
+  const uint32_t T = ctx->res_T;
+  const size_t rows = (size_t)ctx->res_P * ctx->res_G;
+  float* planes[2] = {ctx->d_res_util, ctx->d_res_power};
+  for (float* pl : planes) {
+    if (!pl) continue;
+    if (n_new >= T) {
+      CU(cudaMemsetAsync(pl, 0xFF, rows * (size_t)T * sizeof(float), ctx->stream));
+    } else {
+      const uint64_t total = (uint64_t)rows * n_new;
+      const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 16);
+      gpr::text::k_fill_columns<<<grid, 256, 0, ctx->stream>>>(pl, (uint32_t)rows, T, T, ctx->res_head, n_new);
+      ctx->launches++;
+      CU(cudaGetLastError());
+    }
+  }
+  ctx->res_head = (uint32_t)(((uint64_t)ctx->res_head + n_new) % T);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+  GPR_CATCH(ctx)
 }
 
 // ---- multi-GPU -------------------------------------------------------------------------------
@@ -1398,7 +1434,7 @@ int gpr_text_scan(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes
   if (n_bytes) {
     const uint64_t slices = (n_bytes + gpr::text::kScanBytes - 1) / gpr::text::kScanBytes;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((slices + 255) / 256, (uint64_t)ctx->sm_count * 32);
-    gpr::text::k_text_scan<<<grid, 256, 0, ctx->stream>>>(d, n_bytes, ctx->d_marks, ctx->d_marks + cap,
+    gpr::text::k_text_scan<<<grid, 256, 0, ctx->stream>>>(d, n_bytes, 0, slices, ctx->d_marks, ctx->d_marks + cap,
                                                            ctx->d_mark_counts, cap);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -1416,14 +1452,21 @@ int gpr_text_scan(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes
   return GPR_OK;
 }
 
-int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_spans, int64_t t_end, int64_t step,
-                   uint32_t n_samples, uint32_t n_rows, int32_t plane, uint32_t flags) {
+int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_spans, const gpr_text_grid* grid,
+                   int32_t plane) {
   if (!ctx) return GPR_E_INVALID;
   NvtxRange nvtx_range("gpr_text_parse");
+  if (!grid || grid->struct_size != sizeof(gpr_text_grid)) return fail(ctx, GPR_E_INVALID, "grid is NULL / struct_size mismatch");
   if (slot < 0 || slot > 2 || plane < 0 || plane > 1) return fail(ctx, GPR_E_INVALID, "bad slot %d / plane %d", slot, plane);
   if (!ctx->d_text[slot]) return fail(ctx, GPR_E_STATE, "no text in slot %d (gpr_text_scan)", slot);
   if (n_spans && !spans) return fail(ctx, GPR_E_INVALID, "spans is NULL");
-  if (step <= 0 || n_samples == 0) return fail(ctx, GPR_E_INVALID, "step and n_samples must be > 0");
+  const uint32_t n_samples = grid->n_samples, n_rows = grid->n_rows;
+  if (grid->step <= 0 || grid->step > 0xffffffffll || n_samples == 0 || grid->window_seconds <= 0)
+    return fail(ctx, GPR_E_INVALID, "step, window_seconds and n_samples must be > 0");
+  if ((grid->window_seconds + grid->step - 1) / grid->step > (int64_t)n_samples)
+    return fail(ctx, GPR_E_INVALID, "window of %lld s needs more than %u columns of %lld s", (long long)grid->window_seconds,
+                n_samples, (long long)grid->step);
+  const bool resident = (grid->flags & GPR_TEXT_RESIDENT) != 0;
   const uint64_t n = ctx->text_n[slot];
   for (uint32_t i = 0; i < n_spans; ++i) {
     if (spans[i].begin > spans[i].end || spans[i].end > n || spans[i].row >= n_rows ||
@@ -1433,30 +1476,43 @@ int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_
     spans[i].n_in = spans[i].n_oow = spans[i].n_tiny = 0;
   }
   CU(cudaSetDevice(ctx->device));
-  const size_t cells = (size_t)n_rows * n_samples;
   int rc;
-  const size_t cap_before = ctx->tplane_cap[plane];
-  if ((rc = grow(ctx, &ctx->d_tplane[plane], &ctx->tplane_cap[plane], cells + 4)) != GPR_OK) return rc;
-  if (ctx->tplane_cap[plane] != cap_before && !(flags & GPR_TEXT_FILL))
-    return fail(ctx, GPR_E_STATE, "plane %d had to grow: the first parse of a window must pass GPR_TEXT_FILL", plane);
+  float* pl = nullptr;
+  gpr::text::Grid g;
+  memset(&g, 0, sizeof g);
+  g.t_end = grid->t_end, g.t_lo = grid->t_end - grid->window_seconds;
+  g.step = (uint32_t)grid->step, g.T = n_samples;
+  if (resident) {
+    if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
+    if (n_samples != ctx->res_T || (uint64_t)n_rows > (uint64_t)ctx->res_P * ctx->res_G)
+      return fail(ctx, GPR_E_INVALID, "grid %u rows x %u does not match the resident window (%u x %u)", n_rows, n_samples,
+                  ctx->res_P * ctx->res_G, ctx->res_T);
+    pl = plane == 0 ? ctx->d_res_util : ctx->d_res_power;
+    if (!pl) return fail(ctx, GPR_E_STATE, "the resident window has no power plane");
+    g.ld = ctx->res_T;
+    g.col_end = (ctx->res_head + ctx->res_T - 1) % ctx->res_T;  // the newest bucket sits just before the head
+  } else {
+    const size_t cells = (size_t)n_rows * n_samples;
+    const size_t cap_before = ctx->tplane_cap[plane];
+    if ((rc = grow(ctx, &ctx->d_tplane[plane], &ctx->tplane_cap[plane], cells + 4)) != GPR_OK) return rc;
+    if (ctx->tplane_cap[plane] != cap_before && !(grid->flags & GPR_TEXT_FILL))
+      return fail(ctx, GPR_E_STATE, "plane %d had to grow: the first parse of a window must pass GPR_TEXT_FILL", plane);
+    pl = ctx->d_tplane[plane];
+    g.ld = n_samples, g.col_end = n_samples - 1;
+    // 0xFFFFFFFF: a NaN, and -1 as an int — below every non-negative sample for the integer atomicMax merge
+    if ((grid->flags & GPR_TEXT_FILL) && cells) CU(cudaMemsetAsync(pl, 0xFF, cells * sizeof(float), ctx->stream));
+  }
   if ((rc = grow(ctx, &ctx->d_spans, &ctx->spans_cap, (size_t)n_spans + 1)) != GPR_OK) return rc;
   ctx->last_was_reduce = false;
-  float* pl = ctx->d_tplane[plane];
-  if ((flags & GPR_TEXT_FILL) && cells) {
-    const uint64_t n_vec = (cells + 3) / 4;  // the plane is allocated with 4 cells of slack
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_vec + 255) / 256, (uint64_t)ctx->sm_count * 16);
-    gpr::text::k_text_fill_nan<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(pl), n_vec);
-    ctx->launches++;
-    CU(cudaGetLastError());
-  }
   if (n_spans && n) {
     CU(cudaMemcpyAsync(ctx->d_spans, spans, (size_t)n_spans * sizeof(gpr_text_span), cudaMemcpyHostToDevice,
                        ctx->stream));
-    const uint64_t slices = (n + gpr::text::kParseBytes - 1) / gpr::text::kParseBytes;
-    const uint64_t blocks = (slices + 255) / 256;
-    if (blocks > 0x7fffffffull) return fail(ctx, GPR_E_CAPACITY, "text too large");
-    const gpr::text::Grid g{t_end, step, n_samples, 0u};
-    gpr::text::k_text_parse<<<(uint32_t)blocks, 256, 0, ctx->stream>>>(ctx->d_text[slot], n, ctx->d_spans, n_spans, g, pl);
+    constexpr int kWarps = 4;
+    const uint64_t tiles = (n + gpr::text::kTileBytes - 1) / gpr::text::kTileBytes;
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps,
+                                                                                (uint64_t)ctx->sm_count * ctx->parse_ctas_per_sm));
+    gpr::text::k_text_parse<kWarps><<<blocks, kWarps * 32, gpr::text::text_parse_smem<kWarps>(), ctx->stream>>>(
+        ctx->d_text[slot], n, n + gpr::text::kTextPad, ctx->d_spans, n_spans, g, pl);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(spans, ctx->d_spans, (size_t)n_spans * sizeof(gpr_text_span), cudaMemcpyDeviceToHost,

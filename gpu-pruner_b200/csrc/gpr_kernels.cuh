@@ -55,6 +55,7 @@ struct FoldParams {
   int64_t cutoff;
   uint32_t* dbits;            // [ceil(P/32)]
   uint32_t* cbits;            // [ceil(P/32)] or nullptr
+  uint32_t* vbits;            // [ceil(P/32)] or nullptr: pods vetoed by the power clause (this rank's pods)
   unsigned long long* counts; // [3] n_series, n_candidates, n_decisions of this call (host-mapped slot
                               //     or device memory); written once by the last fold CTA
   unsigned long long* acc;    // [3] device accumulator of the fold grid, zero between calls
@@ -236,6 +237,7 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
       const bool dec = cand && elig[b] != 0 && !(f.created && created[b] >= f.cutoff);
       const uint32_t cw = __ballot_sync(0xffffffffu, cand);
       const uint32_t dw = __ballot_sync(0xffffffffu, dec);
+      const uint32_t vw = __ballot_sync(0xffffffffu, valid && veto[b] != 0u);
       uint32_t ns = cand ? __popc(idle[b]) : 0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
@@ -246,6 +248,7 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
       if (lane == 0) {
         f.dbits[w] = dw;
         if (f.cbits) f.cbits[w] = cw;
+        if (f.vbits) f.vbits[w] = vw;
         n_series += ns;
         n_cand += __popc(cw);
         n_dec += __popc(dw);

@@ -8,24 +8,32 @@
 // bytes) stay on the host (gpu-pruner_b200/host/ingest_device.cpp), which turns them into one
 // `Span` per series: where its sample list sits in the text and which tensor row it feeds.
 //
-// Two passes over the text, both flat over bytes (a thread owns a fixed slice of the text, not a series,
-// so the work is balanced whatever the series lengths are):
+// Two passes over the text, both flat over bytes (the work is balanced whatever the series lengths are):
 //   scan  : report the offsets of `},"values":[` and `"]]` — the two byte patterns that delimit a
 //           sample list.  Neither can occur inside a JSON string (a raw '"' ends the string), so in the
 //           compact encoding Prometheus emits they are exact; the host cross-checks every series and
 //           falls back to the CPU parser for anything else (pretty-printed JSON, histograms, ...).
-//   parse : every '[' inside a span starts a sample; the thread whose slice holds the '[' parses the
-//           sample (reading past its slice if need be) and stores the value at (row, column(ts)).
+//   parse : every '[' inside a span starts a sample.  A warp takes a 4 KB tile of text, lists its '['
+//           offsets, and hands ONE SAMPLE TO EVERY LANE per round (parse_candidate below), so the 32
+//           lanes execute the same digit loops on similar input at the same time.
 //
-// Strictness instead of generality: a sample that is not exactly `[digits[.digits],"number|NaN|±Inf"]`
-// with a number the exact decimal fast path can convert (<= 2^53 mantissa, |exp10| <= 22 — every DCGM
-// integer and every short decimal), two samples of one series that land in the same column, or
-// timestamps that run backwards, mark the whole SPAN `hard`; the host re-parses the rows of hard spans
-// with the CPU text parser and overwrites them.  So the tensor is bit-identical to the CPU ingest
-// (gpu-pruner_b200/host/ingest.cpp) for every input, and malformed input raises the same errors.
+// What a sample becomes: the value, rounded exactly like strtod + (float) (Clinger's fast path, else
+// Eisel-Lemire with the 128-bit table of gpr_pow10_table.h), merged into cell (row, column(ts)) with a
+// NaN-aware max.  `max` is what the consumer computes over the row (max_over_time,
+// /root/reference/gpu-pruner/src/query.promql.j2:10,16), so two samples of a series that fall into one
+// column, samples arriving in any order and several threads hitting one cell all give the same tensor —
+// no ordering or collision bookkeeping.  Cells start as 0xFFFFFFFF (a NaN whose bit pattern is -1 as an
+// int): for the non-negative values DCGM exports the merge is one integer atomicMax without a return
+// value (RED.MAX.S32 at L2).
+//
+// Strictness instead of generality: a sample that is not exactly `[digits[.digits],"number|NaN|±Inf"]`,
+// a number with more than 19 significant digits, or one of the rare inputs Eisel-Lemire declines marks
+// the whole SPAN `hard`; the host re-parses the rows of hard spans with the CPU text parser (strtod) and
+// overwrites them.  So the tensor equals the CPU ingest (gpu-pruner_b200/host/ingest.cpp) for every
+// input, and malformed input raises the same errors.
 //
 // Everything that decides a byte's meaning is in GPR_HD functions that also compile as plain C++:
-// tests/cpp/text_emul.cpp runs the very same code thread by thread on the CPU against the CPU ingest.
+// tests/cpp/text_emul.cpp runs the very same code candidate by candidate on the CPU against the CPU ingest.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -37,13 +45,17 @@
 #define GPR_HD inline
 #endif
 
+#include "gpr_pow10_table.h"
+
 namespace gpr {
 namespace text {
 
-constexpr uint32_t kSpanShared = 1u;  // in : several series feed this row -> merge, do not store
+constexpr uint32_t kSpanShared = 1u;  // in : several series feed this row (informational: every merge is atomic)
 constexpr uint32_t kSpanHard = 2u;    // out: the host must re-parse this span's row
 constexpr uint32_t kScanBytes = 16;   // bytes per thread, scan pass
-constexpr uint32_t kParseBytes = 128; // bytes per thread, parse pass
+constexpr uint32_t kTileBytes = 4096; // bytes per warp and step, parse pass
+constexpr uint32_t kTileHalo = 96;    // a sample may run this far past the tile that owns its '['
+constexpr uint32_t kMaxSample = 80;   // longest sample the device parser accepts (longer: hard)
 constexpr uint32_t kTextPad = 256;    // zero bytes the caller guarantees after the text
 
 struct Span {        // mirrors gpr_text_span (include/gpr.h)
@@ -52,17 +64,37 @@ struct Span {        // mirrors gpr_text_span (include/gpr.h)
   uint32_t row;      // destination row = pod * G + slot
   uint32_t flags;    // kSpan*
   uint32_t n_in;     // out: samples parsed
-  uint32_t n_oow;    // out: samples outside (t_end - N, t_end]
+  uint32_t n_oow;    // out: samples outside the window
   uint32_t n_tiny;   // out: values below the f32 denormal range, clamped to +-denorm_min
   uint32_t reserved;
 };
 
-struct Grid {        // time axis of the window (gpu-pruner_b200/host/ingest.cpp column_of)
-  int64_t t_end;     // seconds; newest column
-  int64_t step;      // seconds per column, > 0
-  uint32_t T;        // columns
+// Time axis of the destination (gpu-pruner_b200/host/ingest_internal.hpp column_of is the same rule).
+// A sample is inside the window iff t_lo < ts <= t_end  (PromQL's [Nm] selector evaluated at t_end,
+// left-open as in Prometheus 3.x).  Buckets are `step` seconds wide and end at t_end:
+//     back = (t_end - ts) / step            0 = newest bucket
+//     col  = (col_end - back) mod T
+// A dense window has col_end = T - 1 (column c = bucket T-1-c); the resident ring of daemon mode passes
+// the ring position of its newest bucket.
+struct Grid {
+  int64_t t_end;     // newest second (inclusive)
+  int64_t t_lo;      // t_end - window seconds (exclusive)
+  uint32_t step;     // seconds per column, > 0
+  uint32_t T;        // columns of the plane
+  uint32_t col_end;  // column of the newest bucket
   uint32_t pad;
+  uint64_t ld;       // elements between rows of the plane
 };
+
+constexpr int64_t kBadTs = INT64_MIN / 4;  // timestamp that is no sane epoch time: outside any window
+
+GPR_HD int64_t column_of(const Grid& g, int64_t ts) {
+  if (ts > g.t_end || ts <= g.t_lo) return -1;
+  const uint64_t d = (uint64_t)(g.t_end - ts);
+  const uint64_t back = g.step == 1u ? d : (d <= 0xffffffffull ? (uint64_t)((uint32_t)d / g.step) : d / g.step);
+  if (back >= g.T) return -1;
+  return back <= g.col_end ? (int64_t)(g.col_end - back) : (int64_t)(g.col_end + g.T - back);
+}
 
 // ---- numbers -------------------------------------------------------------------------------------------
 // exact powers of ten: 10^0 .. 10^22 are representable in binary64
@@ -78,56 +110,73 @@ GPR_HD double pow10_exact(int e) {
   }
 }
 
-// [-+]digits[.digits][(e|E)[-+]digits] at t[p...]; on success *v is the correctly rounded binary64
-// (one exact int->double conversion, one IEEE multiply or divide: Clinger's fast path) and the
-// position after the number is returned.  0 = not convertible this way (caller marks the span hard).
-GPR_HD uint64_t parse_decimal(const uint8_t* __restrict__ t, uint64_t p, double* v) {
-  bool neg = false;
-  if (t[p] == '-' || t[p] == '+') neg = t[p] == '-', ++p;
-  uint64_t m = 0;
-  int nd = 0, frac = 0;
-  bool any = false;
-  for (; t[p] >= '0' && t[p] <= '9'; ++p) {
-    any = true;
-    if (m > 900719925474099ull) return 0;  // next digit could pass 2^53
-    m = m * 10 + (uint64_t)(t[p] - '0'), ++nd;
+GPR_HD void mul64(uint64_t a, uint64_t b, uint64_t* hi, uint64_t* lo) {
+#if defined(__CUDA_ARCH__)
+  *lo = a * b;
+  *hi = __umul64hi(a, b);
+#else
+  const unsigned __int128 p = (unsigned __int128)a * b;
+  *lo = (uint64_t)p, *hi = (uint64_t)(p >> 64);
+#endif
+}
+
+GPR_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return __builtin_clzll(x);
+#endif
+}
+
+GPR_HD double bits_to_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double d;
+  memcpy(&d, &b, sizeof d);
+  return d;
+#endif
+}
+
+// Eisel-Lemire: man * 10^e10 (man != 0, at most 19 decimal digits) -> the correctly rounded binary64,
+// or false when this method cannot decide (caller marks the span hard; the CPU's strtod decides).
+// The formulation with truncated 128-bit powers of ten and the two carry checks of the Wuffs / Go
+// strconv implementations; subnormal and overflowing results are declined too.
+GPR_HD bool eisel_lemire(uint64_t man, int e10, double* out) {
+  if (e10 < kPow10Min || e10 > kPow10Max) return false;
+#if defined(__CUDA_ARCH__)
+  const uint64_t p_hi = kPow10MantDev[e10 - kPow10Min][0], p_lo = kPow10MantDev[e10 - kPow10Min][1];
+#else
+  const uint64_t p_hi = kPow10MantHost[e10 - kPow10Min][0], p_lo = kPow10MantHost[e10 - kPow10Min][1];
+#endif
+  const int clz = clz64(man);
+  man <<= clz;
+  // floor(log2(10^e10)) = (217706 * e10) >> 16 for the table's range
+  uint64_t exp2 = (uint64_t)(((217706ll * e10) >> 16) + 64 + 1023) - (uint64_t)clz;
+  uint64_t x_hi, x_lo;
+  mul64(man, p_hi, &x_hi, &x_lo);
+  if ((x_hi & 0x1FF) == 0x1FF && x_lo + man < man) {  // the truncated low half could carry into the result
+    uint64_t y_hi, y_lo;
+    mul64(man, p_lo, &y_hi, &y_lo);
+    uint64_t m_hi = x_hi;
+    const uint64_t m_lo = x_lo + y_hi;
+    if (m_lo < x_lo) ++m_hi;
+    if ((m_hi & 0x1FF) == 0x1FF && m_lo + 1 == 0 && y_lo + man < man) return false;
+    x_hi = m_hi, x_lo = m_lo;
   }
-  if (!any) return 0;
-  if (t[p] == '.') {
-    ++p;
-    bool anyf = false;
-    for (; t[p] >= '0' && t[p] <= '9'; ++p) {
-      anyf = true;
-      if (m > 900719925474099ull) return 0;
-      m = m * 10 + (uint64_t)(t[p] - '0'), ++frac;
-      if (frac > 22) return 0;
-    }
-    if (!anyf) return 0;
+  const uint64_t msb = x_hi >> 63;
+  uint64_t mant = x_hi >> (msb + 9);
+  exp2 -= 1 ^ msb;
+  if (x_lo == 0 && (x_hi & 0x1FF) == 0 && (mant & 3) == 1) return false;  // exactly half way: undecidable here
+  mant += mant & 1;
+  mant >>= 1;
+  if (mant >> 53) {
+    mant >>= 1;
+    ++exp2;
   }
-  int e10 = -frac;
-  if (t[p] == 'e' || t[p] == 'E') {
-    ++p;
-    bool eneg = false;
-    if (t[p] == '-' || t[p] == '+') eneg = t[p] == '-', ++p;
-    int ex = 0;
-    bool anye = false;
-    for (; t[p] >= '0' && t[p] <= '9'; ++p) {
-      anye = true;
-      ex = ex * 10 + (int)(t[p] - '0');
-      if (ex > 400) return 0;
-    }
-    if (!anye) return 0;
-    e10 += eneg ? -ex : ex;
-  }
-  if (m > 9007199254740992ull) return 0;
-  double d = (double)m;  // exact
-  if (m != 0) {
-    if (e10 < -22 || e10 > 22) return 0;
-    if (e10 < 0) d = d / pow10_exact(-e10);
-    else if (e10 > 0) d = d * pow10_exact(e10);
-  }
-  *v = neg ? -d : d;
-  return p;
+  if (exp2 - 1 >= 0x7FF - 1) return false;  // subnormal or overflow: leave it to strtod
+  *out = bits_to_double((exp2 << 52) | (mant & 0x000FFFFFFFFFFFFFull));
+  return true;
 }
 
 // what gph::to_f32 does (ingest.cpp): a non-zero value that rounds to 0 in f32 stays non-zero
@@ -146,72 +195,125 @@ GPR_HD float to_f32(double x, uint32_t* tiny) {
   return f;
 }
 
-GPR_HD float quiet_nan_f32() {
+GPR_HD float f32_from_bits(uint32_t b) {
 #if defined(__CUDA_ARCH__)
-  return __int_as_float(0x7fc00000);
+  return __uint_as_float(b);
 #else
-  union { uint32_t u; float f; } c;
-  c.u = 0x7fc00000u;
-  return c.f;
+  float f;
+  memcpy(&f, &b, sizeof f);
+  return f;
 #endif
 }
-
-GPR_HD float inf_f32(bool neg) {
+GPR_HD uint32_t f32_bits(float f) {
 #if defined(__CUDA_ARCH__)
-  return __int_as_float(neg ? 0xff800000 : 0x7f800000);
+  return __float_as_uint(f);
 #else
-  union { uint32_t u; float f; } c;
-  c.u = neg ? 0xff800000u : 0x7f800000u;
-  return c.f;
+  uint32_t b;
+  memcpy(&b, &f, sizeof b);
+  return b;
 #endif
 }
-
-// timestamp -> whole seconds (ingest.cpp ts_seconds): garbage maps far outside any window
-constexpr int64_t kBadTs = INT64_MIN / 4;
-GPR_HD int64_t ts_seconds(double t) {
-  if (!(t > -4e12 && t < 4e12)) return kBadTs;
-  return (int64_t)llround(t);
-}
-
-// column of ts, or -1 outside (t_end - N, t_end]   (ingest.cpp column_of)
-GPR_HD int64_t column_of(const Grid& g, int64_t ts) {
-  if (ts > g.t_end || ts < g.t_end - (int64_t)g.T * g.step - g.step) return -1;
-  const int64_t back = (g.t_end - ts + g.step / 2) / g.step;
-  if (back < 0 || back >= (int64_t)g.T) return -1;
-  return (int64_t)g.T - 1 - back;
-}
+GPR_HD float quiet_nan_f32() { return f32_from_bits(0x7fc00000u); }
+constexpr uint32_t kFillBits = 0xFFFFFFFFu;  // "no sample": a NaN that is -1 as an int (below every non-negative value)
 
 // ---- one sample ------------------------------------------------------------------------------------------
-// t[p] == '['.  Strict compact form only.  Returns the offset after the closing ']' or 0 (hard).
-GPR_HD uint64_t parse_timestamp(const uint8_t* __restrict__ t, uint64_t p, int64_t* ts) {
-  double d;
-  const uint64_t q = parse_decimal(t, p + 1, &d);
-  if (q == 0 || t[p + 1] == '+' || t[q] != ',') return 0;
-  *ts = ts_seconds(d);
+// `Src` is anything with `uint8_t operator[](uint32_t) const` (shared-memory tile on the device, a plain
+// buffer in the emulation).  Offsets are relative to the tile; nothing at or beyond p + kMaxSample is read.
+//
+// [-+]digits[.digits] at t[p...] -> *v (value digits only: Prometheus formats sample values with
+// strconv 'f', no exponent; an exponent, like anything else unusual, makes the span hard).
+// Returns the offset after the number, 0 = not convertible here.
+template <typename Src>
+GPR_HD uint32_t parse_value(const Src& t, uint32_t p, uint32_t limit, float* val, uint32_t* tiny) {
+  bool neg = false;
+  uint32_t c = t[p];
+  if (c == '-' || c == '+') neg = c == '-', c = t[++p];
+  uint64_t m = 0;
+  int sig = 0, frac = 0;
+  bool any = false, dot = false;
+  for (; p < limit; c = t[++p]) {
+    const uint32_t d = c - '0';
+    if (d < 10u) {
+      any = true;
+      if (sig == 19) {
+        if (d != 0 || !dot) return 0;  // a 20th significant digit (trailing fractional zeros are harmless)
+        continue;
+      }
+      m = m * 10 + d;
+      sig += (m != 0);
+      frac += dot;
+    } else if (c == '.' && !dot && any) {
+      dot = true;
+      any = false;  // at least one digit must follow the point
+    } else {
+      break;
+    }
+  }
+  if (!any || p >= limit) return 0;
+  float f;
+  if (m == 0) {
+    f = 0.0f;
+  } else if (!dot && m < (1ull << 24)) {
+    f = (float)(uint32_t)m;  // every DCGM_FI_DEV_GPU_UTIL / POWER_USAGE integer: exact
+  } else {
+    double d;
+    if (m <= (1ull << 53) && frac <= 22) {
+      d = (double)m;  // exact; one IEEE division: correctly rounded (Clinger)
+      if (frac) d = d / pow10_exact(frac);
+    } else if (!eisel_lemire(m, -frac, &d)) {
+      return 0;
+    }
+    f = to_f32(d, tiny);
+  }
+  *val = neg ? -f : f;
+  return p;
+}
+
+// t[p] == '['.  `[digits[.digits],` -> whole seconds, rounded half away from zero like llround(strtod())
+// (ingest.cpp ts_seconds).  At most 13 integer and 6 fractional digits: with those the integer rounding
+// below and the rounding of the correctly rounded double agree.  Returns the offset of the ','.
+template <typename Src>
+GPR_HD uint32_t parse_timestamp(const Src& t, uint32_t p, int64_t* ts) {
+  uint64_t ip = 0;
+  uint32_t q = p + 1, c = t[q];
+  const uint32_t q0 = q;
+  for (; c - '0' < 10u && q - q0 < 14; c = t[++q]) ip = ip * 10 + (c - '0');
+  if (q == q0 || q - q0 > 13) return 0;
+  if (c == '.') {
+    c = t[++q];
+    const uint32_t f0 = q;
+    const bool up = c >= '5' && c <= '9';
+    for (; c - '0' < 10u && q - f0 < 7; c = t[++q]) {
+    }
+    if (q == f0 || q - f0 > 6) return 0;
+    ip += up;
+  }
+  if (c != ',') return 0;
+  *ts = ip < 4000000000000ull ? (int64_t)ip : kBadTs;
   return q;
 }
 
-GPR_HD uint64_t parse_sample(const uint8_t* __restrict__ t, uint64_t p, int64_t* ts, float* val,
-                             uint32_t* tiny) {
-  uint64_t q = parse_timestamp(t, p, ts);
+// Returns the offset after the sample's ']' or 0 (hard).
+template <typename Src>
+GPR_HD uint32_t parse_sample(const Src& t, uint32_t p, int64_t* ts, float* val, uint32_t* tiny) {
+  const uint32_t limit = p + kMaxSample - 2;
+  uint32_t q = parse_timestamp(t, p, ts);
   if (q == 0 || t[q + 1] != '"') return 0;
   q += 2;  // past ,"
-  if (t[q] == 'N') {
+  const uint32_t c = t[q];
+  if (c == 'N') {
     if (t[q + 1] != 'a' || t[q + 2] != 'N') return 0;
     *val = quiet_nan_f32();
     q += 3;
-  } else if (t[q] == 'I' || ((t[q] == '+' || t[q] == '-') && t[q + 1] == 'I')) {
-    const bool neg = t[q] == '-';
-    if (t[q] != 'I') ++q;
+  } else if (c == 'I' || ((c == '+' || c == '-') && t[q + 1] == 'I')) {
+    const bool neg = c == '-';
+    if (c != 'I') ++q;
     if (t[q + 1] != 'n' || t[q + 2] != 'f') return 0;
-    *val = inf_f32(neg);
+    *val = f32_from_bits(neg ? 0xff800000u : 0x7f800000u);
     q += 3;
   } else {
-    double d;
-    const uint64_t r = parse_decimal(t, q, &d);
-    if (r == 0) return 0;
-    *val = to_f32(d, tiny);
-    q = r;
+    q = parse_value(t, q, limit, val, tiny);
+    if (q == 0) return 0;
   }
   if (t[q] != '"' || t[q + 1] != ']') return 0;
   return q + 2;
@@ -266,73 +368,39 @@ GPR_HD void scan_slice(const uint8_t* __restrict__ t, uint64_t n, uint64_t slice
 #undef GPR_TEXT_BYTE
 }
 
-// ---- the parse pass: one slice of kParseBytes ----------------------------------------------------------------
-// Sink: void store(uint32_t row, uint32_t col, float v)      sole writer of the row
-//       void merge(uint32_t row, uint32_t col, float v)      row shared by several series
+// ---- the parse pass: one candidate ('[' at tile offset o) ------------------------------------------------------
+// Sink: void put(uint64_t cell, float v)       merge v into plane[cell] (NaN-aware max; NaN never replaces)
 //       void hard(uint32_t span)
-//       void count(uint32_t span, uint32_t n_in, uint32_t n_oow, uint32_t n_tiny)
-// `s` = find_span(spans, n_spans, slice begin) (the kernel computes it once per warp and walks on).
-template <typename Sink>
-GPR_HD void parse_slice(const uint8_t* __restrict__ t, uint64_t n, const Span* __restrict__ spans,
-                        uint32_t n_spans, uint32_t s, uint64_t slice, const Grid& g, Sink& sink) {
-  const uint64_t c0 = slice * kParseBytes;
-  if (c0 >= n) return;
-  const uint64_t c1 = c0 + kParseBytes < n ? c0 + kParseBytes : n;
-  while (s < n_spans && spans[s].end <= c0) ++s;
-  for (; s < n_spans && spans[s].begin < c1; ++s) {
-    const uint64_t sb = spans[s].begin, se = spans[s].end;
-    const uint32_t row = spans[s].row;
-    const bool shared = (spans[s].flags & kSpanShared) != 0;
-    uint64_t p = sb > c0 ? sb : c0;
-    const uint64_t pe = se < c1 ? se : c1;
-    uint32_t n_in = 0, n_oow = 0, n_tiny = 0;
-    bool is_hard = false;
-    int64_t prev_ts = kBadTs, prev_col = -1;
-    bool have_prev = false;
-    for (; p < pe; ++p) {
-      if (t[p] != '[') continue;
-      if (!have_prev && p > sb) {
-        // the sample before this slice's first one (owned by another thread): needed to see
-        // column collisions and backwards time across the slice boundary
-        uint64_t q = p - 1;
-        const uint64_t stop = (p - sb > 96) ? p - 96 : sb;
-        while (q > stop && t[q] != '[') --q;
-        if (t[q] == '[' && q >= sb && parse_timestamp(t, q, &prev_ts) != 0) {
-          prev_col = column_of(g, prev_ts);
-        } else {
-          is_hard = true;
-        }
-      }
-      have_prev = true;
-      int64_t ts;
-      float v;
-      const uint64_t q = parse_sample(t, p, &ts, &v, &n_tiny);
-      if (q == 0 || q > se) {
-        is_hard = true;
-        break;
-      }
-      // between samples exactly one ',' ; after the last one the list closes at `se`
-      if (!((t[q] == ',' && t[q + 1] == '[') || q == se)) {
-        is_hard = true;
-        break;
-      }
-      ++n_in;
-      const int64_t col = column_of(g, ts);
-      if (prev_ts != kBadTs && ts < prev_ts) is_hard = true;            // time runs backwards
-      if (col >= 0 && col == prev_col) is_hard = true;                  // two samples, one cell: merge on the host
-      if (ts != kBadTs) prev_ts = ts;
-      if (col < 0) {
-        ++n_oow;
-      } else {
-        prev_col = col;
-        if (shared) sink.merge(row, (uint32_t)col, v);
-        else sink.store(row, (uint32_t)col, v);
-      }
-      p = q - 1;  // continue after this sample (the for's ++p lands on ',' or the closing ']')
-    }
-    if (is_hard) sink.hard(s);
-    sink.count(s, n_in, n_oow, n_tiny);
+//       void count(uint32_t span, uint32_t n_in, uint32_t n_oow, uint32_t n_tiny)   (the sink aggregates)
+// `tile` holds the text bytes [tile_off, tile_off + kTileBytes + kTileHalo).  `s` is a cursor: on entry any
+// index <= the candidate's span (the kernel starts it at find_span(tile_off) and keeps it per lane, candidates
+// of a lane come in increasing offset order); on return the candidate's span.
+template <typename Src, typename Sink>
+GPR_HD void parse_candidate(const Src& tile, uint64_t tile_off, uint32_t o, const Span* __restrict__ spans,
+                            uint32_t n_spans, uint32_t& s, const Grid& g, Sink& sink) {
+  const uint64_t pos = tile_off + o;
+  while (s < n_spans && spans[s].end <= pos) ++s;
+  if (s >= n_spans || spans[s].begin > pos) return;  // a '[' outside every sample list (label text)
+  const uint64_t se = spans[s].end;
+  int64_t ts;
+  float v;
+  uint32_t tiny = 0;
+  const uint32_t q = parse_sample(tile, o, &ts, &v, &tiny);
+  // between samples exactly one ',' ; after the last one the list closes at `se`
+  if (q == 0 || tile_off + q > se || !(tile_off + q == se || (tile[q] == ',' && tile[q + 1] == '['))) {
+    sink.hard(s);
+    return;
   }
+  const int64_t col = column_of(g, ts);
+  sink.count(s, 1u, col < 0 ? 1u : 0u, tiny);
+  if (col >= 0) sink.put((uint64_t)spans[s].row * g.ld + (uint64_t)col, v);
+}
+
+// reference merge for host-side sinks (the device sink is atomic, gpr_text_kernels.cuh)
+GPR_HD void merge_cell_bits(uint32_t* cell, float v) {
+  if (v != v) return;
+  const float c = f32_from_bits(*cell);
+  if (c != c || c < v) *cell = f32_bits(v);
 }
 
 }  // namespace text

@@ -373,13 +373,24 @@ class IdleEngine:
             return np.sort(opens[:no.value]), np.sort(closes[:nc.value])
 
     def text_parse(self, spans: np.ndarray, t_end: int, step: int, T: int, n_rows: int, slot: int = 0,
-                   plane: int = 0, fill: bool = True) -> np.ndarray:
+                   plane: int = 0, fill: bool = True, window_seconds: Optional[int] = None,
+                   resident: bool = False) -> np.ndarray:
         """Parse the samples of ``spans`` (structured array of SPAN_DTYPE, sorted by begin) of the text in
-        ``slot`` into the context's plane; returns the spans with their out-fields filled."""
+        ``slot`` into the context's plane (or, ``resident=True``, the resident ring); returns the spans with
+        their out-fields filled.  ``window_seconds`` defaults to ``T * step``."""
         spans = np.ascontiguousarray(spans, dtype=self.SPAN_DTYPE)
-        self._check(self._lib.gpr_text_parse(self._h, slot, _ptr(spans), len(spans), int(t_end), int(step), int(T),
-                                             int(n_rows), plane, ffi.GPR_TEXT_FILL if fill else 0))
+        g = ffi.gpr_text_grid()
+        g.struct_size = C.sizeof(ffi.gpr_text_grid)
+        g.flags = (ffi.GPR_TEXT_FILL if fill and not resident else 0) | (ffi.GPR_TEXT_RESIDENT if resident else 0)
+        g.t_end, g.step = int(t_end), int(step)
+        g.window_seconds = int(T) * int(step) if window_seconds is None else int(window_seconds)
+        g.n_samples, g.n_rows = int(T), int(n_rows)
+        self._check(self._lib.gpr_text_parse(self._h, slot, _ptr(spans), len(spans), C.byref(g), plane))
         return spans
+
+    def resident_advance(self, n_new: int):
+        """open the next ``n_new`` buckets of the resident ring without data (all rows: no sample)"""
+        self._check(self._lib.gpr_resident_advance(self._h, int(n_new)))
 
     def text_planes(self):
         u, w = C.c_void_p(), C.c_void_p()

@@ -49,6 +49,7 @@ class gpr_result(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("out_mem_kind", C.c_int32),
         ("decision_bits", C.c_void_p), ("candidate_bits", C.c_void_p), ("series_max", C.c_void_p),
+        ("veto_bits", C.c_void_p),
         ("n_series", C.c_uint64), ("n_candidates", C.c_uint64), ("n_decisions", C.c_uint64),
         ("kernel_ms", C.c_double),
     ]
@@ -69,7 +70,16 @@ class gpr_text_span(C.Structure):
     ]
 
 
-GPR_SPAN_SHARED, GPR_SPAN_HARD, GPR_TEXT_FILL = 1, 2, 1
+class gpr_text_grid(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("flags", C.c_uint32),
+        ("t_end", C.c_int64), ("window_seconds", C.c_int64), ("step", C.c_int64),
+        ("n_samples", C.c_uint32), ("n_rows", C.c_uint32),
+    ]
+
+
+GPR_SPAN_SHARED, GPR_SPAN_HARD = 1, 2
+GPR_TEXT_FILL, GPR_TEXT_RESIDENT = 1, 2
 
 _P = C.c_void_p
 # name -> (restype, argtypes); must list every symbol include/gpr.h declares
@@ -85,6 +95,7 @@ PROTOTYPES = {
     "gpr_resident_init": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "gpr_append": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_int32]),
     "gpr_resident_reindex": (C.c_int, [_P]),
+    "gpr_resident_advance": (C.c_int, [_P, C.c_uint32]),
     "gpr_decide_resident": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result)]),
     "gpr_resident_planes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gpr_comm_unique_id": (C.c_int, [_P]),
@@ -106,8 +117,7 @@ PROTOTYPES = {
     "gpr_get_device_info": (C.c_int, [_P, C.POINTER(gpr_device_info)]),
     "gpr_text_scan": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, C.c_int32, _P, _P, C.c_uint64,
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "gpr_text_parse": (C.c_int, [_P, C.c_int32, _P, C.c_uint32, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
-                                 C.c_int32, C.c_uint32]),
+    "gpr_text_parse": (C.c_int, [_P, C.c_int32, _P, C.c_uint32, C.POINTER(gpr_text_grid), C.c_int32]),
     "gpr_text_planes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "gpr_synth_fill": (C.c_int, [_P, C.c_uint64, C.c_int32, _P, C.c_uint64, C.c_uint32,
                                  C.c_uint32, C.c_uint32, C.c_uint64]),

@@ -3,6 +3,7 @@
 // scale requests — without a GPU.  Strings are returned in a caller-provided buffer as JSON.
 #include <chrono>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -86,6 +87,10 @@ GPH_API int gph_format_float(double v, char* out, int cap) { return put(gph::for
 // util_out/power_out may be NULL to query dimensions + the pod table (JSON) first.
 static int g_ingest_threads = -1;  // -1: DOM path; >= 0: text path with that many threads (0 = all)
 GPH_API void gph_ingest_mode(int threads) { g_ingest_threads = threads; }
+// response of the `node_dmi_info` query applied by the following gph_ingest calls (NULL / "" = none)
+static std::string g_dmi_json;
+GPH_API void gph_ingest_dmi(const char* dmi_json) { g_dmi_json = dmi_json ? dmi_json : ""; }
+static gph::Window g_last_window;  // the window of the most recent successful gph_ingest (tensor dropped)
 
 GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char* power_json,
                        long long duration_min, long long step, long long t_end, unsigned* dims,
@@ -108,6 +113,7 @@ GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char*
       if (power_json) pw = gph::Json::parse(power_json), ppw = &pw;
       w = gph::ingest_matrix(u, ppf, ppw, o);
     }
+    if (!g_dmi_json.empty()) gph::apply_node_types(w, gph::Json::parse(g_dmi_json));
     const double ingest_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     dims[0] = w.P, dims[1] = w.G, dims[2] = w.T;
@@ -122,9 +128,11 @@ GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char*
         gph::Json sj = gph::Json::object();
         sj.set("Hostname", s.hostname), sj.set("container", s.container), sj.set("gpu", s.gpu);
         sj.set("modelName", s.model), sj.set("node_type", s.node_type), sj.set("from_prof", s.from_prof);
+        sj.set("group", (int64_t)s.group);
         slots.push(sj);
       }
       p.set("slots", slots);
+      p.set("has_groups", pe.has_groups);
       p.set("power_slots", (int64_t)pe.power_slots);
       pods.push(p);
     }
@@ -136,11 +144,43 @@ GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char*
     meta.set("samples_out_of_window", (int64_t)w.stats.samples_out_of_window);
     meta.set("duplicates_merged", (int64_t)w.stats.duplicates_merged);
     meta.set("tiny_values_clamped", (int64_t)w.stats.tiny_values_clamped);
+    meta.set("span", (int64_t)w.span);
+    g_last_window = std::move(w);
+    g_last_window.util.clear(), g_last_window.power.clear();
     return pods_json ? (put(meta.dump(), pods_json, cap) >= 0 ? 0 : -3) : 0;
   } catch (const std::exception& e) {
     if (pods_json) put(std::string("{\"error\":\"") + gph::json_escape(e.what()) + "\"}", pods_json, cap);
     return -1;
   }
+}
+
+// Exact `sum by` for the window of the last gph_ingest: corrects the engine's / oracle's raw verdict arrays in
+// place (gph::resolve_sum_by_groups).  veto_bits / eligible / created_ts may be NULL.  counts = n_series,
+// n_candidates, n_decisions.  Returns the number of pods whose verdict changed, or negative.
+GPH_API int gph_resolve_groups(const float* series_max, const unsigned* veto_bits, const unsigned char* eligible,
+                               const long long* created_ts, long long cutoff, unsigned* candidate_bits,
+                               unsigned* decision_bits, unsigned long long* counts) {
+  try {
+    uint64_t c[3] = {counts[0], counts[1], counts[2]};
+    const gph::GroupFixup fx = gph::resolve_sum_by_groups(
+        g_last_window, series_max, veto_bits, eligible, reinterpret_cast<const int64_t*>(created_ts), cutoff,
+        candidate_bits, decision_bits, &c[0], &c[1], &c[2]);
+    counts[0] = c[0], counts[1] = c[1], counts[2] = c[2];
+    return (int)fx.pods_changed;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+// value Prometheus reports for every `sum by` group of the last window (NaN for rows that do not start a group
+// or groups without an element), [P][G] like series_max
+GPH_API int gph_group_values(const float* series_max, double* out) {
+  const gph::Window& w = g_last_window;
+  for (uint32_t p = 0; p < w.P; ++p)
+    for (uint32_t g = 0; g < w.G; ++g)
+      out[(size_t)p * w.G + g] = g < w.pods[p].slots.size() && w.pods[p].slots[g].group == g
+                                     ? gph::group_value(w, series_max, p, g)
+                                     : std::numeric_limits<double>::quiet_NaN();
+  return 0;
 }
 
 // owner walk over a fixture directory: pod_meta_json = the pod's .metadata.  JSON out:

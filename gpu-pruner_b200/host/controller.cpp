@@ -205,6 +205,22 @@ TickResult Controller::run_query_and_scale(const Window& w) {
       out.error = "Failed to run query! idle engine returned a short result";
       return out;
     }
+    // pods with several series in one `sum by` group: the element is the SUM of the members' maxima
+    // (query.promql.j2:9,21); re-derived on the host from the per-series maxima, rare
+    if (v.veto_bits.size() >= W || !rq.power_on) {
+      const GroupFixup fx = resolve_sum_by_groups(w, v.series_max.data(), v.veto_bits.size() >= W ? v.veto_bits.data() : nullptr,
+                                                  rq.eligible, rq.created_ts, rq.cutoff_ts, v.candidate_bits.data(),
+                                                  v.decision_bits.data(), &v.n_series, &v.n_candidates, &v.n_decisions);
+      if (fx.pods_changed)
+        log_.info("sum by: " + std::to_string(fx.pods_examined) + " pod(s) with duplicate series re-evaluated, " +
+                  std::to_string(fx.pods_changed) + " verdict(s) changed");
+    } else {
+      for (const PodEntry& pe : w.pods)
+        if (pe.has_groups) {
+          out.error = "Failed to run query! idle engine returned no veto bitmap for a window with duplicate series";
+          return out;
+        }
+    }
     std::copy(v.decision_bits.begin(), v.decision_bits.begin() + W, dbits.begin());
     std::copy(v.candidate_bits.begin(), v.candidate_bits.begin() + W, cbits.begin());
     std::copy(v.series_max.begin(), v.series_max.begin() + (size_t)P * G, smax.begin());
@@ -221,10 +237,12 @@ TickResult Controller::run_query_and_scale(const Window& w) {
     PodMetricData pmd;
     pmd.name = pe.name, pmd.ns = pe.ns;
     for (uint32_t g = 0; g < pe.slots.size(); ++g) {
-      if (smax[(size_t)p * G + g] == 0.0f) {
+      if (pe.slots[g].group != g) continue;              // elements are `sum by` groups (j2:9)
+      const double value = group_value(w, smax.data(), p, g);
+      if (value == 0.0) {
         const GpuSlot& s = pe.slots[g];
         pmd.container = s.container, pmd.node_type = s.node_type, pmd.gpu_model = s.model;
-        pmd.value = s.from_prof ? 0.0 : 0.0 / 100.0;   // max / 100 on the UTIL branch (j2:20); idle => 0
+        pmd.value = value;                               // what lib.rs:184 reads: 0 for every survivor of `== 0`
         break;
       }
     }

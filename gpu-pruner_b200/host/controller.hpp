@@ -70,6 +70,7 @@ struct VerdictRequest {
 };
 struct Verdict {
   std::vector<uint32_t> decision_bits, candidate_bits;   // ceil(P/32) words
+  std::vector<uint32_t> veto_bits;                       // ceil(P/32) words or empty: pods vetoed by the power clause
   std::vector<float> series_max;                         // [P*G]
   uint64_t n_series = 0, n_candidates = 0, n_decisions = 0;
   double kernel_ms = 0;

@@ -36,6 +36,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     const uint32_t W = (w.P + 31) / 32;
     out->decision_bits.assign(W, 0), out->candidate_bits.assign(W, 0);
     out->series_max.assign((size_t)w.P * w.G, 0.f);
+    out->veto_bits.assign(W, 0);
     gpr_window win;
     memset(&win, 0, sizeof win);
     win.struct_size = sizeof win;
@@ -62,6 +63,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     res.decision_bits = out->decision_bits.data();
     res.candidate_bits = out->candidate_bits.data();
     res.series_max = out->series_max.data();
+    res.veto_bits = out->veto_bits.data();
     const int rc = gpr_decide(ctx_, &win, &res);
     if (rc != GPR_OK) {
       *error = "idle engine (" + std::to_string(rc) + "): " + gpr_last_error(ctx_);
@@ -120,11 +122,14 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     }
     opens->resize(no), closes->resize(nc);
   }
-  void parse(int slot, std::vector<gpr_text_span>& spans, int64_t t_end, int64_t step, uint32_t T, uint32_t n_rows,
-             int plane, bool fill) override {
-    check(gpr_text_parse(ctx_, slot, spans.data(), (uint32_t)spans.size(), t_end, step, T, n_rows, plane,
-                         fill ? GPR_TEXT_FILL : 0u),
-          "gpr_text_parse");
+  void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) override {
+    gpr_text_grid g;
+    memset(&g, 0, sizeof g);
+    g.struct_size = sizeof g;
+    g.flags = (grid.fill ? GPR_TEXT_FILL : 0u) | (grid.resident ? GPR_TEXT_RESIDENT : 0u);
+    g.t_end = grid.t_end, g.window_seconds = grid.span, g.step = grid.step;
+    g.n_samples = grid.T, g.n_rows = grid.n_rows;
+    check(gpr_text_parse(ctx_, slot, spans.data(), (uint32_t)spans.size(), &g, plane), "gpr_text_parse");
   }
   void patch_row(int plane, uint32_t row, uint32_t T, const float* data) override {
     float *u = nullptr, *p = nullptr;

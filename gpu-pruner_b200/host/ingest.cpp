@@ -1,6 +1,7 @@
 #include "ingest.hpp"
 
 #include <thread>
+#include <unordered_map>
 
 #include "ingest_internal.hpp"
 
@@ -47,7 +48,7 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
   Assigner asg(w);
   std::vector<RawSeries> useries, pseries;
   int64_t newest = kNoTs;
-  int64_t min_step = std::numeric_limits<int64_t>::max();
+  StepVote vote;
 
   auto scan = [&](const Json& resp, bool is_power, bool is_prof) {
     for (const Json& s : result_array(resp).items()) {
@@ -69,7 +70,7 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
         const int64_t ts = ts_seconds(tv[0].as_number());
         if (ts == kBadTs) continue;
         newest = std::max(newest, ts);
-        if (prev != kNoTs && ts > prev) min_step = std::min(min_step, ts - prev);
+        if (prev != kNoTs) vote.add(ts - prev);
         prev = ts;
       }
     }
@@ -77,7 +78,7 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
   if (prof) scan(*prof, false, true);  // PROF first so it wins the `or`
   scan(util, false, false);
   if (power) scan(*power, true, false);
-  finish_shape(w, opt, newest, min_step, power != nullptr);
+  finish_shape(w, opt, newest, vote.result(), power != nullptr);
 
   auto place = [&](const std::vector<RawSeries>& list, std::vector<float>& plane) {
     for (const RawSeries& rs : list) {
@@ -133,7 +134,8 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
   if (power) scan(*power, true, false);
 
   // pre-pass only when the caller did not say where the window ends / what the step is
-  int64_t newest = kNoTs, min_step = std::numeric_limits<int64_t>::max();
+  int64_t newest = kNoTs;
+  StepVote vote;
   if (opt.t_end <= 0 || opt.step <= 0) {
     auto pre = [&](const std::vector<TextSeries>& list) {
       for (const TextSeries& ts : list) {
@@ -142,7 +144,7 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
           const int64_t ti = ts_seconds(t);
           if (ti == kBadTs) return;
           newest = std::max(newest, ti);
-          if (prev != kNoTs && ti > prev) min_step = std::min(min_step, ti - prev);
+          if (prev != kNoTs) vote.add(ti - prev);
           prev = ti;
         });
       }
@@ -150,7 +152,7 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
     pre(useries);
     pre(pseries);
   }
-  finish_shape(w, opt, newest, min_step, power != nullptr);
+  finish_shape(w, opt, newest, vote.result(), power != nullptr);
 
   auto place = [&](std::vector<TextSeries>& list, std::vector<float>& plane) {
     // rows written by exactly one series can be filled concurrently; shared rows are merged afterwards
@@ -203,6 +205,109 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
   place(useries, w.util);
   if (power) place(pseries, w.power);
   return w;
+}
+
+// =====================================================================================================
+// node_dmi_info join (query.promql.j2:23-34)
+//   label_replace(label_replace(node_dmi_info, "Hostname", "$1", "instance", "(.+)"), "node_type", "$1",
+//                 "product_name", "(.+)")
+//   idle_gpus * on (Hostname) group_left(node_type) (...)  or on (...) idle_gpus
+// node_dmi_info has the value 1, so only the label travels.  label_replace leaves the destination label
+// untouched when the (fully anchored) regex does not match, i.e. when the source label is empty or absent.
+void apply_node_types(Window& w, const Json& dmi) {
+  const Json* result = &dmi;
+  if (dmi.is_object()) {
+    const Json& st = dmi["status"];
+    if (st.is_string() && st.as_string() != "success")
+      throw std::runtime_error("prometheus response status: " + st.as_string());
+    result = &dmi["data"]["result"];
+  }
+  if (!result->is_array()) throw std::runtime_error("node_dmi_info: not a Prometheus vector / matrix response");
+  std::unordered_map<std::string, std::string> by_host;  // Hostname -> node_type ("" = label absent)
+  for (const Json& s : result->items()) {
+    const Json& m = s["metric"];
+    if (!m.is_object()) throw std::runtime_error("node_dmi_info: series without a label map");
+    auto str = [&](const char* k) {
+      const Json* v = m.find(k);
+      return v && v->is_string() ? v->as_string() : std::string();
+    };
+    const std::string instance = str("instance"), product = str("product_name");
+    const std::string host = !instance.empty() ? instance : str("Hostname");
+    const std::string node_type = !product.empty() ? product : str("node_type");
+    // many-to-one matching: two series with the same `on` signature on the "one" side fail the whole query
+    if (!by_host.emplace(host, node_type).second)
+      throw std::runtime_error("Failed to run query! found duplicate series for the match group {Hostname=\"" + host +
+                               "\"} on the right hand-side of the operation (node_dmi_info)");
+  }
+  for (PodEntry& pe : w.pods)
+    for (GpuSlot& g : pe.slots) {
+      auto it = by_host.find(g.hostname);
+      // no DMI series for the host: `or on (...)` restores the element without the label; a DMI series
+      // without product_name: group_left copies an absent label.  Both read back as "unknown" (lib.rs:176-179)
+      g.node_type = it != by_host.end() && !it->second.empty() ? it->second : "unknown";
+    }
+}
+
+// =====================================================================================================
+// exact `sum by` for duplicate series (query.promql.j2:9,21)
+namespace {
+// Prometheus' `sum` (promql/engine.go, kahanSumInc): Neumaier-compensated float64 sum
+struct KahanSum {
+  double sum = 0.0, c = 0.0;
+  bool any = false;
+  void add(double x) {
+    any = true;
+    const double t = sum + x;
+    if (std::isinf(t)) c = 0.0;
+    else if (std::fabs(sum) >= std::fabs(x)) c += (sum - t) + x;
+    else c += (x - t) + sum;
+    sum = t;
+  }
+  double value() const { return std::isinf(sum) ? sum : sum + c; }
+};
+}  // namespace
+
+double group_value(const Window& w, const float* series_max, uint32_t p, uint32_t slot) {
+  const PodEntry& pe = w.pods[p];
+  KahanSum k;
+  for (uint32_t g = slot; g < pe.slots.size(); ++g) {
+    if (pe.slots[g].group != slot) continue;
+    const float m = series_max[(size_t)p * w.G + g];
+    if (std::isnan(m)) continue;  // no sample in the window: the series is no element of the instant vector
+    // `/ 100` on the UTIL branch happens before the sum (query.promql.j2:20)
+    k.add(pe.slots[g].from_prof ? (double)m : (double)m / 100.0);
+  }
+  return k.any ? k.value() : std::numeric_limits<double>::quiet_NaN();
+}
+
+GroupFixup resolve_sum_by_groups(const Window& w, const float* series_max, const uint32_t* veto_bits,
+                                 const uint8_t* eligible, const int64_t* created_ts, int64_t cutoff,
+                                 uint32_t* candidate_bits, uint32_t* decision_bits, uint64_t* n_series,
+                                 uint64_t* n_candidates, uint64_t* n_decisions) {
+  GroupFixup fx;
+  for (uint32_t p = 0; p < w.P; ++p) {
+    const PodEntry& pe = w.pods[p];
+    if (!pe.has_groups) continue;
+    ++fx.pods_examined;
+    const uint32_t word = p >> 5, bit = 1u << (p & 31);
+    const bool veto = veto_bits && (veto_bits[word] & bit);
+    // what the engine counted: every idle ROW of a candidate pod
+    const bool was_cand = (candidate_bits[word] & bit) != 0, was_dec = (decision_bits[word] & bit) != 0;
+    uint64_t rows_idle = 0, groups_idle = 0;
+    for (uint32_t g = 0; g < pe.slots.size(); ++g) {
+      if (series_max[(size_t)p * w.G + g] == 0.0f) ++rows_idle;
+      if (pe.slots[g].group == g && group_value(w, series_max, p, g) == 0.0) ++groups_idle;
+    }
+    const bool cand = groups_idle > 0 && !veto;
+    const bool dec = cand && (!eligible || eligible[p]) && !(created_ts && created_ts[p] >= cutoff);
+    if (n_series) *n_series = *n_series - (was_cand ? rows_idle : 0) + (cand ? groups_idle : 0);
+    if (n_candidates) *n_candidates = *n_candidates - (was_cand ? 1 : 0) + (cand ? 1 : 0);
+    if (n_decisions) *n_decisions = *n_decisions - (was_dec ? 1 : 0) + (dec ? 1 : 0);
+    if (cand != was_cand || dec != was_dec) ++fx.pods_changed;
+    candidate_bits[word] = cand ? candidate_bits[word] | bit : candidate_bits[word] & ~bit;
+    decision_bits[word] = dec ? decision_bits[word] | bit : decision_bits[word] & ~bit;
+  }
+  return fx;
 }
 
 }  // namespace gph

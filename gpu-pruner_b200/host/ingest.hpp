@@ -17,15 +17,17 @@
 
 namespace gph {
 
-struct GpuSlot {            // one (Hostname, container, pod, namespace, gpu, modelName) group
+struct GpuSlot {            // one SERIES of a (Hostname, container, pod, namespace, gpu, modelName) group
   std::string hostname, container, gpu, model, node_type;
-  bool from_prof = false;   // cell holds DCGM_FI_PROF_GR_ENGINE_ACTIVE (0..1) rather than GPU_UTIL (0..100)
+  bool from_prof = false;   // row holds DCGM_FI_PROF_GR_ENGINE_ACTIVE (0..1) rather than GPU_UTIL (0..100)
+  uint32_t group = 0;       // slot index of the first series of its `sum by` group (== own index: first / only one)
 };
 
 struct PodEntry {
   std::string name, ns;
-  std::vector<GpuSlot> slots;        // util / prof groups, in order of first appearance
-  uint32_t power_slots = 0;
+  std::vector<GpuSlot> slots;        // util / prof series, in order of first appearance
+  uint32_t power_slots = 0;          // power series (each its own row: `unless` needs no grouping)
+  bool has_groups = false;           // some `sum by` group of this pod has more than one series
 };
 
 struct IngestStats {
@@ -36,7 +38,9 @@ struct IngestStats {
 
 struct Window {
   uint32_t P = 0, G = 0, T = 0;
-  int64_t t_end = 0, step = 1;        // seconds; column c covers timestamp t_end - (T-1-c)*step
+  // seconds.  A sample is inside iff t_end - span < ts <= t_end (the [Nm] selector evaluated at t_end,
+  // left-open); column c holds the bucket (t_end - (T-c)*step, t_end - (T-1-c)*step], T = ceil(span/step)
+  int64_t t_end = 0, step = 1, span = 0;
   std::vector<PodEntry> pods;
   std::vector<float> util;            // [P][G][T], NaN = no sample
   std::vector<float> power;           // empty, or [P][G][T]
@@ -48,7 +52,7 @@ struct Window {
 
 struct IngestOptions {
   int64_t duration_min = 30;          // window length, --duration
-  int64_t step = 0;                   // seconds; 0 = infer (smallest positive timestamp delta)
+  int64_t step = 0;                   // seconds; 0 = infer (the most frequent positive timestamp delta)
   int64_t t_end = 0;                  // 0 = newest timestamp in the response
 };
 
@@ -64,5 +68,28 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
 // implementation it is tested against (tests/test_host.py).
 Window ingest_matrix_text(const std::string& util, const std::string* prof, const std::string* power,
                           const IngestOptions& opt, int n_threads = 0);
+
+// `node_dmi_info` enrichment (query.promql.j2:23-34): `dmi` is the response of the instant (or range) query
+// `node_dmi_info`; every slot whose Hostname has a DMI series gets that series' product_name as node_type,
+// the others keep "unknown" (lib.rs:176-179).  Two DMI series for one Hostname make the reference's query
+// fail (many-to-one matching with a duplicate on the "one" side): throws std::runtime_error.
+void apply_node_types(Window& w, const Json& dmi);
+
+// Exact `sum by` (query.promql.j2:9,21) for pods with duplicate series.  The tensor keeps every series
+// in its own row; the engine's verdict treats every row as an element.  For pods with has_groups this
+// re-derives the verdict from the per-series window maxima: element value = compensated float64 sum of
+// the members' maxima (UTIL members / 100), element idle iff value == 0, pod candidate iff any element is
+// idle and the pod is not vetoed.  Arrays are the engine's outputs, corrected in place; `eligible` /
+// `created_ts` / `cutoff` re-apply the gates (main.rs:473-510) for the pods that change.
+struct GroupFixup {
+  uint64_t pods_examined = 0, pods_changed = 0;
+};
+GroupFixup resolve_sum_by_groups(const Window& w, const float* series_max, const uint32_t* veto_bits,
+                                 const uint8_t* eligible, const int64_t* created_ts, int64_t cutoff,
+                                 uint32_t* candidate_bits, uint32_t* decision_bits, uint64_t* n_series,
+                                 uint64_t* n_candidates, uint64_t* n_decisions);
+// value of the element (group) that slot `slot` of pod `p` starts, from the per-series maxima: what
+// Prometheus reports for it (NaN = no element)
+double group_value(const Window& w, const float* series_max, uint32_t p, uint32_t slot);
 
 }  // namespace gph

@@ -212,7 +212,9 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
         spans[k].push_back(sp);
       }
       const auto tp = std::chrono::steady_clock::now();
-      dev.parse(texts[k]->slot, spans[k], w.t_end, w.step, w.T, n_rows, plane, fill);
+      TextDevice::TextGrid grid;
+      grid.t_end = w.t_end, grid.span = w.span, grid.step = w.step, grid.T = w.T, grid.n_rows = n_rows, grid.fill = fill;
+      dev.parse(texts[k]->slot, spans[k], grid, plane);
       rep.parse_ms += ms_since(tp);
       fill = false;
       rep.spans += spans[k].size();

@@ -22,9 +22,15 @@ class TextDevice {
   // `},"values":[` ('}' position) and `"]]` ('"' position)
   virtual void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens,
                     std::vector<uint64_t>* closes) = 0;
-  // parse the samples of `spans` (sorted by begin) of the text in `slot` into plane 0 (util) / 1 (power)
-  virtual void parse(int slot, std::vector<gpr_text_span>& spans, int64_t t_end, int64_t step, uint32_t T,
-                     uint32_t n_rows, int plane, bool fill) = 0;
+  // parse the samples of `spans` (sorted by begin) of the text in `slot` into plane 0 (util) / 1 (power):
+  // samples with grid.t_end - grid.span < ts <= grid.t_end, bucket (t_end - ts) / step, NaN-aware max merge
+  struct TextGrid {
+    int64_t t_end = 0, span = 0, step = 1;
+    uint32_t T = 0, n_rows = 0;
+    bool fill = true;        // start from an all-"no sample" plane
+    bool resident = false;   // destination = the resident ring of daemon mode instead of the context plane
+  };
+  virtual void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) = 0;
   virtual void patch_row(int plane, uint32_t row, uint32_t T, const float* data) = 0;
   virtual const float* plane(int plane) = 0;
 };

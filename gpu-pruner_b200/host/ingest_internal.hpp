@@ -108,8 +108,7 @@ inline float to_f32(double x, uint64_t* clamped) {
   return f;
 }
 
-// duplicates of one group: per-step max.  For the non-negative DCGM metrics the window max of that
-// is 0 exactly when every member's max is 0, i.e. when `sum by` of the maxima is 0.
+// several samples of one series in one bucket: NaN-aware max — what max_over_time over the row computes anyway
 inline void merge_cell(float& cell, float v) {
   cell = std::isnan(cell) ? v : (std::isnan(v) ? cell : std::max(cell, v));
 }
@@ -154,30 +153,19 @@ class Assigner {
     gkey_.assign(host).append(1, '\x1f').append(ctr).append(1, '\x1f').append(gpu).append(1, '\x1f').append(model);
     uint32_t slot;
     if (is_power) {
+      // every power series is its own row: `unless on (pod, namespace)` looks at each series' max
+      // (query.promql.j2:36-44), there is no `sum by` on that side
       auto& idx = pslot_index_[p];
-      auto f = idx.find(gkey_);
-      if (f == idx.end()) slot = idx[gkey_] = w_.pods[p].power_slots++;
-      else slot = f->second, ++w_.stats.duplicates_merged;
+      if (!idx.emplace(gkey_, 0u).second) ++w_.stats.duplicates_merged;
+      slot = w_.pods[p].power_slots++;
     } else {
       auto& idx = slot_index_[p];
       auto f = idx.find(gkey_);
-      bool fresh = false;
-      if (f == idx.end()) {
-        slot = idx[gkey_] = (uint32_t)w_.pods[p].slots.size();
-        GpuSlot g;
-        g.hostname = std::string(host), g.container = std::string(ctr), g.gpu = std::string(gpu);
-        g.model = std::string(model);
-        std::string_view nt;
-        g.node_type = m.str("node_type", &nt) ? std::string(nt) : "unknown";  // lib.rs:176-179
-        g.from_prof = is_prof;
-        w_.pods[p].slots.push_back(g);
-        fresh = true;
-      } else {
-        slot = f->second;
-      }
+      const bool fresh = f == idx.end();
+      const uint32_t group = fresh ? (uint32_t)w_.pods[p].slots.size() : f->second;
       // `A or B` (query.promql.j2:10-20) matches on the FULL label set: a UTIL element is dropped only
       // if a PROF element with identical labels exists; series that differ in any other label both
-      // survive the `or` and are then folded together by `sum by`
+      // survive the `or` and are then added up by `sum by`
       // (the signature is only built when a PROF series is involved: never for the usual UTIL-only tick)
       auto signature = [&]() {
         std::vector<std::string> parts;
@@ -190,17 +178,26 @@ class Assigner {
         return sig;
       };
       if (is_prof) {
-        prof_sigs_[std::make_pair(p, slot)].push_back(signature());
-        w_.pods[p].slots[slot].from_prof = true;
+        prof_sigs_[std::make_pair(p, group)].push_back(signature());
       } else {
-        auto ps = prof_sigs_.find(std::make_pair(p, slot));
+        auto ps = prof_sigs_.find(std::make_pair(p, group));
         if (ps != prof_sigs_.end()) {
           const std::string sig = signature();
           for (const std::string& x : ps->second)
             if (x == sig) return Shadowed;
         }
       }
-      if (!fresh) ++w_.stats.duplicates_merged;
+      // every series keeps its own row; members of one `sum by` group are tied together by `group`
+      slot = (uint32_t)w_.pods[p].slots.size();
+      if (fresh) idx[gkey_] = slot;
+      GpuSlot g;
+      g.hostname = std::string(host), g.container = std::string(ctr), g.gpu = std::string(gpu);
+      g.model = std::string(model);
+      g.node_type = "unknown";  // lib.rs:176-179; the node_dmi_info join fills it in (apply_node_types)
+      g.from_prof = is_prof;
+      g.group = group;
+      w_.pods[p].slots.push_back(g);
+      if (!fresh) w_.pods[p].has_groups = true, ++w_.stats.duplicates_merged;
     }
     *pod_out = p, *slot_out = slot;
     return Placed;
@@ -215,17 +212,33 @@ class Assigner {
   std::map<std::pair<uint32_t, uint32_t>, std::vector<std::string>> prof_sigs_;
 };
 
-inline void finish_shape(Window& w, const IngestOptions& opt, int64_t newest, int64_t min_step, bool with_power,
+// the scrape interval when the caller does not give one: the most frequent positive gap between
+// consecutive samples (the smallest gap would let one exporter restart or 29/30/31 s jitter decide)
+struct StepVote {
+  std::unordered_map<int64_t, uint64_t> votes;
+  void add(int64_t delta) {
+    if (delta > 0) ++votes[delta];
+  }
+  int64_t result() const {
+    int64_t best = 1;
+    uint64_t n = 0;
+    for (const auto& kv : votes)
+      if (kv.second > n || (kv.second == n && kv.first < best)) best = kv.first, n = kv.second;
+    return best;
+  }
+};
+
+inline void finish_shape(Window& w, const IngestOptions& opt, int64_t newest, int64_t inferred_step, bool with_power,
                          bool allocate = true) {
   w.P = (uint32_t)w.pods.size();
   uint32_t G = 1;
   for (const PodEntry& pe : w.pods)
     G = std::max<uint32_t>(G, std::max<uint32_t>((uint32_t)pe.slots.size(), pe.power_slots));
   w.G = G;
-  w.step = opt.step > 0 ? opt.step : (min_step == std::numeric_limits<int64_t>::max() ? 1 : min_step);
+  w.step = opt.step > 0 ? opt.step : std::max<int64_t>(1, inferred_step);
   w.t_end = opt.t_end > 0 ? opt.t_end : (newest == kNoTs ? 0 : newest);
-  const int64_t span = opt.duration_min * 60;
-  w.T = (uint32_t)std::max<int64_t>(1, span / w.step);  // (t_end - N, t_end] sampled every `step`
+  w.span = std::max<int64_t>(1, opt.duration_min * 60);
+  w.T = (uint32_t)((w.span + w.step - 1) / w.step);  // every second of (t_end - N, t_end] has a bucket
   if (!allocate) return;  // device ingest: the planes live in HBM
   const size_t cells = (size_t)w.P * w.G * w.T;
   const float nan = std::numeric_limits<float>::quiet_NaN();
@@ -236,15 +249,16 @@ inline void finish_shape(Window& w, const IngestOptions& opt, int64_t newest, in
 // timestamp in whole seconds; anything that is not a sane epoch time maps to "far outside any window"
 constexpr int64_t kBadTs = std::numeric_limits<int64_t>::min() / 4;
 inline int64_t ts_seconds(double t) {
-  if (!(t > -4e12 && t < 4e12)) return kBadTs;  // also NaN
+  if (!(t > -4e12 && t < 4e12)) return kBadTs;
   return (int64_t)std::llround(t);
 }
 
-// column of timestamp ts, or -1 when it lies outside (t_end - N, t_end]
+// column of timestamp ts, or -1 when it lies outside (t_end - N, t_end].  Buckets are `step` wide and end
+// at t_end (the device parser uses the same rule, csrc/gpr_text.cuh column_of)
 inline int64_t column_of(const Window& w, int64_t ts) {
-  if (ts > w.t_end || ts < w.t_end - (int64_t)w.T * w.step - w.step) return -1;
-  const int64_t back = (w.t_end - ts + w.step / 2) / w.step;  // 0 = newest column
-  if (ts > w.t_end || back < 0 || back >= (int64_t)w.T) return -1;
+  if (ts > w.t_end || ts <= w.t_end - w.span) return -1;
+  const int64_t back = (w.t_end - ts) / w.step;  // 0 = newest column
+  if (back >= (int64_t)w.T) return -1;
   return (int64_t)w.T - 1 - back;
 }
 

@@ -120,13 +120,19 @@ std::string render_query(const Cli& a) {
   return q;
 }
 
-Selectors render_selectors(const Cli& a) {
-  const std::string d = "[" + std::to_string(a.duration) + "m]";
+static Selectors selectors_over(const Cli& a, const std::string& d) {
   Selectors s;
   s.prof = "DCGM_FI_PROF_GR_ENGINE_ACTIVE{" + matchers(a, true) + "}" + d;
   s.util = "DCGM_FI_DEV_GPU_UTIL{" + matchers(a, true) + "}" + d;
   if (power_truthy(a)) s.power = "DCGM_FI_DEV_POWER_USAGE{" + matchers(a, false) + "}" + d;
+  s.dmi = "node_dmi_info";
   return s;
+}
+
+Selectors render_selectors(const Cli& a) { return selectors_over(a, "[" + std::to_string(a.duration) + "m]"); }
+
+Selectors render_selectors(const Cli& a, int64_t seconds) {
+  return selectors_over(a, "[" + std::to_string(seconds) + "s]");
 }
 
 }  // namespace gph

@@ -21,7 +21,11 @@ struct Selectors {
   std::string prof;   // DCGM_FI_PROF_GR_ENGINE_ACTIVE{...}[Nm]   (query.promql.j2:10-14)
   std::string util;   // DCGM_FI_DEV_GPU_UTIL{...}[Nm]            (query.promql.j2:16-20)
   std::string power;  // DCGM_FI_DEV_POWER_USAGE{...}[Nm] or ""   (query.promql.j2:39-42)
+  std::string dmi;    // node_dmi_info, an instant query             (query.promql.j2:25-30)
 };
+// the same selectors over the last `seconds` only (daemon mode: a tick asks for what was scraped since
+// the previous one; the 30-minute window itself stays resident in HBM)
+Selectors render_selectors(const Cli& args, int64_t seconds);
 Selectors render_selectors(const Cli& args);
 
 struct LabelNames {  // query.promql.j2:5-7

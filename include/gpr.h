@@ -49,7 +49,7 @@ extern "C" {
 #endif
 
 #define GPR_VERSION_MAJOR 0
-#define GPR_VERSION_MINOR 1
+#define GPR_VERSION_MINOR 2
 #define GPR_VERSION_PATCH 0
 
 /* ---- status codes ------------------------------------------------------------------- */
@@ -113,7 +113,9 @@ typedef struct gpr_config {
 /*
  * One window = the range-vector result laid out densely.
  *
- *   n_gpus          series slots per pod, 1..32 (a pod cannot span nodes; GPR_E_UNSUPPORTED above).
+ *   n_gpus          series slots per pod, 1..32 (GPR_E_UNSUPPORTED above; the host ingest splits larger pods).
+ *   capacity        for HOST windows only the number of cells counts: n_pods * n_gpus * n_samples must not
+ *                   exceed max_pods * max_gpus * max_samples of gpr_create (staging is dense).
  *   util[p][g][t]   f32, t fastest; NaN = "no sample" (stale / absent / scrape gap); or biased
  *                   bytes when util_format = GPR_FMT_U8B (cast the pointer).
  *                   Restates DCGM_FI_DEV_GPU_UTIL{pod != ""}[Nm]   (query.promql.j2:16-20)
@@ -157,7 +159,11 @@ typedef struct gpr_window {
  *   series_max      optional, n_pods * n_gpus f32: window max per series, NaN if no sample
  *                   (the reference's reported `value` is this / 100; lib.rs:184,
  *                   query.promql.j2:20).
- *   out_mem_kind    where the three buffers above live.
+ *   veto_bits       optional, ceil(n_pods/32) words, THIS rank's pods only (never exchanged): pods with a
+ *                   power series at or above the threshold (the `unless on (pod, namespace)` clause,
+ *                   query.promql.j2:36-44).  With series_max it lets a caller re-derive a pod's verdict
+ *                   (exact `sum by` of duplicate series, gpu-pruner_b200/host/ingest.cpp).
+ *   out_mem_kind    where the buffers above live.
  *   n_series        number of idle series in non-vetoed pods = QueryResponse.num_pods
  *                   (main.rs:418; a series count despite the name).
  *   n_candidates / n_decisions   popcounts of the two bitmaps (this rank's pods).
@@ -170,6 +176,7 @@ typedef struct gpr_result {
   uint32_t *decision_bits;
   uint32_t *candidate_bits;
   float *series_max;
+  uint32_t *veto_bits;
   uint64_t n_series;
   uint64_t n_candidates;
   uint64_t n_decisions;
@@ -203,6 +210,11 @@ GPR_API int gpr_resident_init(gpr_ctx *ctx, uint32_t n_pods, uint32_t n_gpus, ui
 /* new columns laid out [p][g][n_new] (row_stride 0 = n_new); power_cols may be NULL.      */
 GPR_API int gpr_append(gpr_ctx *ctx, const float *util_cols, const float *power_cols, uint32_t n_new,
                uint64_t row_stride, int32_t mem_kind);
+/* Open the next n_new buckets of the ring without data: their columns become "no sample" in every row of
+ * every resident plane and the ring head moves on.  The tick's samples are then merged in by
+ * gpr_text_parse(GPR_TEXT_RESIDENT) (device-side ingest of the tick's range-query slice).  With
+ * GPR_F_BLOCK_INDEX call gpr_resident_reindex after the parse.                                      */
+GPR_API int gpr_resident_advance(gpr_ctx *ctx, uint32_t n_new);
 /* rebuild the GPR_F_BLOCK_INDEX index after writing the resident planes directly
  * (gpr_resident_planes); a no-op without an index                                          */
 GPR_API int gpr_resident_reindex(gpr_ctx *ctx);
@@ -288,12 +300,20 @@ GPR_API int gpr_synth_eligible(gpr_ctx *ctx, uint64_t seed, uint8_t *dst, uint64
  *   the caller       parses the label maps (~1 % of the bytes) and assigns every series its tensor
  *                    row — label precedence of lib.rs:153-187, `sum by` groups of query.promql.j2:9
  *                    (gpu-pruner_b200/host/ingest_device.cpp does this);
- *   gpr_text_parse   parses all samples of the given spans into a context-owned plane
- *                    [n_rows][n_samples] f32 (NaN = no sample), column = (t_end - ts) / step.
- * The device parser is strict: anything but `[digits[.digits],"<short decimal>|NaN|+Inf|-Inf"]`,
- * two samples of one series in one column, or time running backwards sets GPR_SPAN_HARD on the span;
+ *   gpr_text_parse   parses all samples of the given spans into a plane [n_rows][n_samples] f32
+ *                    (0xFFFFFFFF, a NaN = no sample) — a context-owned plane, or the resident ring of
+ *                    daemon mode.
+ * Where a sample goes (the same rule as the CPU ingest, gpu-pruner_b200/host/ingest_internal.hpp):
+ *   inside the window iff  t_end - window_seconds < ts <= t_end      (PromQL [Nm] at t_end, left-open)
+ *   bucket back = (t_end - ts) / step  (0 = newest), column n_samples - 1 - back; several samples of a
+ *   row in one bucket are merged with a NaN-aware max — which is what max_over_time over the row
+ *   (query.promql.j2:10,16) computes anyway, so collisions, sample order and duplicate series need no
+ *   special handling.
+ * Numbers are converted exactly like strtod + (float): Clinger's fast path or Eisel-Lemire (17-digit
+ * DCGM_FI_PROF_GR_ENGINE_ACTIVE ratios included).  The device parser is strict: anything but
+ * `[digits[.digits],"<decimal, at most 19 significant digits>|NaN|+Inf|-Inf"]` sets GPR_SPAN_HARD on the span;
  * the caller re-parses the rows of hard spans on the CPU and overwrites them with gpr_memcpy, so the
- * tensor is bit-identical to a CPU ingest for every input.
+ * tensor equals a CPU ingest for every input.
  */
 typedef struct gpr_text_span {
   uint64_t begin;    /* offset of the first byte after `"values":[` (a '[')                    */
@@ -301,30 +321,43 @@ typedef struct gpr_text_span {
   uint32_t row;      /* destination row = pod * n_gpus + slot                                  */
   uint32_t flags;    /* GPR_SPAN_SHARED in; GPR_SPAN_HARD out                                  */
   uint32_t n_in;     /* out: samples parsed                                                    */
-  uint32_t n_oow;    /* out: samples outside (t_end - n_samples*step, t_end]                   */
+  uint32_t n_oow;    /* out: samples outside the window                                        */
   uint32_t n_tiny;   /* out: non-zero values below the f32 denormal range, kept non-zero       */
   uint32_t reserved;
 } gpr_text_span;
-#define GPR_SPAN_SHARED 1u /* several series feed this row: merge (NaN-aware max), do not store  */
+#define GPR_SPAN_SHARED 1u /* several series feed this row (informational; every merge is atomic)   */
 #define GPR_SPAN_HARD 2u   /* the device parser gave up on this span: re-parse its row on the CPU */
-#define GPR_TEXT_FILL 1u   /* gpr_text_parse: fill the plane with NaN first                      */
+
+typedef struct gpr_text_grid {
+  uint32_t struct_size;
+  uint32_t flags;          /* GPR_TEXT_*                                                            */
+  int64_t t_end;           /* newest second of the window (inclusive)                               */
+  int64_t window_seconds;  /* samples with t_end - window_seconds < ts <= t_end are inside          */
+  int64_t step;            /* seconds per column, > 0                                               */
+  uint32_t n_samples;      /* columns; >= ceil(window_seconds / step)                               */
+  uint32_t n_rows;
+} gpr_text_grid;
+#define GPR_TEXT_FILL 1u     /* fill the destination plane with "no sample" first (context planes)    */
+#define GPR_TEXT_RESIDENT 2u /* destination = the resident ring (gpr_resident_init): n_samples must be its
+                                n_samples, n_rows <= its rows; the newest bucket is the ring's newest
+                                column (call gpr_resident_advance first to open the tick's buckets)  */
 
 /* Copy `n_bytes` of response text to the device (pinned host memory from gpr_host_alloc moves at
- * full PCIe speed) and scan it.  Up to `cap` offsets are written to each of opens[] (position of the
- * '}' of `},"values":[`) and closes[] (position of the '"' of `"]]`), UNSORTED; the true counts are
- * returned in *n_opens / *n_closes (GPR_E_CAPACITY if either exceeds cap).  The text stays resident
- * in the context's slot `slot` (0..2: a tick has up to three responses — PROF, UTIL, POWER) for
- * gpr_text_parse until the next gpr_text_scan of that slot.  Blocking.                           */
+ * full PCIe speed; ordinary memory is staged through a pinned ring by a few host threads, and every
+ * chunk is scanned as it lands) and scan it.  Up to `cap` offsets are written to each of opens[]
+ * (position of the '}' of `},"values":[`) and closes[] (position of the '"' of `"]]`), UNSORTED; the
+ * true counts are returned in *n_opens / *n_closes (GPR_E_CAPACITY if either exceeds cap).  The text
+ * stays resident in the context's slot `slot` (0..2: a tick has up to three responses — PROF, UTIL,
+ * POWER) for gpr_text_parse until the next gpr_text_scan of that slot.  Blocking.                   */
 GPR_API int gpr_text_scan(gpr_ctx *ctx, int32_t slot, const char *text, uint64_t n_bytes,
                           int32_t mem_kind, uint64_t *opens, uint64_t *closes, uint64_t cap,
                           uint64_t *n_opens, uint64_t *n_closes);
 /* Parse the samples of spans[0..n_spans) (host array, sorted by begin, non-overlapping) of the text in
  * `slot` into plane `plane` (0 = util, 1 = power).  Out-fields of the spans are filled.  Blocking.  */
 GPR_API int gpr_text_parse(gpr_ctx *ctx, int32_t slot, gpr_text_span *spans, uint32_t n_spans,
-                           int64_t t_end, int64_t step, uint32_t n_samples, uint32_t n_rows,
-                           int32_t plane, uint32_t flags);
-/* Device pointers of the planes (NULL if never parsed); valid until the next gpr_text_parse that has
- * to grow them, or gpr_destroy.  Hand them to gpr_decide with mem_kind = GPR_MEM_DEVICE.           */
+                           const gpr_text_grid *grid, int32_t plane);
+/* Device pointers of the context planes (NULL if never parsed); valid until the next gpr_text_parse
+ * that has to grow them, or gpr_destroy.  Hand them to gpr_decide with mem_kind = GPR_MEM_DEVICE.   */
 GPR_API int gpr_text_planes(gpr_ctx *ctx, float **util, float **power);
 
 #ifdef __cplusplus

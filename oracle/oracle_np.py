@@ -87,6 +87,8 @@ def decide(util, power=None, eligible=None, created_ts=None, cutoff_ts=0, power_
         "decision_bits": pack_bits(decision),
         "candidate_bits": pack_bits(candidate),
         "series_max": smax.astype(np.float32),
+        "veto": veto,
+        "veto_bits": pack_bits(veto),
         "n_series": n_series,
         "n_candidates": int(candidate.sum()),
         "n_decisions": int(decision.sum()),

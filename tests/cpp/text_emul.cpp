@@ -1,12 +1,13 @@
 // TEST INFRASTRUCTURE.  Runs the device ingest (gpu-pruner_b200/host/ingest_device.cpp) on an EMULATED
 // device: the very functions the CUDA kernels call (gpu-pruner_b200/csrc/gpr_text.cuh, GPR_HD) executed
-// slice by slice on the CPU, with a sink that also checks the "every cell of a stored row is written at
-// most once" property the plain device stores rely on.  Each case directory (util.json [prof.json]
+// tile by tile, candidate by candidate on the CPU, seeing exactly the bytes a warp's shared-memory stage
+// holds (tile + halo).  Each case directory (util.json [prof.json]
 // [power.json]) is ingested by the CPU text path and by the emulated device path; shape, pods,
 // statistics and every tensor cell must agree, or both must reject the input.
 //
 //   text_emul <t_end> <step> <duration_min> <case_dir>...
 // prints per case:  OK device=<0|1> spans=.. hard=.. patched=.. [reason]  |  REJECT  |  MISMATCH <what>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -43,56 +44,61 @@ class EmulDevice : public TextDevice {
     for (uint64_t s = slices; s-- > 0;) tx::scan_slice(t.data(), (uint64_t)n, s, sink);
   }
 
-  void parse(int slot, std::vector<gpr_text_span>& spans, int64_t t_end, int64_t step, uint32_t T,
-             uint32_t n_rows, int plane, bool fill) override {
-    std::vector<float>& pl = plane_[plane];
-    if (fill) pl.assign((size_t)n_rows * T, tx::quiet_nan_f32());
-    if (pl.size() != (size_t)n_rows * T) throw std::logic_error("emul: plane shape changed without fill");
-    std::vector<uint8_t> stores(pl.size(), 0);
+  void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) override {
+    if (grid.resident) throw std::logic_error("emul: no resident ring");
+    std::vector<uint32_t>& pl = plane_[plane];
+    const uint32_t T = grid.T;
+    if (grid.fill) pl.assign((size_t)grid.n_rows * T, tx::kFillBits);
+    if (pl.size() != (size_t)grid.n_rows * T) throw std::logic_error("emul: plane shape changed without fill");
     struct Sink {
-      std::vector<float>& pl;
-      std::vector<uint8_t>& stores;
+      std::vector<uint32_t>& pl;
       tx::Span* sp;
-      uint32_t T;
-      void store(uint32_t row, uint32_t col, float v) {
-        pl[(size_t)row * T + col] = v;
-        if (stores[(size_t)row * T + col] < 255) ++stores[(size_t)row * T + col];
-      }
-      void merge(uint32_t row, uint32_t col, float v) {
-        float& c = pl[(size_t)row * T + col];
-        c = std::isnan(c) ? v : (std::isnan(v) ? c : (c < v ? v : c));
-      }
+      void put(uint64_t cell, float v) { tx::merge_cell_bits(&pl[cell], v); }
       void hard(uint32_t s) { sp[s].flags |= tx::kSpanHard; }
       void count(uint32_t s, uint32_t a, uint32_t b, uint32_t c) {
         sp[s].n_in += a, sp[s].n_oow += b, sp[s].n_tiny += c;
       }
-    } sink{pl, stores, reinterpret_cast<tx::Span*>(spans.data()), T};
-    const tx::Grid g{t_end, step, T, 0};
-    const uint8_t* t = text_[slot].data();
+    } sink{pl, reinterpret_cast<tx::Span*>(spans.data())};
+    tx::Grid g;
+    memset(&g, 0, sizeof g);
+    g.t_end = grid.t_end, g.t_lo = grid.t_end - grid.span, g.step = (uint32_t)grid.step, g.T = T;
+    g.col_end = T - 1, g.ld = T;
+    const std::vector<uint8_t>& text = text_[slot];
     const uint64_t n = n_[slot];
     const tx::Span* sp = reinterpret_cast<const tx::Span*>(spans.data());
-    const uint64_t slices = (n + tx::kParseBytes - 1) / tx::kParseBytes;
-    for (uint64_t s = slices; s-- > 0;) {
-      const uint32_t hint = tx::find_span(sp, (uint32_t)spans.size(), s * tx::kParseBytes);
-      tx::parse_slice(t, n, sp, (uint32_t)spans.size(), hint, s, g, sink);
+    const uint64_t tiles = (n + tx::kTileBytes - 1) / tx::kTileBytes;
+    // what a warp sees: one tile plus the halo, nothing else (bytes beyond are poisoned); tiles in reverse
+    // order and candidates from the back: nothing may depend on the order things run in
+    struct Tile {
+      const uint8_t* p;
+      uint32_t operator[](uint32_t i) const { return p[i]; }
+    };
+    std::vector<uint8_t> stage(tx::kTileBytes + tx::kTileHalo + 64);
+    for (uint64_t k = tiles; k-- > 0;) {
+      const uint64_t off = k * tx::kTileBytes;
+      const uint64_t have = std::min<uint64_t>(tx::kTileBytes + tx::kTileHalo, (n + tx::kTextPad - off) & ~15ull);
+      memset(stage.data(), 0xEE, stage.size());
+      memcpy(stage.data(), text.data() + off, have);
+      const uint32_t tile_n = (uint32_t)std::min<uint64_t>(tx::kTileBytes, n - off);
+      const uint32_t s0 = tx::find_span(sp, (uint32_t)spans.size(), off);
+      const Tile tile{stage.data()};
+      for (uint32_t o = tile_n; o-- > 0;) {
+        if (stage[o] != '[') continue;
+        uint32_t s = s0;
+        tx::parse_candidate(tile, off, o, sp, (uint32_t)spans.size(), s, g, sink);
+      }
     }
-    // a cell stored twice by spans the device did not give up on would be a data race on the GPU
-    std::vector<uint8_t> row_hard(n_rows, 0);
-    for (const gpr_text_span& s : spans)
-      if (s.flags & GPR_SPAN_HARD) row_hard[s.row] = 1;
-    for (size_t i = 0; i < stores.size(); ++i)
-      if (stores[i] > 1 && !row_hard[i / T]) throw std::logic_error("emul: cell stored twice in a row not marked hard");
   }
 
   void patch_row(int plane, uint32_t row, uint32_t T, const float* data) override {
     memcpy(plane_[plane].data() + (size_t)row * T, data, (size_t)T * sizeof(float));
   }
-  const float* plane(int plane) override { return plane_[plane].data(); }
+  const float* plane(int plane) override { return reinterpret_cast<const float*>(plane_[plane].data()); }
 
  private:
   std::vector<uint8_t> text_[3];
   uint64_t n_[3] = {0, 0, 0};
-  std::vector<float> plane_[2];
+  std::vector<uint32_t> plane_[2];   // f32 bit patterns (cells start as 0xFFFFFFFF, like the device planes)
 };
 
 bool slurp(const std::string& path, std::string* out) {
@@ -107,7 +113,7 @@ bool same_plane(const float* a, const float* b, size_t n, bool bits, size_t* whe
   for (size_t i = 0; i < n; ++i) {
     const bool na = std::isnan(a[i]), nb = std::isnan(b[i]);
     bool ok = na == nb && (na || a[i] == b[i]);
-    if (ok && bits && !na) ok = memcmp(a + i, b + i, 4) == 0;
+    if (ok && bits && !na && a[i] != 0.0f) ok = memcmp(a + i, b + i, 4) == 0;  // the sign of a zero may differ after a merge
     if (!ok) {
       *where = i;
       return false;
@@ -192,9 +198,7 @@ int main(int argc, char** argv) {
       const float* du = rep.on_device ? wd.d_util : wd.util.data();
       const float* dp = rep.on_device ? wd.d_power : (wd.power.empty() ? nullptr : wd.power.data());
       size_t at = 0;
-      // rows merged from several series may differ in the sign of a zero (max is order-independent
-      // up to that); everything else is bit-exact
-      const bool bits = sa.duplicates_merged == 0;
+      const bool bits = true;
       if (cells && !same_plane(wc.util.data(), du, cells, bits, &at)) what = "util cell " + std::to_string(at);
       if (what.empty() && !wc.power.empty() && (!dp || !same_plane(wc.power.data(), dp, cells, bits, &at)))
         what = "power cell " + std::to_string(at);

@@ -106,6 +106,38 @@ def ingest_mode(threads):
     lib().gph_ingest_mode(threads)
 
 
+def ingest_dmi(dmi):
+    """response of the node_dmi_info query applied by the following ingest() calls (None = none)"""
+    lib().gph_ingest_dmi(None if dmi is None else json.dumps(dmi).encode())
+
+
+def resolve_groups(series_max, candidate_bits, decision_bits, counts, veto_bits=None, eligible=None, created_ts=None,
+                   cutoff=0):
+    """exact `sum by` on the window of the last ingest(): returns corrected (candidate_bits, decision_bits, counts, changed)"""
+    import numpy as np
+    sm = np.ascontiguousarray(series_max, dtype=np.float32)
+    cb = np.array(candidate_bits, dtype=np.uint32)
+    db = np.array(decision_bits, dtype=np.uint32)
+    cn = np.array(counts, dtype=np.uint64)
+    p = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt).ctypes.data_as(C.c_void_p)
+    vb, el, cr = (None if veto_bits is None else np.ascontiguousarray(veto_bits, dtype=np.uint32),
+                  None if eligible is None else np.ascontiguousarray(eligible, dtype=np.uint8),
+                  None if created_ts is None else np.ascontiguousarray(created_ts, dtype=np.int64))
+    rc = lib().gph_resolve_groups(sm.ctypes.data_as(C.c_void_p), p(vb, np.uint32), p(el, np.uint8), p(cr, np.int64),
+                                  C.c_longlong(int(cutoff)), cb.ctypes.data_as(C.c_void_p), db.ctypes.data_as(C.c_void_p),
+                                  cn.ctypes.data_as(C.c_void_p))
+    assert rc >= 0
+    return cb, db, tuple(int(x) for x in cn), rc
+
+
+def group_values(series_max):
+    import numpy as np
+    sm = np.ascontiguousarray(series_max, dtype=np.float32)
+    out = np.zeros(sm.shape, np.float64)
+    assert lib().gph_group_values(sm.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+    return out
+
+
 def ingest(util, prof=None, power=None, duration_min=30, step=0, t_end=0):
     import numpy as np
     dims = (C.c_uint * 3)()

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"libgpr.so does not export {s}"
         assert s in ffi.PROTOTYPES, f"ffi.py has no prototype for {s}"
     assert set(ffi.PROTOTYPES) == set(_declared_symbols())
-    assert lib.gpr_version() == 100
+    assert lib.gpr_version() == 200
 
 
 def test_struct_layout_matches_a_c_compiler(tmp_path):

@@ -376,9 +376,15 @@ def test_block_index_rebuild_after_direct_writes(T, engines, oracle_c):
 def test_error_paths(engines):
     import gpu_pruner_b200 as g
     eng = engines["ldg"]
-    with pytest.raises(g.GprError) as ei:          # over capacity
-        eng.decide(np.zeros((12001, 1, 8), np.float32))
+    with pytest.raises(g.GprError) as ei:          # over capacity: more cells than the staging planes hold
+        eng.decide(np.zeros((12001, 8, 2048), np.float32))
     assert ei.value.code == g.ffi.GPR_E_CAPACITY
+    # only the number of cells counts (staging is dense): more pods / samples than the shape given at create
+    # is fine as long as the product fits (a window that grows by one GPU slot must not fail)
+    d = eng.decide(np.zeros((12001, 1, 8), np.float32))
+    assert d.n_decisions == 12001
+    d = eng.decide(np.zeros((3, 9, 2052), np.float32))
+    assert d.n_decisions == 3
     torch.cuda.synchronize()
     with pytest.raises(g.GprError) as ei:          # missing required output
         eng.decide_ptr(torch.zeros(8, device="cuda:0"), 1, 1, 8, None)

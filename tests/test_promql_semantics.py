@@ -119,12 +119,21 @@ def test_dense_path_equals_promql_semantics(seed, oracle_np, oracle_c):
     finally:
         H.ingest_mode(-1)
     names = [(p["name"], p["namespace"]) for p in meta["pods"]]
+    veto_bits = oracle_np.decide(u, w, power_threshold=thr)["veto_bits"]
     for orc in (oracle_np, oracle_c):
-        r = orc.decide(u, w, power_threshold=thr)
-        cand = oracle_np.unpack_bits(r["candidate_bits"], len(names))
+        r = orc.decide(u, w, power_threshold=thr)      # every tensor ROW an element: what the kernels compute
+        # duplicate series of a `sum by` group: element = sum of the members' maxima (host-side, ingest.cpp)
+        cb, db, counts, _ = H.resolve_groups(r["series_max"], r["candidate_bits"], r["decision_bits"],
+                                             (r["n_series"], r["n_candidates"], r["n_decisions"]), veto_bits=veto_bits)
+        cand = oracle_np.unpack_bits(cb, len(names))
         pods_b = {names[i] for i in np.flatnonzero(cand)}
         assert pods_b == set(pods_a), (seed, sorted(pods_b ^ set(pods_a)))
-        assert r["n_series"] == n_series
+        assert counts[0] == n_series
+        # the value PodMetricData would carry (lib.rs:184): 0 for every element that survived `== 0`, and the
+        # same elements as the PromQL-style evaluation (one per idle group of a surviving pod)
+        vals = H.group_values(r["series_max"])
+        idle_groups = sum(int((vals[i] == 0.0).sum()) for i in np.flatnonzero(cand))
+        assert idle_groups == n_series and all(v == 0.0 for v in vec.values())
 
 
 def test_duplicate_dmi_series_is_a_query_error():
