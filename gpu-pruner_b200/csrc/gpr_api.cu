@@ -1085,6 +1085,13 @@ int gpr_resident_planes(gpr_ctx* ctx, float** util, float** power, uint64_t* row
   return GPR_OK;
 }
 
+int gpr_resident_head(gpr_ctx* ctx, uint32_t* head) {
+  if (!ctx || !head) return GPR_E_INVALID;
+  if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window");
+  *head = ctx->res_head;
+  return GPR_OK;
+}
+
 int gpr_resident_advance(gpr_ctx* ctx, uint32_t n_new) {
   if (!ctx) return GPR_E_INVALID;
   GPR_TRY
@@ -1461,8 +1468,9 @@ int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_
   if (!ctx->d_text[slot]) return fail(ctx, GPR_E_STATE, "no text in slot %d (gpr_text_scan)", slot);
   if (n_spans && !spans) return fail(ctx, GPR_E_INVALID, "spans is NULL");
   const uint32_t n_samples = grid->n_samples, n_rows = grid->n_rows;
-  if (grid->step <= 0 || grid->step > 0xffffffffll || n_samples == 0 || grid->window_seconds <= 0)
-    return fail(ctx, GPR_E_INVALID, "step, window_seconds and n_samples must be > 0");
+  if (grid->step <= 0 || grid->step > 4000000ll || n_samples == 0 || grid->window_seconds <= 0 ||
+      grid->window_seconds > 4000000000ll)
+    return fail(ctx, GPR_E_INVALID, "step (<= 4e6 s), window_seconds and n_samples must be > 0");
   if ((grid->window_seconds + grid->step - 1) / grid->step > (int64_t)n_samples)
     return fail(ctx, GPR_E_INVALID, "window of %lld s needs more than %u columns of %lld s", (long long)grid->window_seconds,
                 n_samples, (long long)grid->step);
@@ -1480,8 +1488,9 @@ int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_
   float* pl = nullptr;
   gpr::text::Grid g;
   memset(&g, 0, sizeof g);
-  g.t_end = grid->t_end, g.t_lo = grid->t_end - grid->window_seconds;
-  g.step = (uint32_t)grid->step, g.T = n_samples;
+  // the device works in milliseconds, the resolution of Prometheus timestamps
+  g.t_end = grid->t_end * 1000, g.t_lo = (grid->t_end - grid->window_seconds) * 1000;
+  g.step = (uint32_t)(grid->step * 1000), g.T = n_samples;
   if (resident) {
     if (!ctx->d_res_util) return fail(ctx, GPR_E_STATE, "no resident window (gpr_resident_init)");
     if (n_samples != ctx->res_T || (uint64_t)n_rows > (uint64_t)ctx->res_P * ctx->res_G)

@@ -69,17 +69,18 @@ struct Span {        // mirrors gpr_text_span (include/gpr.h)
   uint32_t reserved;
 };
 
-// Time axis of the destination (gpu-pruner_b200/host/ingest_internal.hpp column_of is the same rule).
+// Time axis of the destination (gpu-pruner_b200/host/ingest_internal.hpp column_of is the same rule), in
+// MILLISECONDS — the resolution of Prometheus timestamps, so membership and bucketing are exact.
 // A sample is inside the window iff t_lo < ts <= t_end  (PromQL's [Nm] selector evaluated at t_end,
-// left-open as in Prometheus 3.x).  Buckets are `step` seconds wide and end at t_end:
+// left-open as in Prometheus 3.x).  Buckets are `step` wide and end at t_end:
 //     back = (t_end - ts) / step            0 = newest bucket
 //     col  = (col_end - back) mod T
 // A dense window has col_end = T - 1 (column c = bucket T-1-c); the resident ring of daemon mode passes
 // the ring position of its newest bucket.
 struct Grid {
-  int64_t t_end;     // newest second (inclusive)
-  int64_t t_lo;      // t_end - window seconds (exclusive)
-  uint32_t step;     // seconds per column, > 0
+  int64_t t_end;     // newest millisecond (inclusive)
+  int64_t t_lo;      // t_end - window (exclusive)
+  uint32_t step;     // milliseconds per column, > 0
   uint32_t T;        // columns of the plane
   uint32_t col_end;  // column of the newest bucket
   uint32_t pad;
@@ -91,7 +92,7 @@ constexpr int64_t kBadTs = INT64_MIN / 4;  // timestamp that is no sane epoch ti
 GPR_HD int64_t column_of(const Grid& g, int64_t ts) {
   if (ts > g.t_end || ts <= g.t_lo) return -1;
   const uint64_t d = (uint64_t)(g.t_end - ts);
-  const uint64_t back = g.step == 1u ? d : (d <= 0xffffffffull ? (uint64_t)((uint32_t)d / g.step) : d / g.step);
+  const uint64_t back = d <= 0xffffffffull ? (uint64_t)((uint32_t)d / g.step) : d / g.step;
   if (back >= g.T) return -1;
   return back <= g.col_end ? (int64_t)(g.col_end - back) : (int64_t)(g.col_end + g.T - back);
 }
@@ -220,8 +221,8 @@ constexpr uint32_t kFillBits = 0xFFFFFFFFu;  // "no sample": a NaN that is -1 as
 // `Src` is anything with `uint8_t operator[](uint32_t) const` (shared-memory tile on the device, a plain
 // buffer in the emulation).  Offsets are relative to the tile; nothing at or beyond p + kMaxSample is read.
 //
-// [-+]digits[.digits] at t[p...] -> *v (value digits only: Prometheus formats sample values with
-// strconv 'f', no exponent; an exponent, like anything else unusual, makes the span hard).
+// [-+]digits[.digits][(e|E)[-+]digits] at t[p...] -> *v.  Prometheus prints sample values with strconv 'f' and
+// switches to 'e' below 1e-6 and from 1e21 on (util/jsonutil MarshalFloat), so both forms occur.
 // Returns the offset after the number, 0 = not convertible here.
 template <typename Src>
 GPR_HD uint32_t parse_value(const Src& t, uint32_t p, uint32_t limit, float* val, uint32_t* tiny) {
@@ -250,17 +251,32 @@ GPR_HD uint32_t parse_value(const Src& t, uint32_t p, uint32_t limit, float* val
     }
   }
   if (!any || p >= limit) return 0;
+  int e10 = -frac;
+  bool has_exp = false;
+  if (c == 'e' || c == 'E') {
+    has_exp = true;
+    c = t[++p];
+    bool eneg = false;
+    if (c == '-' || c == '+') eneg = c == '-', c = t[++p];
+    int ex = 0, nd = 0;
+    for (; c - '0' < 10u && nd < 4; c = t[++p], ++nd) ex = ex * 10 + (int)(c - '0');
+    if (nd == 0 || nd > 3) return 0;
+    e10 += eneg ? -ex : ex;
+  }
   float f;
   if (m == 0) {
     f = 0.0f;
-  } else if (!dot && m < (1ull << 24)) {
+  } else if (!dot && !has_exp && m < (1ull << 24)) {
     f = (float)(uint32_t)m;  // every DCGM_FI_DEV_GPU_UTIL / POWER_USAGE integer: exact
   } else {
     double d;
-    if (m <= (1ull << 53) && frac <= 22) {
-      d = (double)m;  // exact; one IEEE division: correctly rounded (Clinger)
-      if (frac) d = d / pow10_exact(frac);
-    } else if (!eisel_lemire(m, -frac, &d)) {
+    if (m > (1ull << 53))  // "13098385200945040.0": trailing zeros carry no information, and without them
+      while (m % 10 == 0) m /= 10, ++e10;  // the exact path below applies (rare; 64-bit division is slow)
+    if (m <= (1ull << 53) && e10 >= -22 && e10 <= 22) {
+      d = (double)m;  // exact; one IEEE multiplication or division by an exact power of ten: correctly rounded (Clinger)
+      if (e10 < 0) d = d / pow10_exact(-e10);
+      else if (e10 > 0) d = d * pow10_exact(e10);
+    } else if (!eisel_lemire(m, e10, &d)) {
       return 0;
     }
     f = to_f32(d, tiny);
@@ -269,9 +285,9 @@ GPR_HD uint32_t parse_value(const Src& t, uint32_t p, uint32_t limit, float* val
   return p;
 }
 
-// t[p] == '['.  `[digits[.digits],` -> whole seconds, rounded half away from zero like llround(strtod())
-// (ingest.cpp ts_seconds).  At most 13 integer and 6 fractional digits: with those the integer rounding
-// below and the rounding of the correctly rounded double agree.  Returns the offset of the ','.
+// t[p] == '['.  `[digits[.digits],` -> milliseconds.  At most 13 integer and 3 fractional digits (Prometheus
+// prints timestamps with millisecond resolution; anything finer is declined and goes to the CPU parser, whose
+// llround(strtod() * 1000) this reproduces exactly for such input).  Returns the offset of the ','.
 template <typename Src>
 GPR_HD uint32_t parse_timestamp(const Src& t, uint32_t p, int64_t* ts) {
   uint64_t ip = 0;
@@ -279,17 +295,16 @@ GPR_HD uint32_t parse_timestamp(const Src& t, uint32_t p, int64_t* ts) {
   const uint32_t q0 = q;
   for (; c - '0' < 10u && q - q0 < 14; c = t[++q]) ip = ip * 10 + (c - '0');
   if (q == q0 || q - q0 > 13) return 0;
+  uint32_t ms = 0;
   if (c == '.') {
     c = t[++q];
     const uint32_t f0 = q;
-    const bool up = c >= '5' && c <= '9';
-    for (; c - '0' < 10u && q - f0 < 7; c = t[++q]) {
-    }
-    if (q == f0 || q - f0 > 6) return 0;
-    ip += up;
+    uint32_t scale = 100;
+    for (; c - '0' < 10u && q - f0 < 4; c = t[++q]) ms += (c - '0') * scale, scale /= 10;
+    if (q == f0 || q - f0 > 3) return 0;
   }
   if (c != ',') return 0;
-  *ts = ip < 4000000000000ull ? (int64_t)ip : kBadTs;
+  *ts = ip < 4000000000000ull ? (int64_t)(ip * 1000 + ms) : kBadTs;
   return q;
 }
 
@@ -392,7 +407,7 @@ GPR_HD void parse_candidate(const Src& tile, uint64_t tile_off, uint32_t o, cons
     return;
   }
   const int64_t col = column_of(g, ts);
-  sink.count(s, 1u, col < 0 ? 1u : 0u, tiny);
+  sink.count(s, 1u, col < 0 ? 1u : 0u, col < 0 ? 0u : tiny);  // clamped values are counted where they are stored
   if (col >= 0) sink.put((uint64_t)spans[s].row * g.ld + (uint64_t)col, v);
 }
 

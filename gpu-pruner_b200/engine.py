@@ -388,6 +388,11 @@ class IdleEngine:
         self._check(self._lib.gpr_text_parse(self._h, slot, _ptr(spans), len(spans), C.byref(g), plane))
         return spans
 
+    def resident_head(self) -> int:
+        h = C.c_uint32()
+        self._check(self._lib.gpr_resident_head(self._h, C.byref(h)))
+        return h.value
+
     def resident_advance(self, n_new: int):
         """open the next ``n_new`` buckets of the resident ring without data (all rows: no sample)"""
         self._check(self._lib.gpr_resident_advance(self._h, int(n_new)))

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "gpr_append": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_int32]),
     "gpr_resident_reindex": (C.c_int, [_P]),
     "gpr_resident_advance": (C.c_int, [_P, C.c_uint32]),
+    "gpr_resident_head": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "gpr_decide_resident": (C.c_int, [_P, C.POINTER(gpr_window), C.POINTER(gpr_result)]),
     "gpr_resident_planes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gpr_comm_unique_id": (C.c_int, [_P]),

@@ -53,13 +53,47 @@ bool file_exists(const std::string& p) {
   return stat(p.c_str(), &st) == 0;
 }
 
-// file://DIR with util.json [prof.json] [power.json] [query.json = {"end": ts, "step": s}]
+// file://DIR — recorded range-query responses instead of a Prometheus server:
+//   DIR/util.json [prof.json] [power.json] [dmi.json] [query.json = {"end": ts, "step": s}]     every tick the same
+//   DIR/tick-0000/..., DIR/tick-0001/...                                                       one directory per tick,
+//     each either with the files above, or with full/ (the whole [Nm] range) and delta/ (only what was scraped
+//     since the previous tick: query.json = {"end", "step", "start"}, samples in (start, end]) — the two answers a
+//     server would give to the two questions daemon mode can ask.
 class FileSource : public WindowSource {
  public:
   FileSource(std::string dir, TextIngestor* ingestor, const Logger* log)
       : dir_(std::move(dir)), ingestor_(ingestor), log_(log) {}
   Window fetch(const Cli& args) override {
-    const std::string up = dir_ + "/util.json";
+    std::string base = dir_;
+    if (file_exists(dir_ + "/tick-0000")) {
+      char name[32];
+      snprintf(name, sizeof name, "/tick-%04d", tick_++);
+      base = dir_ + name;
+      if (!file_exists(base)) throw std::runtime_error("Failed to run query! " + base + " not found (no more recorded ticks)");
+    }
+    const bool can_reside = args.daemon_mode && ingestor_ != nullptr;
+    // daemon mode with a resident window: ask only for what was scraped since the previous tick
+    const int64_t since = can_reside ? ingestor_->resident_t_end() : 0;
+    if (since > 0 && file_exists(base + "/delta/util.json") && file_exists(base + "/delta/query.json")) {
+      const Json meta = Json::parse_file(base + "/delta/query.json");
+      const int64_t start = (int64_t)meta["start"].as_number(0), end = (int64_t)meta["end"].as_number(0);
+      if (start == since && end > start) {
+        try {
+          return load(args, base + "/delta", end - start, true);
+        } catch (const NeedFullWindow& e) {
+          if (log_) log_->info(std::string("Resident window rebuilt from the full range: ") + e.what());
+        }
+      } else if (log_) {
+        log_->info("Recorded delta does not continue the resident window (starts at " + std::to_string(start) +
+                   ", resident up to " + std::to_string(since) + "): using the full range");
+      }
+    }
+    return load(args, file_exists(base + "/full/util.json") ? base + "/full" : base, 0, can_reside);
+  }
+
+ private:
+  Window load(const Cli& args, const std::string& d, int64_t slice_seconds, bool resident) {
+    const std::string up = d + "/util.json";
     if (!file_exists(up)) throw std::runtime_error("Failed to run query! " + up + " not found");
     auto slurp = [](const std::string& path) {
       std::ifstream f(path, std::ios::binary);
@@ -70,27 +104,35 @@ class FileSource : public WindowSource {
     const std::string util = slurp(up);
     std::string prof, power;
     const std::string *pprof = nullptr, *ppower = nullptr;
-    if (file_exists(dir_ + "/prof.json")) prof = slurp(dir_ + "/prof.json"), pprof = &prof;
+    if (file_exists(d + "/prof.json")) prof = slurp(d + "/prof.json"), pprof = &prof;
     const bool want_power = args.power_threshold && *args.power_threshold != 0.0;
-    if (want_power && file_exists(dir_ + "/power.json")) power = slurp(dir_ + "/power.json"), ppower = &power;
+    if (want_power && file_exists(d + "/power.json")) power = slurp(d + "/power.json"), ppower = &power;
     IngestOptions opt;
     opt.duration_min = args.duration;
-    if (file_exists(dir_ + "/query.json")) {
-      const Json meta = Json::parse_file(dir_ + "/query.json");
+    if (file_exists(d + "/query.json")) {
+      const Json meta = Json::parse_file(d + "/query.json");
       opt.t_end = (int64_t)meta["end"].as_number(0);
       opt.step = (int64_t)meta["step"].as_number(0);
     }
-    if (!ingestor_) return ingest_matrix_text(util, pprof, ppower, opt);
-    std::string note;
-    Window w = ingestor_->ingest(args, util, pprof, ppower, opt, &note);
-    if (log_ && !note.empty()) log_->info(note);
+    opt.slice_seconds = slice_seconds;
+    opt.resident = resident;
+    Window w;
+    if (!ingestor_) {
+      w = ingest_matrix_text(util, pprof, ppower, opt);
+    } else {
+      std::string note;
+      w = ingestor_->ingest(args, util, pprof, ppower, opt, &note);
+      if (log_ && !note.empty()) log_->info(note);
+    }
+    // node_type for the rows of PodMetricData: the node_dmi_info join of query.promql.j2:23-34
+    if (file_exists(d + "/dmi.json")) apply_node_types(w, Json::parse_file(d + "/dmi.json"));
     return w;
   }
 
- private:
   std::string dir_;
   TextIngestor* ingestor_;
   const Logger* log_;
+  int tick_ = 0;
 };
 
 class CpuTextIngestor : public TextIngestor {
@@ -189,7 +231,8 @@ TickResult Controller::run_query_and_scale(const Window& w) {
   if (P > 0) {
     VerdictRequest rq;
     rq.window = &w;
-    rq.power_on = (!w.power.empty() || w.d_power) && args_.power_threshold && *args_.power_threshold != 0.0;
+    rq.power_on = (!w.power.empty() || w.d_power || (w.resident && w.resident_power)) && args_.power_threshold &&
+                  *args_.power_threshold != 0.0;
     rq.power_threshold = rq.power_on ? *args_.power_threshold : 0.0;
     rq.eligible = kube_ ? eligible.data() : nullptr;
     rq.created_ts = kube_ ? created.data() : nullptr;

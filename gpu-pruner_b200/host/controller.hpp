@@ -83,6 +83,9 @@ class TextIngestor {
   virtual ~TextIngestor() = default;
   virtual Window ingest(const Cli& args, const std::string& util, const std::string* prof, const std::string* power,
                         const IngestOptions& opt, std::string* note) = 0;
+  // daemon mode: newest second of the window this ingestor keeps resident between ticks (0 = none: the next
+  // tick must bring the full range).  An ingest with opt.slice_seconds > 0 may throw NeedFullWindow.
+  virtual int64_t resident_t_end() const { return 0; }
 };
 class VerdictEngine {
  public:

@@ -6,7 +6,11 @@
 // parsed on the GPU straight into HBM and the decision runs on those device planes — the f32 window
 // never crosses PCIe, only the text does (once).
 #include <chrono>
+#include <algorithm>
 #include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
 #include <stdexcept>
 
 #include "../../include/gpr.h"
@@ -31,6 +35,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
   // ---- VerdictEngine --------------------------------------------------------------------------------
   bool decide(const VerdictRequest& rq, Verdict* out, std::string* error) override {
     const Window& w = *rq.window;
+    if (w.resident) return decide_resident(rq, out, error);
     const bool on_device = w.d_util != nullptr;
     if (on_device ? !ensure_ctx(rq.gpu_device, error) : !ensure(w, rq.power_on, rq.gpu_device, error)) return false;
     const uint32_t W = (w.P + 31) / 32;
@@ -74,23 +79,81 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     return true;
   }
 
+  // the resident window of daemon mode: same kernels on the ring, gates from the host
+  bool decide_resident(const VerdictRequest& rq, Verdict* out, std::string* error) {
+    const Window& w = *rq.window;
+    if (!ctx_) {
+      *error = "idle engine: no resident window";
+      return false;
+    }
+    // the ring has rows for resident_pods pods; the ones beyond the pods known so far hold no sample
+    const uint32_t Pr = w.resident_pods, W = (Pr + 31) / 32;
+    std::vector<uint32_t> dbits(W, 0), cbits(W, 0), vbits(W, 0);
+    std::vector<float> smax((size_t)Pr * w.G, 0.f);
+    std::vector<uint8_t> elig(Pr, 0);
+    std::vector<int64_t> created(Pr, std::numeric_limits<int64_t>::max());
+    for (uint32_t p = 0; p < w.P; ++p) {
+      elig[p] = rq.eligible ? rq.eligible[p] : 1;
+      if (rq.created_ts) created[p] = rq.created_ts[p];
+    }
+    gpr_window win;
+    memset(&win, 0, sizeof win);
+    win.struct_size = sizeof win;
+    win.mem_kind = GPR_MEM_HOST;  // the gates; the planes are the ring's
+    win.power_threshold = rq.power_on && w.resident_power ? rq.power_threshold : 0.0;
+    win.cutoff_ts = rq.cutoff_ts;
+    win.eligible = elig.data();
+    win.created_ts = rq.created_ts ? created.data() : nullptr;
+    gpr_result res;
+    memset(&res, 0, sizeof res);
+    res.struct_size = sizeof res;
+    res.out_mem_kind = GPR_MEM_HOST;
+    res.decision_bits = dbits.data(), res.candidate_bits = cbits.data(), res.veto_bits = vbits.data();
+    res.series_max = smax.data();
+    const int rc = gpr_decide_resident(ctx_, &win, &res);
+    if (rc != GPR_OK) {
+      *error = "idle engine (" + std::to_string(rc) + "): " + gpr_last_error(ctx_);
+      return false;
+    }
+    const uint32_t Wp = (w.P + 31) / 32;
+    out->decision_bits.assign(dbits.begin(), dbits.begin() + Wp);
+    out->candidate_bits.assign(cbits.begin(), cbits.begin() + Wp);
+    out->veto_bits.assign(vbits.begin(), vbits.begin() + Wp);
+    out->series_max.assign(smax.begin(), smax.begin() + (size_t)w.P * w.G);
+    out->n_series = res.n_series, out->n_candidates = res.n_candidates, out->n_decisions = res.n_decisions;
+    out->kernel_ms = res.kernel_ms;
+    return true;
+  }
+
   // ---- TextIngestor ---------------------------------------------------------------------------------
+  int64_t resident_t_end() const override { return session_ ? session_->resident_t_end() : 0; }
+
   Window ingest(const Cli& args, const std::string& util, const std::string* prof, const std::string* power,
                 const IngestOptions& opt, std::string* note) override {
     std::string error;
     if (!ensure_ctx(args.gpu_device, &error)) throw std::runtime_error("Failed to run query! " + error);
     const auto t0 = std::chrono::steady_clock::now();
     DeviceIngestReport rep;
-    Window w = ingest_matrix_device(*this, util, prof, power, opt, &rep);
+    if (!session_) session_.reset(new DeviceIngestSession(*this));
+    Window w = session_->ingest(util, prof, power, opt, &rep);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (note) {
-      char buf[480];
-      if (rep.on_device)
+      char buf[600];
+      if (rep.on_device && opt.slice_seconds > 0)
         snprintf(buf, sizeof buf,
-                 "Device ingest: %llu series lists parsed on the GPU into a %ux%ux%u window in %.1f ms "
+                 "Device ingest: %llu series lists of the last %lld s appended to the resident %ux%ux%u window in %.1f ms "
                  "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, series walk %.1f, labels->rows %.1f, "
                  "parse %.1f ms)",
-                 (unsigned long long)rep.spans, w.P, w.G, w.T, ms, (unsigned long long)rep.hard_spans,
+                 (unsigned long long)rep.spans, (long long)opt.slice_seconds, w.P, w.G, w.T, ms,
+                 (unsigned long long)rep.hard_spans, (unsigned long long)rep.rows_patched, rep.scan_ms, rep.labels_ms,
+                 rep.assign_ms, rep.parse_ms);
+      else if (rep.on_device)
+        snprintf(buf, sizeof buf,
+                 "Device ingest: %llu series lists parsed on the GPU into a %s%ux%ux%u window in %.1f ms "
+                 "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, series walk %.1f, labels->rows %.1f, "
+                 "parse %.1f ms)",
+                 (unsigned long long)rep.spans, w.resident ? "resident " : "", w.P, w.G, w.T, ms,
+                 (unsigned long long)rep.hard_spans,
                  (unsigned long long)rep.rows_patched, rep.scan_ms, rep.labels_ms, rep.assign_ms, rep.parse_ms);
       else
         snprintf(buf, sizeof buf, "Device ingest not used (%s): CPU text parser, %.1f ms", rep.reason.c_str(), ms);
@@ -131,13 +194,29 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     g.n_samples = grid.T, g.n_rows = grid.n_rows;
     check(gpr_text_parse(ctx_, slot, spans.data(), (uint32_t)spans.size(), &g, plane), "gpr_text_parse");
   }
-  void patch_row(int plane, uint32_t row, uint32_t T, const float* data) override {
+  void patch_row(int plane, uint32_t row, uint32_t T, const float* data, uint32_t n_newest, bool resident) override {
     float *u = nullptr, *p = nullptr;
-    check(gpr_text_planes(ctx_, &u, &p), "gpr_text_planes");
-    float* base = plane == 0 ? u : p;
-    check(gpr_memcpy(ctx_, base + (size_t)row * T, data, (size_t)T * sizeof(float), GPR_MEM_DEVICE, GPR_MEM_HOST),
-          "row patch");
+    uint32_t head = 0;  // dense planes: the newest bucket is column T - 1, as if the head were at 0
+    if (resident) {
+      uint64_t ld = 0;
+      check(gpr_resident_planes(ctx_, &u, &p, &ld), "gpr_resident_planes");
+      check(gpr_resident_head(ctx_, &head), "gpr_resident_head");
+    } else {
+      check(gpr_text_planes(ctx_, &u, &p), "gpr_text_planes");
+    }
+    float* base = (plane == 0 ? u : p) + (size_t)row * T;
+    // the newest n buckets sit at ring positions head - n .. head - 1 (mod T): at most two runs
+    const uint32_t first = (head + T - n_newest % T) % T;
+    const uint32_t run1 = std::min(n_newest, T - first);
+    check(gpr_memcpy(ctx_, base + first, data, (size_t)run1 * sizeof(float), GPR_MEM_DEVICE, GPR_MEM_HOST), "row patch");
+    if (run1 < n_newest)
+      check(gpr_memcpy(ctx_, base, data + run1, (size_t)(n_newest - run1) * sizeof(float), GPR_MEM_DEVICE, GPR_MEM_HOST),
+            "row patch");
   }
+  void resident_init(uint32_t pods, uint32_t G, uint32_t T, bool with_power) override {
+    check(gpr_resident_init(ctx_, pods, G, T, with_power ? GPR_F_POWER_PLANE : 0u), "gpr_resident_init");
+  }
+  void resident_advance(uint32_t n_new) override { check(gpr_resident_advance(ctx_, n_new), "gpr_resident_advance"); }
   const float* plane(int plane) override {
     float *u = nullptr, *p = nullptr;
     check(gpr_text_planes(ctx_, &u, &p), "gpr_text_planes");
@@ -187,6 +266,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
   }
   void drop() {
     if (!ctx_) return;
+    session_.reset();  // its resident window dies with the context
     if (d_elig_) gpr_device_free(ctx_, d_elig_), d_elig_ = nullptr;
     if (d_created_) gpr_device_free(ctx_, d_created_), d_created_ = nullptr;
     gate_cap_ = 0;
@@ -212,6 +292,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
   }
 
   gpr_ctx* ctx_ = nullptr;
+  std::unique_ptr<DeviceIngestSession> session_;
   uint64_t cap_cells_ = 0;
   bool cap_power_ = false;
   void* d_elig_ = nullptr;

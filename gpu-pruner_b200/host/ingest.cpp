@@ -85,7 +85,7 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
       float* row = plane.data() + ((size_t)rs.pod * w.G + rs.slot) * w.T;
       for (const Json& tv : rs.values->items()) {
         ++w.stats.samples_in;
-        const int64_t col = column_of(w, ts_seconds(tv[0].as_number()));
+        const int64_t col = column_of(w, ts_millis(tv[0].as_number()));
         if (col < 0) {
           ++w.stats.samples_out_of_window;
           continue;
@@ -169,7 +169,7 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
         float* row = plane.data() + ((size_t)ts.pod * w.G + ts.slot) * w.T;
         for_each_sample(ts.vb, ts.ve, [&](double t, double v) {
           ++n_in;
-          const int64_t col = column_of(w, ts_seconds(t));
+          const int64_t col = column_of(w, ts_millis(t));
           if (col < 0) {
             ++n_out;
             return;

@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <string>
 #include <vector>
@@ -47,6 +48,11 @@ struct Window {
   // device-resident planes (ingest_matrix_device): util / power above are empty then
   const float* d_util = nullptr;
   const float* d_power = nullptr;
+  // daemon mode: the window lives in the engine's resident ring (gpr_resident_*); P counts the pods known so
+  // far, the ring has room for resident_rows / G of them
+  bool resident = false;
+  bool resident_power = false;
+  uint32_t resident_pods = 0;
   IngestStats stats;
 };
 
@@ -54,6 +60,17 @@ struct IngestOptions {
   int64_t duration_min = 30;          // window length, --duration
   int64_t step = 0;                   // seconds; 0 = infer (the most frequent positive timestamp delta)
   int64_t t_end = 0;                  // 0 = newest timestamp in the response
+  // daemon mode (main.rs:286-330, --check-interval): > 0 = the responses only cover (t_end - slice_seconds, t_end],
+  // what was scraped since the previous tick; the rest of the window is resident in HBM
+  int64_t slice_seconds = 0;
+  bool resident = false;              // keep the window resident for the following ticks
+};
+
+// thrown by a delta ingest when the resident state cannot absorb the tick (new GPU slot beyond the ring's shape,
+// more pods than it has rows for, a PROF series that stopped reporting, a changed step / window): the caller
+// fetches the full window again
+struct NeedFullWindow : std::runtime_error {
+  using std::runtime_error::runtime_error;
 };
 
 // `util` is required; `prof` and `power` may be null pointers.  Each is a full Prometheus HTTP API

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <memory>
 
 #include "ingest_internal.hpp"
 
@@ -57,7 +58,7 @@ struct SeriesLoc {
 
 // Walk the series of one response using the device's marker lists; labels -> rows through `asg`.
 void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool is_power, bool is_prof,
-               DeviceIngestReport& rep) {
+               DeviceIngestReport& rep, bool remember) {
   const std::string& t = *plan.text;
   std::vector<uint64_t> opens, closes;
   auto t0 = std::chrono::steady_clock::now();
@@ -137,7 +138,8 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
     if (flat.parse(b, e)) {
       ++w.stats.series_in;
       if (!element) continue;
-      r = asg.assign(flat, is_power, is_prof, &p, &slot);
+      r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), flat, is_power, is_prof, &p, &slot)
+                   : asg.assign(flat, is_power, is_prof, &p, &slot);
     } else {
       Json metric;
       try {
@@ -148,7 +150,8 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
       if (!metric.is_object()) throw NotCompact{"label map is not an object"};
       ++w.stats.series_in;
       if (!element) continue;
-      r = asg.assign(metric, is_power, is_prof, &p, &slot);
+      r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), JsonMetric{metric}, is_power, is_prof, &p, &slot)
+                   : asg.assign(metric, is_power, is_prof, &p, &slot);
     }
     if (r == Assigner::Placed) plan.series.push_back(DevSeries{p, slot, (uint64_t)loc.vb, (uint64_t)loc.list_close});
   }
@@ -157,12 +160,30 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
 
 }  // namespace
 
-Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std::string* prof,
-                            const std::string* power, const IngestOptions& opt, DeviceIngestReport* report) {
+struct DeviceIngestSession::State {
+  Window w;                        // skeleton: pods / slots / shape, no planes
+  std::unique_ptr<Assigner> asg;   // bound to `w`; lives as long as the rows do
+  bool valid = false;              // the resident ring holds the window ending at w.t_end
+  uint32_t pods_cap = 0;           // pods the ring has rows for
+  bool with_power = false;
+  std::vector<std::pair<uint32_t, uint32_t>> prof_rows;  // (pod, slot) fed by PROF series, sorted
+};
+
+DeviceIngestSession::DeviceIngestSession(TextDevice& dev) : dev_(dev), st_(new State()) {}
+DeviceIngestSession::~DeviceIngestSession() { delete st_; }
+int64_t DeviceIngestSession::resident_t_end() const { return st_->valid ? st_->w.t_end : 0; }
+void DeviceIngestSession::invalidate() { st_->valid = false; }
+
+Window DeviceIngestSession::ingest(const std::string& util, const std::string* prof, const std::string* power,
+                                   const IngestOptions& opt, DeviceIngestReport* report) {
   DeviceIngestReport local;
   DeviceIngestReport& rep = report ? *report : local;
   rep = DeviceIngestReport{};
+  State& st = *st_;
+  const bool delta = opt.slice_seconds > 0;
   auto cpu = [&](const std::string& why) {
+    st.valid = false;
+    if (delta) throw NeedFullWindow("device ingest not possible for the tick's slice: " + why);
     rep.on_device = false, rep.reason = why;
     Window w = ingest_matrix_text(util, prof, power, opt);
     w.stats.warnings.push_back("device ingest not used: " + why);
@@ -170,8 +191,29 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
   };
   if (opt.t_end <= 0 || opt.step <= 0) return cpu("window end / step not given (query.json)");
 
-  Window w;
-  Assigner asg(w);
+  if (delta) {
+    // what must hold for the ring to take this tick: same grid, contiguous with what is resident
+    const char* why = nullptr;
+    if (!st.valid) why = "nothing resident";
+    else if (opt.step != st.w.step || opt.duration_min * 60 != st.w.span) why = "step / window length changed";
+    else if (opt.t_end - opt.slice_seconds != st.w.t_end) why = "the slice does not start where the resident window ends";
+    else if (opt.slice_seconds % opt.step != 0) why = "the slice is not a whole number of steps";
+    else if (opt.slice_seconds / opt.step >= (int64_t)st.w.T) why = "the slice is as long as the window";
+    else if ((power != nullptr) != st.with_power) why = "power plane appeared / disappeared";
+    if (why) {
+      st.valid = false;
+      throw NeedFullWindow(why);
+    }
+  } else {
+    st.w = Window();
+    st.asg.reset(new Assigner(st.w));
+    st.valid = false;
+    st.prof_rows.clear();
+  }
+  Window& w = st.w;
+  w.stats = IngestStats();
+  Assigner& asg = *st.asg;
+
   TextPlan plans[3];  // prof, util, power — the order the CPU paths assign rows in
   int n_plans = 0;
   auto add = [&](const std::string* text, int slot) -> TextPlan* {
@@ -183,26 +225,68 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
   TextPlan* pl_util = add(&util, 1);
   TextPlan* pl_power = add(power, 2);
   try {
-    if (pl_prof) plan_text(dev, *pl_prof, asg, w, false, true, rep);
-    plan_text(dev, *pl_util, asg, w, false, false, rep);
-    if (pl_power) plan_text(dev, *pl_power, asg, w, true, false, rep);
+    const bool remember = delta || opt.resident;
+    if (pl_prof) plan_text(dev_, *pl_prof, asg, w, false, true, rep, remember);
+    plan_text(dev_, *pl_util, asg, w, false, false, rep, remember);
+    if (pl_power) plan_text(dev_, *pl_power, asg, w, true, false, rep, remember);
   } catch (const NotCompact& e) {
     return cpu(e.why);
   }
-  finish_shape(w, opt, 0, 1, power != nullptr, /*allocate=*/false);  // t_end / step given: nothing to infer
-  const uint32_t n_rows = w.P * w.G;
-  if (n_rows == 0) {
+  std::vector<std::pair<uint32_t, uint32_t>> prof_rows;
+  if (pl_prof)
+    for (const DevSeries& s : pl_prof->series) prof_rows.emplace_back(s.pod, s.slot);
+  std::sort(prof_rows.begin(), prof_rows.end());
+
+  uint32_t n_new = 0;  // buckets this call opens (delta) — 0: the whole window
+  if (!delta) {
+    finish_shape(w, opt, 0, 1, power != nullptr, /*allocate=*/false);  // t_end / step given: nothing to infer
+    st.with_power = power != nullptr;
+    st.prof_rows = prof_rows;
+    if (opt.resident) {
+      st.pods_cap = w.P + w.P / 4 + 64;   // head-room: new pods get rows without a rebuild
+      dev_.resident_init(st.pods_cap, w.G, w.T, st.with_power);
+    }
+  } else {
+    // the shape is the ring's: anything that does not fit needs the full window again
+    uint32_t g_now = 1;
+    for (const PodEntry& pe : w.pods) g_now = std::max<uint32_t>(g_now, std::max<uint32_t>((uint32_t)pe.slots.size(), pe.power_slots));
+    const char* why = nullptr;
+    if (w.pods.size() > st.pods_cap) why = "more pods than the resident window has rows for";
+    else if (g_now > w.G) why = "a pod gained a GPU slot beyond the resident window's shape";
+    // `A or B` (query.promql.j2:10-20) is resolved per tick at assignment time; if the set of PROF-fed rows
+    // changes, UTIL samples that were (not) shadowed earlier in the window no longer match a fresh query
+    else if (prof_rows != st.prof_rows) why = "the set of DCGM_FI_PROF_GR_ENGINE_ACTIVE series changed";
+    if (why) {
+      st.valid = false;
+      throw NeedFullWindow(why);
+    }
+    w.P = (uint32_t)w.pods.size();
+    w.t_end = opt.t_end;
+    n_new = (uint32_t)(opt.slice_seconds / opt.step);
+    dev_.resident_advance(n_new);
+  }
+  const bool resident = delta || opt.resident;
+  const uint32_t n_rows = (resident ? st.pods_cap : w.P) * w.G;
+  auto result = [&]() {
+    Window out = w;  // pods / shape / stats
+    out.resident = resident;
+    if (resident) out.resident_pods = st.pods_cap, out.resident_power = st.with_power, st.valid = true;
+    return out;
+  };
+  if (w.P == 0) {
     rep.on_device = true;
-    return w;
+    return result();
   }
 
-  // rows fed by more than one series are merged on the device (NaN-aware max), the rest stored
+  // window the parse accepts: the whole range, or only the tick's slice
+  const int64_t parse_span = delta ? opt.slice_seconds : w.span;
+  const uint32_t patch_cols = delta ? n_new : w.T;
   auto run_plane = [&](std::vector<TextPlan*> texts, int plane) {
     std::vector<uint32_t> writers(n_rows, 0);
     for (TextPlan* tp : texts)
       for (const DevSeries& s : tp->series) ++writers[(size_t)s.pod * w.G + s.slot];
     std::vector<std::vector<gpr_text_span>> spans(texts.size());
-    bool fill = true;
+    bool fill = !resident;
     for (size_t k = 0; k < texts.size(); ++k) {
       for (const DevSeries& s : texts[k]->series) {
         gpr_text_span sp;
@@ -213,8 +297,9 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
       }
       const auto tp = std::chrono::steady_clock::now();
       TextDevice::TextGrid grid;
-      grid.t_end = w.t_end, grid.span = w.span, grid.step = w.step, grid.T = w.T, grid.n_rows = n_rows, grid.fill = fill;
-      dev.parse(texts[k]->slot, spans[k], grid, plane);
+      grid.t_end = w.t_end, grid.span = parse_span, grid.step = w.step, grid.T = w.T, grid.n_rows = n_rows;
+      grid.fill = fill, grid.resident = resident;
+      dev_.parse(texts[k]->slot, spans[k], grid, plane);
       rep.parse_ms += ms_since(tp);
       fill = false;
       rep.spans += spans[k].size();
@@ -228,6 +313,8 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
     std::vector<std::vector<float>> rows;
     std::vector<uint32_t> row_ids;
     std::vector<int64_t> row_slot(any_dirty ? n_rows : 0, -1);
+    Window bucket;  // the grid of the patched columns: the newest `patch_cols` buckets
+    bucket.t_end = w.t_end, bucket.step = w.step, bucket.span = parse_span, bucket.T = patch_cols;
     for (size_t k = 0; k < texts.size(); ++k) {
       const std::string& t = *texts[k]->text;
       for (const gpr_text_span& sp : spans[k]) {
@@ -239,13 +326,13 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
         }
         if (row_slot[sp.row] < 0) {
           row_slot[sp.row] = (int64_t)rows.size();
-          rows.emplace_back(w.T, std::numeric_limits<float>::quiet_NaN());
+          rows.emplace_back(patch_cols, std::numeric_limits<float>::quiet_NaN());
           row_ids.push_back(sp.row);
         }
         float* row = rows[(size_t)row_slot[sp.row]].data();
         for_each_sample(t.data() + sp.begin - 1, t.data() + sp.end + 1, [&](double ts, double v) {
           ++w.stats.samples_in;
-          const int64_t col = column_of(w, ts_seconds(ts));
+          const int64_t col = column_of(bucket, ts_millis(ts));
           if (col < 0) {
             ++w.stats.samples_out_of_window;
             return;
@@ -254,20 +341,29 @@ Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std:
         });
       }
     }
-    for (size_t i = 0; i < rows.size(); ++i) dev.patch_row(plane, row_ids[i], w.T, rows[i].data());
+    for (size_t i = 0; i < rows.size(); ++i) dev_.patch_row(plane, row_ids[i], w.T, rows[i].data(), patch_cols, resident);
     rep.rows_patched += rows.size();
   };
   std::vector<TextPlan*> util_texts;
   if (pl_prof) util_texts.push_back(pl_prof);
   util_texts.push_back(pl_util);
   run_plane(util_texts, 0);
-  w.d_util = dev.plane(0);
-  if (pl_power) {
-    run_plane({pl_power}, 1);
-    w.d_power = dev.plane(1);
-  }
+  if (pl_power) run_plane({pl_power}, 1);
   rep.on_device = true;
-  return w;
+  Window out = result();
+  if (!resident) {
+    out.d_util = dev_.plane(0);
+    if (pl_power) out.d_power = dev_.plane(1);
+  }
+  return out;
+}
+
+Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std::string* prof,
+                            const std::string* power, const IngestOptions& opt, DeviceIngestReport* report) {
+  DeviceIngestSession once(dev);
+  IngestOptions o = opt;
+  o.slice_seconds = 0, o.resident = false;
+  return once.ingest(util, prof, power, o, report);
 }
 
 }  // namespace gph

@@ -31,8 +31,13 @@ class TextDevice {
     bool resident = false;   // destination = the resident ring of daemon mode instead of the context plane
   };
   virtual void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) = 0;
-  virtual void patch_row(int plane, uint32_t row, uint32_t T, const float* data) = 0;
+  // overwrite the newest `n_newest` buckets of `row` (chronological order in `data`; n_newest == T: the whole
+  // row) — rows the strict device parser declined, re-parsed on the CPU
+  virtual void patch_row(int plane, uint32_t row, uint32_t T, const float* data, uint32_t n_newest, bool resident) = 0;
   virtual const float* plane(int plane) = 0;
+  // daemon mode: (re)create the resident ring [rows][T] (all "no sample"), and open the next n_new buckets
+  virtual void resident_init(uint32_t pods, uint32_t G, uint32_t T, bool with_power) = 0;
+  virtual void resident_advance(uint32_t n_new) = 0;
 };
 
 struct DeviceIngestReport {
@@ -44,11 +49,32 @@ struct DeviceIngestReport {
   double scan_ms = 0, labels_ms = 0, assign_ms = 0, parse_ms = 0;
 };
 
-// Needs opt.t_end > 0 and opt.step > 0 (the caller issued the range query, so it knows both);
+// One-shot: needs opt.t_end > 0 and opt.step > 0 (the caller issued the range query, so it knows both);
 // otherwise, and for any response that is not in Prometheus' compact encoding, the CPU text path
 // runs instead and the returned Window carries host vectors as usual.
 Window ingest_matrix_device(TextDevice& dev, const std::string& util, const std::string* prof,
                             const std::string* power, const IngestOptions& opt,
                             DeviceIngestReport* report = nullptr);
+
+// Daemon mode (main.rs:286-330): the row assignment and the window survive between ticks.  The first tick (and
+// any tick after NeedFullWindow) ingests the full range query into the engine's resident ring; later ticks ingest
+// only what was scraped since (opt.slice_seconds), appended to the ring.  Pods and slots keep their rows for the
+// life of the session, so a pod whose series stop reporting simply ages out of the window.
+class DeviceIngestSession {
+ public:
+  explicit DeviceIngestSession(TextDevice& dev);
+  ~DeviceIngestSession();
+  // opt.slice_seconds == 0: full window (re)build; > 0: delta — throws NeedFullWindow if it cannot be absorbed
+  Window ingest(const std::string& util, const std::string* prof, const std::string* power, const IngestOptions& opt,
+                DeviceIngestReport* report = nullptr);
+  // newest second the resident window holds (0 = nothing resident): the next delta must start right after it
+  int64_t resident_t_end() const;
+  void invalidate();
+
+ private:
+  struct State;
+  TextDevice& dev_;
+  State* st_;
+};
 
 }  // namespace gph

@@ -119,6 +119,24 @@ class Assigner {
   explicit Assigner(Window& w) : w_(w) {}
   enum Result { Skipped, Shadowed, Placed };
 
+  // Daemon mode: the same series comes back every tick and must keep its row.  A series is identified by the
+  // bytes of its label map as the server prints them (sorted keys, so the text is canonical) plus the plane it
+  // feeds; known series skip the label work altogether.
+  template <typename M>
+  Result assign_remembered(std::string_view raw_labels, const M& m, bool is_power, bool is_prof, uint32_t* pod_out,
+                           uint32_t* slot_out) {
+    key_raw_.assign(1, is_power ? 'W' : (is_prof ? 'P' : 'U')).append(raw_labels);
+    auto it = known_.find(key_raw_);
+    if (it != known_.end()) {
+      *pod_out = it->second.pod, *slot_out = it->second.slot;
+      if (it->second.result == Skipped) ++w_.stats.series_skipped;
+      return it->second.result;
+    }
+    const Result r = assign(m, is_power, is_prof, pod_out, slot_out);
+    known_.emplace(key_raw_, Known{r, *pod_out, *slot_out});
+    return r;
+  }
+
   Result assign(const Json& m, bool is_power, bool is_prof, uint32_t* pod_out, uint32_t* slot_out) {
     return assign(JsonMetric{m}, is_power, is_prof, pod_out, slot_out);
   }
@@ -204,6 +222,12 @@ class Assigner {
   }
 
  private:
+  struct Known {
+    Result result;
+    uint32_t pod, slot;
+  };
+  std::unordered_map<std::string, Known> known_;
+  std::string key_raw_;
   Window& w_;
   std::unordered_map<std::string, uint32_t> pod_index_;
   std::string key_, gkey_;
@@ -253,11 +277,19 @@ inline int64_t ts_seconds(double t) {
   return (int64_t)std::llround(t);
 }
 
-// column of timestamp ts, or -1 when it lies outside (t_end - N, t_end].  Buckets are `step` wide and end
-// at t_end (the device parser uses the same rule, csrc/gpr_text.cuh column_of)
-inline int64_t column_of(const Window& w, int64_t ts) {
-  if (ts > w.t_end || ts <= w.t_end - w.span) return -1;
-  const int64_t back = (w.t_end - ts) / w.step;  // 0 = newest column
+// Prometheus timestamps are milliseconds; window membership and bucketing are exact in that unit (rounding
+// to whole seconds first would move samples across the window's edges — and across the ticks of daemon mode)
+inline int64_t ts_millis(double t) {
+  if (!(t > -4e12 && t < 4e12)) return kBadTs;
+  return (int64_t)std::llround(t * 1000.0);
+}
+
+// column of a timestamp (milliseconds), or -1 when it lies outside (t_end - N, t_end].  Buckets are `step`
+// wide and end at t_end (the device parser uses the same rule, csrc/gpr_text.cuh column_of)
+inline int64_t column_of(const Window& w, int64_t ts_ms) {
+  const int64_t end = w.t_end * 1000;
+  if (ts_ms > end || ts_ms <= end - w.span * 1000) return -1;
+  const int64_t back = (end - ts_ms) / (w.step * 1000);  // 0 = newest column
   if (back >= (int64_t)w.T) return -1;
   return (int64_t)w.T - 1 - back;
 }

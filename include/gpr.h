@@ -222,6 +222,8 @@ GPR_API int gpr_resident_reindex(gpr_ctx *ctx);
 GPR_API int gpr_decide_resident(gpr_ctx *ctx, const gpr_window *win, gpr_result *res);
 /* device pointers of the resident planes (for generators / inspection); power may be NULL */
 GPR_API int gpr_resident_planes(gpr_ctx *ctx, float **util, float **power, uint64_t *row_stride);
+/* ring position the next appended bucket goes to; the newest bucket is at (head + n_samples - 1) % n_samples  */
+GPR_API int gpr_resident_head(gpr_ctx *ctx, uint32_t *head);
 
 /* ---- multi-GPU: one process per GPU, pods sharded by rank, one allgather of the bitmap - */
 #define GPR_UNIQUE_ID_BYTES 128

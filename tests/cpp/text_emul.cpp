@@ -45,11 +45,14 @@ class EmulDevice : public TextDevice {
   }
 
   void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) override {
-    if (grid.resident) throw std::logic_error("emul: no resident ring");
-    std::vector<uint32_t>& pl = plane_[plane];
+    std::vector<uint32_t>& pl = grid.resident ? ring_[plane] : plane_[plane];
     const uint32_t T = grid.T;
-    if (grid.fill) pl.assign((size_t)grid.n_rows * T, tx::kFillBits);
-    if (pl.size() != (size_t)grid.n_rows * T) throw std::logic_error("emul: plane shape changed without fill");
+    if (grid.resident) {
+      if (T != ring_T_ || (size_t)grid.n_rows * T > pl.size()) throw std::logic_error("emul: grid does not match the ring");
+    } else {
+      if (grid.fill) pl.assign((size_t)grid.n_rows * T, tx::kFillBits);
+      if (pl.size() != (size_t)grid.n_rows * T) throw std::logic_error("emul: plane shape changed without fill");
+    }
     struct Sink {
       std::vector<uint32_t>& pl;
       tx::Span* sp;
@@ -61,8 +64,8 @@ class EmulDevice : public TextDevice {
     } sink{pl, reinterpret_cast<tx::Span*>(spans.data())};
     tx::Grid g;
     memset(&g, 0, sizeof g);
-    g.t_end = grid.t_end, g.t_lo = grid.t_end - grid.span, g.step = (uint32_t)grid.step, g.T = T;
-    g.col_end = T - 1, g.ld = T;
+    g.t_end = grid.t_end * 1000, g.t_lo = (grid.t_end - grid.span) * 1000, g.step = (uint32_t)(grid.step * 1000), g.T = T;
+    g.col_end = grid.resident ? (ring_head_ + T - 1) % T : T - 1, g.ld = T;
     const std::vector<uint8_t>& text = text_[slot];
     const uint64_t n = n_[slot];
     const tx::Span* sp = reinterpret_cast<const tx::Span*>(spans.data());
@@ -90,15 +93,38 @@ class EmulDevice : public TextDevice {
     }
   }
 
-  void patch_row(int plane, uint32_t row, uint32_t T, const float* data) override {
-    memcpy(plane_[plane].data() + (size_t)row * T, data, (size_t)T * sizeof(float));
+  void patch_row(int plane, uint32_t row, uint32_t T, const float* data, uint32_t n_newest, bool resident) override {
+    uint32_t* base = (resident ? ring_[plane] : plane_[plane]).data() + (size_t)row * T;
+    const uint32_t head = resident ? ring_head_ : 0;
+    for (uint32_t i = 0; i < n_newest; ++i) memcpy(base + (head + T - n_newest + i) % T, data + i, 4);
   }
   const float* plane(int plane) override { return reinterpret_cast<const float*>(plane_[plane].data()); }
+  void resident_init(uint32_t pods, uint32_t G, uint32_t T, bool with_power) override {
+    ring_T_ = T, ring_head_ = 0, ring_rows_ = pods * G;
+    ring_[0].assign((size_t)ring_rows_ * T, tx::kFillBits);
+    ring_[1].clear();
+    if (with_power) ring_[1].assign((size_t)ring_rows_ * T, tx::kFillBits);
+  }
+  void resident_advance(uint32_t n_new) override {
+    for (auto& pl : ring_)
+      for (size_t r = 0; r * ring_T_ < pl.size(); ++r)
+        for (uint32_t i = 0; i < n_new; ++i) pl[r * ring_T_ + (ring_head_ + i) % ring_T_] = tx::kFillBits;
+    ring_head_ = (ring_head_ + n_new) % ring_T_;
+  }
+  // row of the ring in chronological order (oldest bucket first)
+  std::vector<float> ring_row(int plane, uint32_t row) const {
+    std::vector<float> out(ring_T_);
+    for (uint32_t c = 0; c < ring_T_; ++c) memcpy(&out[c], &ring_[plane][(size_t)row * ring_T_ + (ring_head_ + c) % ring_T_], 4);
+    return out;
+  }
+  bool has_ring_power() const { return !ring_[1].empty(); }
 
  private:
   std::vector<uint8_t> text_[3];
   uint64_t n_[3] = {0, 0, 0};
   std::vector<uint32_t> plane_[2];   // f32 bit patterns (cells start as 0xFFFFFFFF, like the device planes)
+  std::vector<uint32_t> ring_[2];    // the resident window of daemon mode: [rows][T], a ring over the time axis
+  uint32_t ring_T_ = 0, ring_head_ = 0, ring_rows_ = 0;
 };
 
 bool slurp(const std::string& path, std::string* out) {
@@ -124,7 +150,131 @@ bool same_plane(const float* a, const float* b, size_t n, bool bits, size_t* whe
 
 }  // namespace
 
+// ---- daemon mode: a sequence of ticks through one DeviceIngestSession on the emulated ring -------------------------
+//   text_emul --ticks <duration_min> <dir>      dir/tick-0000/{full,delta}/{util.json,[prof.json],[power.json],query.json}
+// After every tick the resident ring must hold exactly the window a fresh full-range ingest of that tick yields:
+// same samples for every series of every pod, nothing but "no sample" anywhere else.
+// prints per tick:  OK tick=<k> mode=<full|delta> [why]   |   MISMATCH tick=<k> <what>
+namespace {
+std::string slot_key(const GpuSlot& s) {
+  return s.hostname + "\x1f" + s.container + "\x1f" + s.gpu + "\x1f" + s.model + "\x1f" + (s.from_prof ? "P" : "U");
+}
+bool file_there(const std::string& p) {
+  std::ifstream f(p);
+  return (bool)f;
+}
+bool row_is_empty(const std::vector<float>& r) {
+  for (float v : r)
+    if (!std::isnan(v)) return false;
+  return true;
+}
+bool rows_equal(const std::vector<float>& a, const float* b) {
+  for (size_t i = 0; i < a.size(); ++i) {
+    const bool na = std::isnan(a[i]), nb = std::isnan(b[i]);
+    if (na != nb || (!na && a[i] != b[i])) return false;
+  }
+  return true;
+}
+
+int run_ticks(int64_t duration_min, const std::string& dir) {
+  EmulDevice dev;
+  DeviceIngestSession session(dev);
+  int bad = 0;
+  for (int k = 0;; ++k) {
+    char name[32];
+    snprintf(name, sizeof name, "/tick-%04d", k);
+    const std::string base = dir + name;
+    if (!file_there(base + "/full/util.json")) break;
+    auto load = [&](const std::string& d, std::string* util, std::string* prof, std::string* power, bool* hp, bool* hw,
+                    IngestOptions* o) {
+      slurp(d + "/util.json", util);
+      *hp = slurp(d + "/prof.json", prof), *hw = slurp(d + "/power.json", power);
+      const Json meta = Json::parse_file(d + "/query.json");
+      o->duration_min = duration_min;
+      o->t_end = (int64_t)meta["end"].as_number(0), o->step = (int64_t)meta["step"].as_number(0);
+      return (int64_t)meta["start"].as_number(0);
+    };
+    std::string util, prof, power, mode = "full", why;
+    bool hp = false, hw = false;
+    IngestOptions o;
+    Window wr;
+    bool done = false;
+    const int64_t since = session.resident_t_end();
+    try {
+      if (since > 0 && file_there(base + "/delta/util.json")) {
+        const int64_t start = load(base + "/delta", &util, &prof, &power, &hp, &hw, &o);
+        if (start == since) {
+          o.slice_seconds = o.t_end - start, o.resident = true;
+          try {
+            wr = session.ingest(util, hp ? &prof : nullptr, hw ? &power : nullptr, o);
+            mode = "delta", done = true;
+          } catch (const NeedFullWindow& e) {
+            why = e.what();
+          }
+        } else {
+          why = "delta does not continue the resident window";
+        }
+      }
+      load(base + "/full", &util, &prof, &power, &hp, &hw, &o);
+      o.slice_seconds = 0, o.resident = true;
+      if (!done) wr = session.ingest(util, hp ? &prof : nullptr, hw ? &power : nullptr, o);
+      // the reference for this tick: a fresh full-range ingest on the CPU
+      IngestOptions of = o;
+      of.resident = false;
+      const Window wf = ingest_matrix_text(util, hp ? &prof : nullptr, hw ? &power : nullptr, of, 2);
+      std::string what;
+      if (!wr.resident) what = "session did not keep the window resident";
+      if (what.empty() && (wr.T != wf.T || wr.step != wf.step || wr.t_end != wf.t_end || wr.span != wf.span)) what = "grid";
+      std::vector<uint8_t> row_used((size_t)wr.resident_pods * wr.G, 0);
+      for (uint32_t pf = 0; what.empty() && pf < wf.P; ++pf) {
+        const PodEntry& a = wf.pods[pf];
+        uint32_t pr = 0;
+        while (pr < wr.P && !(wr.pods[pr].name == a.name && wr.pods[pr].ns == a.ns)) ++pr;
+        if (pr == wr.P) {
+          what = "pod " + a.name + " missing from the resident window";
+          break;
+        }
+        const PodEntry& b = wr.pods[pr];
+        // every fresh row must be found among the resident rows of the same series key (duplicates: any order)
+        for (uint32_t sf = 0; what.empty() && sf < a.slots.size(); ++sf) {
+          bool found = false;
+          for (uint32_t sr = 0; !found && sr < b.slots.size(); ++sr) {
+            const size_t row = (size_t)pr * wr.G + sr;
+            if (row_used[row] || slot_key(b.slots[sr]) != slot_key(a.slots[sf])) continue;
+            if (rows_equal(dev.ring_row(0, (uint32_t)row), wf.util.data() + ((size_t)pf * wf.G + sf) * wf.T)) row_used[row] = 1, found = true;
+          }
+          if (!found) what = "util row of " + a.name + " gpu " + a.slots[sf].gpu + " differs from a fresh ingest";
+        }
+        if (what.empty() && a.power_slots) {
+          if (!dev.has_ring_power()) what = "no resident power plane";
+          // power rows carry no identity beyond the pod: compare as a multiset
+          std::vector<uint8_t> used(b.power_slots, 0);
+          for (uint32_t sf = 0; what.empty() && sf < a.power_slots; ++sf) {
+            bool found = false;
+            for (uint32_t sr = 0; !found && sr < b.power_slots; ++sr)
+              if (!used[sr] && rows_equal(dev.ring_row(1, pr * wr.G + sr), wf.power.data() + ((size_t)pf * wf.G + sf) * wf.T)) used[sr] = 1, found = true;
+            if (!found) what = "power row of " + a.name + " differs from a fresh ingest";
+          }
+          for (uint32_t sr = 0; what.empty() && sr < b.power_slots; ++sr)
+            if (!used[sr] && !row_is_empty(dev.ring_row(1, pr * wr.G + sr))) what = "stale power row in " + a.name;
+        }
+      }
+      // everything else in the ring — aged-out series, pods that left, unused rows — must hold no sample
+      for (size_t row = 0; what.empty() && row < row_used.size(); ++row)
+        if (!row_used[row] && !row_is_empty(dev.ring_row(0, (uint32_t)row))) what = "stale samples in resident row " + std::to_string(row);
+      if (what.empty()) printf("OK tick=%d mode=%s %s\n", k, mode.c_str(), why.c_str());
+      else printf("MISMATCH tick=%d %s\n", k, what.c_str()), ++bad;
+    } catch (const std::exception& e) {
+      printf("MISMATCH tick=%d exception %s\n", k, e.what());
+      ++bad;
+    }
+  }
+  return bad ? 1 : 0;
+}
+}  // namespace
+
 int main(int argc, char** argv) {
+  if (argc == 4 && std::string(argv[1]) == "--ticks") return run_ticks(atoll(argv[2]), argv[3]);
   if (argc < 5) return 2;
   IngestOptions o;
   o.t_end = atoll(argv[1]), o.step = atoll(argv[2]), o.duration_min = atoll(argv[3]);

@@ -93,10 +93,13 @@ def test_parse_value_matches_strtod_then_float(driver):
              "0.1", "0.07", "99.99999999999999", "1234567.1234567", "16777216", "16777217", "4294967296.5",
              "0.000000000000000000000000000000000000000000001", "0.0000000000000000000000000000000000000000000001",
              "340282350000000000000000000000000000000", "0.1234567890123456789", "1.7976931348623157",
-             "000123", "0.000", "5.0000000000000000000"]
+             "000123", "0.000", "5.0000000000000000000", "5e-07", "1.2345e+21", "1e2", "1E1", "1e-50", "1e23",
+             "9.999999e-07", "1e+21", "0e0", "3.4028235e+38", "1e39", "4.9e-324", "1.5e-46"]
     for _ in range(60_000):
         x = rng.random() if rng.random() < 0.6 else rng.uniform(0, 700)
-        texts.append(repr(x) if "e" not in repr(x) else "%.17f" % x)
+        texts.append(repr(x))          # includes Go-style exponent forms for the tiny ones ("5e-07")
+        if rng.random() < 0.05:
+            texts.append(repr(x * 10.0 ** rng.randrange(-30, 30)))
         if rng.random() < 0.1:
             texts.append(str(rng.randrange(0, 101)))
         if rng.random() < 0.05:
@@ -113,29 +116,34 @@ def test_parse_value_matches_strtod_then_float(driver):
             assert int(bits, 16) in (0x00000001, 0x80000001) and tiny == "1", t
             continue
         assert int(bits, 16) == struct.unpack("<I", struct.pack("<f", want))[0], (t, bits)
-    assert len(declined) <= 6, declined[:10]     # > 19 significant digits and the like
+    # declined: more than 19 significant digits, results in the subnormal range, and the handful of exactly-half-way
+    # products Eisel-Lemire leaves to a slower method — never a shortest-round-trip decimal below 1e21
+    realistic = {t for t in texts if "e" not in t and 0 <= float(t) <= 1000}
+    for t in declined:
+        digits = len(t.lstrip("-+").split("e")[0].replace(".", "").lstrip("0"))
+        assert digits > 19 or t not in realistic, t
+    assert len(declined) < len(texts) // 100, declined[:10]
     assert "0.30000000000000004" not in declined and "123456789012345678" not in declined
 
 
 def test_parse_value_declines_what_it_cannot_decide(driver):
-    out = _run(driver, ["V 1e5", "V .5", "V 5.", "V 12345678901234567890", "V 1.2.3", "V abc", "V +", "V 0x10",
-                        "V 1234567890123456789012"])
+    out = _run(driver, ["V .5", "V 5.", "V 12345678901234567890", "V 1.2.3", "V abc", "V +", "V 0x10",
+                        "V 1234567890123456789012", "V 1e", "V 1e+", "V 1e1234", "V e5", "V 1.e5"])
     assert all(line.split()[0] == "0" for line in out), out
 
 
-def test_parse_timestamp_rounds_like_llround(driver):
-    texts = ["1700000000", "1700000000.4", "1700000000.5", "1700000000.499999", "1700000000.500000", "1700000000.123",
-             "0", "9999999999999", "4000000000000", "3999999999999.5"]
+def test_parse_timestamp_is_exact_in_milliseconds(driver):
+    texts = ["1700000000", "1700000000.4", "1700000000.5", "1700000000.499", "1700000000.500", "1700000000.123",
+             "0", "0.001", "9999999999999", "4000000000000", "3999999999999.5", "1700000000.05"]
     out = _run(driver, ["T " + t for t in texts])
     for t, line in zip(texts, out):
         q, ts = line.split()
         assert int(q) == len(t) + 1, t
         x = float(t)
-        want = int(np.floor(x + 0.5))
-        if not (x < 4e12) or want >= 4_000_000_000_000:
+        if not (x < 4e12):
             assert int(ts) < -(1 << 60)          # "no sane epoch time": far outside every window
         else:
-            assert int(ts) == want, t
-    # longer than the integer shortcut is exact for: declined (the span goes to the CPU parser)
-    out = _run(driver, ["T 1700000000.1234567", "T 17000000001234", "T -5", "T +5", "T 1e9", "T "])
+            assert int(ts) == round(x * 1000), t  # what the CPU path computes: llround(strtod(t) * 1000)
+    # finer than a millisecond, signs, exponents: declined (the span goes to the CPU parser)
+    out = _run(driver, ["T 1700000000.1234", "T 17000000001234", "T -5", "T +5", "T 1e9", "T ", "T 5."])
     assert all(line.split()[0] == "0" for line in out), out
