@@ -13,6 +13,7 @@
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in nsys / ncu --nvtx timelines
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -170,13 +171,27 @@ struct gpr_ctx {
   size_t spans_cap = 0;
   float* d_tplane[2] = {nullptr, nullptr};
   size_t tplane_cap[2] = {0, 0};
-  // pageable text is staged through a small pinned ring by a few host threads (upload_pageable)
-  static constexpr int kUpThreads = 4, kUpSlots = 2;
-  static constexpr size_t kUpChunk = 4u << 20;
-  unsigned char* h_up_ring = nullptr;  // [kUpThreads][kUpSlots][kUpChunk], pinned
+  // The text goes up in chunks through a few producer threads (pageable text is staged through a small pinned
+  // ring) and every chunk is scanned as soon as it has landed; the markers of a chunk are written by the scan
+  // kernel straight into a block of mapped pinned memory (ScanPipe, gpr_text_scan_begin / _next).
+  static constexpr int kUpThreads = 16, kUpSlots = 2;
+  // chunk size.  Pageable text: GPR_TEXT_CHUNK_MB (1..16), default 2 — the pinned staging ring is
+  // up_threads x 2 x chunk, and page-locking it is paid by the first scan of a process (measured on the box:
+  // 1, 2 and 4 MB chunks all reach ~41 GB/s with 8 producers).  Pinned / device text needs no staging and goes
+  // in 16 MB pieces (49 GB/s).
+  static constexpr size_t kPinnedChunk = 16u << 20;
+  static constexpr int kMarkBlocks = 64;                   // ring of marker blocks (chunks in flight ahead of the consumer)
+  static constexpr uint32_t kMarkCap = 16384;              // markers of one kind per chunk (2 MB: one per 128 B)
+  size_t up_chunk = 2u << 20;
+  size_t up_slot_bytes = 0;            // up_chunk + a page (the 16 bytes of overlap, page aligned)
+  unsigned char* h_up_ring = nullptr;  // [up_threads][kUpSlots][up_slot_bytes], pinned
+  uint32_t* h_mark_blocks = nullptr;   // [kMarkBlocks][2 + 2 * kMarkCap], pinned + device-mapped
+  uint32_t* d_mark_blocks = nullptr;   // the same in device memory: the scan appends here (atomics), then publishes
   cudaStream_t up_stream[kUpThreads] = {};
   cudaEvent_t up_event[kUpThreads][kUpSlots] = {};
-  int up_threads = kUpThreads;         // GPR_TEXT_UPLOAD_THREADS (0 = plain cudaMemcpy)
+  cudaEvent_t mark_event[kMarkBlocks] = {};
+  int up_threads = 8;                  // GPR_TEXT_UPLOAD_THREADS (1..16)
+  struct ScanPipe* pipe = nullptr;     // the scan in progress (gpr_text_scan_begin .. last gpr_text_scan_next)
 
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -193,6 +208,8 @@ struct gpr_ctx {
   uint64_t launches = 0;
   char err[512] = "";
 };
+
+void scan_pipe_abort(gpr_ctx* ctx);   // defined with the text ingest below
 
 namespace {
 
@@ -742,6 +759,140 @@ __global__ void __launch_bounds__(128) k_reindex(const float* __restrict__ plane
 
 }  // namespace
 
+// ---- upload + scan pipeline ------------------------------------------------------------------------------------
+// The text is cut into chunks.  A few producer threads each take every nt-th chunk: copy it into their pinned
+// double buffer (pageable sources; a plain cudaMemcpy would go through the driver's single bounce buffer at
+// ~10 GB/s), enqueue the H2D copy on their own stream, and right behind it the scan kernel for that chunk, which
+// appends the chunk's markers to a block of mapped pinned memory.  A chunk is copied with 16 bytes of overlap
+// into the next one (identical bytes written twice), so its scan never needs another stream's data.  The
+// consumer (gpr_text_scan_next) takes the chunks in text order while later ones are still in flight.
+struct ScanPipe {
+  int slot = 0;
+  const char* src = nullptr;
+  uint8_t* dst = nullptr;
+  uint64_t n = 0, n_chunks = 0, chunk = 0;
+  int nt = 1;
+  int src_kind = GPR_MEM_HOST;
+  bool staged = false;  // source is pageable host memory: goes through the pinned ring
+  std::vector<std::thread> th;
+  std::atomic<uint64_t> consumed{0};                      // chunks handed to the caller
+  std::atomic<uint64_t> recorded[gpr_ctx::kMarkBlocks];   // chunk + 1 whose event has been recorded in this block
+  std::atomic<int> error{0};                              // first cudaError_t of a producer
+  std::atomic<bool> stop{false};
+  uint64_t next = 0;                                      // next chunk the consumer returns
+};
+
+namespace {
+
+constexpr uint32_t kBlockWords = 2 + 2 * gpr_ctx::kMarkCap;
+
+// markers of one chunk, 32-bit offsets relative to the chunk: [n_open, n_close, opens[cap], closes[cap]]
+struct ChunkSink {
+  uint32_t* block;
+  uint64_t base;
+  __device__ __forceinline__ void values_open(uint64_t p) {
+    const uint32_t i = atomicAdd(block + 0, 1u);
+    if (i < gpr_ctx::kMarkCap) block[2 + i] = (uint32_t)(p - base);
+  }
+  __device__ __forceinline__ void values_close(uint64_t p) {
+    const uint32_t i = atomicAdd(block + 1, 1u);
+    if (i < gpr_ctx::kMarkCap) block[2 + gpr_ctx::kMarkCap + i] = (uint32_t)(p - base);
+  }
+};
+
+// copies a chunk's markers from the device block to the host-mapped one with plain coalesced stores (the scan's
+// atomic appends must not go to host memory: an atomic across PCIe costs microseconds)
+__global__ void __launch_bounds__(256) k_publish_marks(const uint32_t* __restrict__ d_block, uint32_t* __restrict__ h_block) {
+  const uint32_t no = min(d_block[0], gpr_ctx::kMarkCap), nc = min(d_block[1], gpr_ctx::kMarkCap);
+  for (uint32_t i = threadIdx.x; i < no; i += blockDim.x) h_block[2 + i] = d_block[2 + i];
+  for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x)
+    h_block[2 + gpr_ctx::kMarkCap + i] = d_block[2 + gpr_ctx::kMarkCap + i];
+  if (threadIdx.x == 0) h_block[0] = d_block[0], h_block[1] = d_block[1];
+}
+
+__global__ void __launch_bounds__(256) k_text_scan_chunk(const uint8_t* __restrict__ t, uint64_t n, uint64_t slice_begin,
+                                                         uint64_t slice_end, uint32_t* block) {
+  ChunkSink sink{block, slice_begin * gpr::text::kScanBytes};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t slice = slice_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slice < slice_end; slice += stride)
+    gpr::text::scan_slice(t, n, slice, sink);
+}
+
+void scan_producer(gpr_ctx* ctx, ScanPipe* sp, int k) {
+  constexpr int NS = gpr_ctx::kUpSlots, NB = gpr_ctx::kMarkBlocks;
+  const size_t SLOT = ctx->up_slot_bytes;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  bool used[NS] = {};
+  int slot = 0;
+  cudaStream_t st = ctx->up_stream[k];
+  for (uint64_t c = (uint64_t)k; c < sp->n_chunks && e == cudaSuccess && !sp->stop.load(); c += (uint64_t)sp->nt) {
+    // the marker block of this chunk is free once the consumer has taken chunk c - NB
+    while (c >= sp->consumed.load(std::memory_order_acquire) + NB && !sp->stop.load()) std::this_thread::yield();
+    if (sp->stop.load()) break;
+    const uint64_t off = c * sp->chunk;
+    const uint64_t len = std::min<uint64_t>(sp->chunk, sp->n - off);
+    const uint64_t len_ov = std::min<uint64_t>(len + 16, sp->n - off);  // overlap into the next chunk
+    const void* from = sp->src + off;
+    if (sp->staged) {
+      unsigned char* buf = ctx->h_up_ring + ((size_t)k * NS + slot) * SLOT;
+      if (used[slot]) e = cudaEventSynchronize(ctx->up_event[k][slot]);  // its previous DMA has drained
+      if (e != cudaSuccess) break;
+      memcpy(buf, from, len_ov);
+      from = buf;
+    }
+    e = cudaMemcpyAsync(sp->dst + off, from, len_ov,
+                        sp->src_kind == GPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && sp->staged) e = cudaEventRecord(ctx->up_event[k][slot], st), used[slot] = true;
+    slot = (slot + 1) % NS;
+    if (e != cudaSuccess) break;
+    // (the kernels that last used block c % NB have completed: their chunk was consumed)
+    uint32_t* h_block = ctx->h_mark_blocks + (size_t)(c % NB) * kBlockWords;
+    uint32_t* d_block = ctx->d_mark_blocks + (size_t)(c % NB) * kBlockWords;
+    e = cudaMemsetAsync(d_block, 0, 2 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) break;
+    const uint64_t s0 = off / gpr::text::kScanBytes;
+    const uint64_t s1 = (off + len + gpr::text::kScanBytes - 1) / gpr::text::kScanBytes;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((s1 - s0 + 255) / 256, (uint64_t)ctx->sm_count * 8));
+    k_text_scan_chunk<<<grid, 256, 0, st>>>(sp->dst, sp->n, s0, s1, d_block);
+    k_publish_marks<<<1, 256, 0, st>>>(d_block, h_block);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->mark_event[c % NB], st);
+    if (e != cudaSuccess) break;
+    sp->recorded[c % NB].store(c + 1, std::memory_order_release);
+  }
+  if (e != cudaSuccess) {
+    int zero = 0;
+    sp->error.compare_exchange_strong(zero, (int)e);
+    sp->stop.store(true);
+  }
+}
+
+int scan_pipe_finish(gpr_ctx* ctx, bool ok) {
+  ScanPipe* sp = ctx->pipe;
+  if (!sp) return GPR_OK;
+  if (!ok) sp->stop.store(true);
+  for (std::thread& t : sp->th) t.join();
+  cudaError_t e = (cudaError_t)sp->error.load();
+  // work queued on the context's stream afterwards (the parse kernels) must see the whole text
+  for (int k = 0; k < sp->nt && e == cudaSuccess; ++k) {
+    e = cudaEventRecord(ctx->up_event[k][0], ctx->up_stream[k]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->up_event[k][0], 0);
+  }
+  if (!ok)
+    for (int k = 0; k < sp->nt; ++k) cudaStreamSynchronize(ctx->up_stream[k]);
+  delete sp;
+  ctx->pipe = nullptr;
+  if (e != cudaSuccess) return fail(ctx, GPR_E_CUDA, "text upload / scan: %s", cudaGetErrorString(e));
+  return GPR_OK;
+}
+
+}  // namespace
+
+void scan_pipe_abort(gpr_ctx* ctx) {
+  if (ctx && ctx->pipe) (void)scan_pipe_finish(ctx, false);
+}
+
+
 // ===========================================================================================
 // extern "C"
 // ===========================================================================================
@@ -781,7 +932,12 @@ void gpr_destroy(gpr_ctx* ctx) {
   for (void* p : dev)
     if (p) cudaFree(p);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  scan_pipe_abort(ctx);
   if (ctx->h_up_ring) cudaFreeHost(ctx->h_up_ring);
+  if (ctx->h_mark_blocks) cudaFreeHost(ctx->h_mark_blocks);
+  if (ctx->d_mark_blocks) cudaFree(ctx->d_mark_blocks);
+  for (cudaEvent_t e : ctx->mark_event)
+    if (e) cudaEventDestroy(e);
   for (int k = 0; k < gpr_ctx::kUpThreads; ++k) {
     if (ctx->up_stream[k]) cudaStreamDestroy(ctx->up_stream[k]);
     for (cudaEvent_t e : ctx->up_event[k])
@@ -856,7 +1012,9 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     CU(cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_done, 0, 2 * sizeof(unsigned long long)));
     c->pdl_enabled = env_int("GPR_PDL", 1) != 0;
-    c->up_threads = std::max(0, std::min((int)gpr_ctx::kUpThreads, env_int("GPR_TEXT_UPLOAD_THREADS", gpr_ctx::kUpThreads)));
+    c->up_threads = std::max(1, std::min((int)gpr_ctx::kUpThreads, env_int("GPR_TEXT_UPLOAD_THREADS", 8)));
+    c->up_chunk = (size_t)std::max(1, std::min(16, env_int("GPR_TEXT_CHUNK_MB", 2))) << 20;
+    c->up_slot_bytes = c->up_chunk + 4096;
     c->exchange_debug = env_int("GPR_DEBUG_EXCHANGE", 0);
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
                       ((size_t)kSlots * 4 + 2) * sizeof(unsigned long long)));
@@ -1348,115 +1506,149 @@ static_assert(sizeof(gpr_text_span) == sizeof(gpr::text::Span) && offsetof(gpr_t
               "gpr_text_span mirrors gpr::text::Span");
 static_assert(GPR_SPAN_SHARED == gpr::text::kSpanShared && GPR_SPAN_HARD == gpr::text::kSpanHard, "span flags");
 
-// Host -> device copy of response text that sits in ordinary pageable memory.  A plain cudaMemcpy stages
-// it through the driver's single bounce buffer (measured 10.7 GB/s); here a few host threads copy
-// alternate 4 MB chunks into their own pinned double buffers and each enqueues its chunk on its own
-// stream, so the memcpy work is spread over cores and overlaps the DMA.  The context's stream then waits
-// for all of them.  Pinned / registered sources skip this and go down at PCIe speed.
-static int upload_text(gpr_ctx* ctx, uint8_t* dst, const char* src, uint64_t n, int32_t mem_kind) {
-  if (n == 0) return GPR_OK;
-  if (mem_kind == GPR_MEM_DEVICE) {
-    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, ctx->stream));
-    return GPR_OK;
-  }
-  cudaPointerAttributes at;
-  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  (void)cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind
-  constexpr int NT = gpr_ctx::kUpThreads, NS = gpr_ctx::kUpSlots;
-  constexpr size_t CH = gpr_ctx::kUpChunk;
-  const int nt = std::min<int>(ctx->up_threads, NT);
-  if (pinned || nt <= 0 || n < 4 * CH) {
-    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
-    return GPR_OK;
-  }
-  if (!ctx->h_up_ring) {
-    CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_up_ring), (size_t)NT * NS * CH, cudaHostAllocDefault));
+int gpr_text_scan_begin(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes, int32_t mem_kind) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  NvtxRange nvtx_range("gpr_text_scan_begin");
+  if (slot < 0 || slot > 2) return fail(ctx, GPR_E_INVALID, "text slot %d (0..2)", slot);
+  if (!text && n_bytes) return fail(ctx, GPR_E_INVALID, "text is NULL");
+  if (mem_kind != GPR_MEM_HOST && mem_kind != GPR_MEM_DEVICE) return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", mem_kind);
+  scan_pipe_abort(ctx);  // an unfinished scan is dropped
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_text[slot], &ctx->text_cap[slot], (size_t)n_bytes + gpr::text::kTextPad)) != GPR_OK)
+    return rc;
+  constexpr int NT = gpr_ctx::kUpThreads, NS = gpr_ctx::kUpSlots, NB = gpr_ctx::kMarkBlocks;
+  if (!ctx->h_mark_blocks) {
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_mark_blocks), (size_t)NB * kBlockWords * sizeof(uint32_t),
+                     cudaHostAllocMapped));
+    CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_mark_blocks), (size_t)NB * kBlockWords * sizeof(uint32_t)));
+    for (int b = 0; b < NB; ++b) CU(cudaEventCreateWithFlags(&ctx->mark_event[b], cudaEventDisableTiming));
     for (int k = 0; k < NT; ++k) {
       CU(cudaStreamCreateWithFlags(&ctx->up_stream[k], cudaStreamNonBlocking));
       for (int s = 0; s < NS; ++s) CU(cudaEventCreateWithFlags(&ctx->up_event[k][s], cudaEventDisableTiming));
     }
   }
-  // the destination may still be read by earlier work on the context's stream
-  CU(cudaEventRecord(ctx->ev_join, ctx->stream));
-  for (int k = 0; k < nt; ++k) CU(cudaStreamWaitEvent(ctx->up_stream[k], ctx->ev_join, 0));
-  const uint64_t n_chunks = (n + CH - 1) / CH;
-  cudaError_t errs[NT];
-  for (int k = 0; k < NT; ++k) errs[k] = cudaSuccess;
-  auto work = [&](int k) {
-    cudaError_t e = cudaSetDevice(ctx->device);
-    bool used[NS] = {};
-    int slot = 0;
-    for (uint64_t c = (uint64_t)k; c < n_chunks && e == cudaSuccess; c += (uint64_t)nt, slot = (slot + 1) % NS) {
-      unsigned char* buf = ctx->h_up_ring + ((size_t)k * NS + slot) * CH;
-      if (used[slot]) e = cudaEventSynchronize(ctx->up_event[k][slot]);  // its previous DMA has drained
-      if (e != cudaSuccess) break;
-      const uint64_t off = c * CH, len = std::min<uint64_t>(CH, n - off);
-      memcpy(buf, src + off, len);
-      e = cudaMemcpyAsync(dst + off, buf, len, cudaMemcpyHostToDevice, ctx->up_stream[k]);
-      if (e == cudaSuccess) e = cudaEventRecord(ctx->up_event[k][slot], ctx->up_stream[k]);
-      used[slot] = true;
-    }
-    errs[k] = e;
-  };
-  std::vector<std::thread> th;
-  int started = 1;  // share 0 runs on this thread
-  try {
-    th.reserve((size_t)nt);
-    for (int k = 1; k < nt; ++k) th.emplace_back(work, k), ++started;
-  } catch (...) {  // no thread to be had: nothing may cross the C ABI, the shares are done here instead
+  uint8_t* d = ctx->d_text[slot];
+  ctx->text_n[slot] = n_bytes;
+  ctx->last_was_reduce = false;
+  // the zero pad behind the text, and everything earlier on the context's stream that may still read the buffer
+  CU(cudaMemsetAsync(d + n_bytes, 0, gpr::text::kTextPad, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ScanPipe* sp = new ScanPipe();
+  sp->slot = slot, sp->src = text, sp->dst = d, sp->n = n_bytes, sp->src_kind = mem_kind;
+  for (auto& r : sp->recorded) r.store(0);
+  if (mem_kind == GPR_MEM_HOST && n_bytes) {
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, text) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();  // an unregistered pointer may leave an error code behind
+    sp->staged = !pinned;
   }
-  work(0);
-  for (std::thread& x : th) x.join();
-  for (int k = started; k < nt; ++k) work(k);
-  for (int k = 0; k < nt; ++k) CU(errs[k]);
-  // everything enqueued: the context's stream continues once every upload stream has drained
-  for (int k = 0; k < nt; ++k) {
-    CU(cudaEventRecord(ctx->up_event[k][0], ctx->up_stream[k]));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->up_event[k][0], 0));
+  sp->chunk = sp->staged ? ctx->up_chunk : gpr_ctx::kPinnedChunk;
+  sp->n_chunks = (n_bytes + sp->chunk - 1) / sp->chunk;
+  // pinned and device sources need no staging copy: one producer keeps the DMA engine busy
+  sp->nt = sp->staged ? (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->up_threads, sp->n_chunks)) : 1;
+  if (sp->staged && !ctx->h_up_ring)
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_up_ring), (size_t)ctx->up_threads * NS * ctx->up_slot_bytes,
+                     cudaHostAllocDefault));
+  ctx->pipe = sp;
+  ctx->launches += 2 * sp->n_chunks;
+  try {
+    for (int k = 0; k < sp->nt; ++k) sp->th.emplace_back(scan_producer, ctx, sp, k);
+  } catch (...) {
+    if (sp->th.empty()) {  // no thread to be had at all: produce on this thread (blocks run ahead by at most NB chunks)
+      (void)scan_pipe_finish(ctx, false);
+      return fail(ctx, GPR_E_NOMEM, "could not start an upload thread");
+    }
+    sp->nt = (int)sp->th.size();  // fewer producers than planned would skip chunks: restart with what we have
+    (void)scan_pipe_finish(ctx, false);
+    return fail(ctx, GPR_E_NOMEM, "could not start the upload threads");
   }
   return GPR_OK;
+  GPR_CATCH(ctx)
+}
+
+int gpr_text_scan_next(gpr_ctx* ctx, uint64_t* opens, uint64_t* closes, uint64_t cap, uint64_t* n_opens, uint64_t* n_closes,
+                       uint64_t* bytes_done, int32_t* more) {
+  if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
+  if (!n_opens || !n_closes || !bytes_done || !more || (cap && (!opens || !closes)))
+    return fail(ctx, GPR_E_INVALID, "output pointers are NULL");
+  ScanPipe* sp = ctx->pipe;
+  if (!sp) return fail(ctx, GPR_E_STATE, "no scan in progress (gpr_text_scan_begin)");
+  *n_opens = *n_closes = 0;
+  if (sp->next >= sp->n_chunks) {  // everything delivered (also: empty text)
+    *bytes_done = sp->n, *more = 0;
+    return scan_pipe_finish(ctx, true);
+  }
+  constexpr int NB = gpr_ctx::kMarkBlocks;
+  const uint64_t c = sp->next;
+  while (sp->recorded[c % NB].load(std::memory_order_acquire) != c + 1) {
+    if (sp->error.load() || sp->stop.load()) return scan_pipe_finish(ctx, false) != GPR_OK ? GPR_E_CUDA : fail(ctx, GPR_E_CUDA, "text upload stopped");
+    std::this_thread::yield();
+  }
+  CU(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaEventSynchronize(ctx->mark_event[c % NB]);
+  if (e != cudaSuccess) {
+    (void)scan_pipe_finish(ctx, false);
+    return fail(ctx, GPR_E_CUDA, "text scan: %s", cudaGetErrorString(e));
+  }
+  const uint32_t* block = ctx->h_mark_blocks + (size_t)(c % NB) * kBlockWords;
+  const uint64_t no = block[0], nc = block[1], base = c * sp->chunk;
+  if (no > gpr_ctx::kMarkCap || nc > gpr_ctx::kMarkCap || no > cap || nc > cap) {
+    const bool caller = no <= gpr_ctx::kMarkCap && nc <= gpr_ctx::kMarkCap;
+    *n_opens = no, *n_closes = nc;
+    if (!caller) (void)scan_pipe_finish(ctx, false);  // (a too small `cap` may be retried with a larger one)
+    return fail(ctx, GPR_E_CAPACITY, "%llu / %llu markers in one %llu-byte chunk, room for %llu", (unsigned long long)no,
+                (unsigned long long)nc, (unsigned long long)sp->chunk, (unsigned long long)(caller ? cap : gpr_ctx::kMarkCap));
+  }
+  for (uint64_t i = 0; i < no; ++i) opens[i] = base + block[2 + i];
+  for (uint64_t i = 0; i < nc; ++i) closes[i] = base + block[2 + gpr_ctx::kMarkCap + i];
+  std::sort(opens, opens + no);
+  std::sort(closes, closes + nc);
+  *n_opens = no, *n_closes = nc;
+  sp->next = c + 1;
+  sp->consumed.store(c + 1, std::memory_order_release);
+  *bytes_done = std::min<uint64_t>(sp->n, (c + 1) * sp->chunk);
+  *more = 1;
+  if (sp->next >= sp->n_chunks) {
+    *more = 0;
+    return scan_pipe_finish(ctx, true);
+  }
+  return GPR_OK;
+  GPR_CATCH(ctx)
 }
 
 int gpr_text_scan(gpr_ctx* ctx, int32_t slot, const char* text, uint64_t n_bytes, int32_t mem_kind,
                   uint64_t* opens, uint64_t* closes, uint64_t cap, uint64_t* n_opens, uint64_t* n_closes) {
   if (!ctx) return GPR_E_INVALID;
+  GPR_TRY
   NvtxRange nvtx_range("gpr_text_scan");
-  if (slot < 0 || slot > 2) return fail(ctx, GPR_E_INVALID, "text slot %d (0..2)", slot);
-  if ((!text && n_bytes) || !n_opens || !n_closes || (cap && (!opens || !closes)))
-    return fail(ctx, GPR_E_INVALID, "text / output arrays are NULL");
-  if (mem_kind != GPR_MEM_HOST && mem_kind != GPR_MEM_DEVICE) return fail(ctx, GPR_E_INVALID, "bad mem_kind %d", mem_kind);
-  CU(cudaSetDevice(ctx->device));
-  int rc;
-  if ((rc = grow(ctx, &ctx->d_text[slot], &ctx->text_cap[slot], (size_t)n_bytes + gpr::text::kTextPad)) != GPR_OK)
-    return rc;
-  if ((rc = grow(ctx, &ctx->d_marks, &ctx->marks_cap, (size_t)2 * cap + 2)) != GPR_OK) return rc;
-  if (!ctx->d_mark_counts) CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_mark_counts), 2 * sizeof(unsigned long long)));
-  uint8_t* d = ctx->d_text[slot];
-  if ((rc = upload_text(ctx, d, text, n_bytes, mem_kind)) != GPR_OK) return rc;
-  CU(cudaMemsetAsync(d + n_bytes, 0, gpr::text::kTextPad, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_mark_counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  ctx->text_n[slot] = n_bytes;
-  ctx->last_was_reduce = false;
-  unsigned long long counts[2] = {0, 0};
-  if (n_bytes) {
-    const uint64_t slices = (n_bytes + gpr::text::kScanBytes - 1) / gpr::text::kScanBytes;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((slices + 255) / 256, (uint64_t)ctx->sm_count * 32);
-    gpr::text::k_text_scan<<<grid, 256, 0, ctx->stream>>>(d, n_bytes, 0, slices, ctx->d_marks, ctx->d_marks + cap,
-                                                           ctx->d_mark_counts, cap);
-    ctx->launches++;
-    CU(cudaGetLastError());
+  if (!n_opens || !n_closes || (cap && (!opens || !closes))) return fail(ctx, GPR_E_INVALID, "output arrays are NULL");
+  int rc = gpr_text_scan_begin(ctx, slot, text, n_bytes, mem_kind);
+  if (rc != GPR_OK) return rc;
+  std::vector<uint64_t> co(gpr_ctx::kMarkCap), cc(gpr_ctx::kMarkCap);
+  uint64_t no = 0, nc = 0;
+  int32_t more = 1;
+  while (more) {
+    uint64_t a = 0, b = 0, done = 0;
+    rc = gpr_text_scan_next(ctx, co.data(), cc.data(), gpr_ctx::kMarkCap, &a, &b, &done, &more);
+    if (rc != GPR_OK) {
+      scan_pipe_abort(ctx);
+      return rc;
+    }
+    for (uint64_t i = 0; i < a; ++i, ++no)
+      if (no < cap) opens[no] = co[i];
+    for (uint64_t i = 0; i < b; ++i, ++nc)
+      if (nc < cap) closes[nc] = cc[i];
   }
-  CU(cudaMemcpyAsync(counts, ctx->d_mark_counts, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  *n_opens = counts[0], *n_closes = counts[1];
-  const uint64_t no = std::min<uint64_t>(counts[0], cap), nc = std::min<uint64_t>(counts[1], cap);
-  if (no) CU(cudaMemcpyAsync(opens, ctx->d_marks, no * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (nc) CU(cudaMemcpyAsync(closes, ctx->d_marks + cap, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (counts[0] > cap || counts[1] > cap)
-    return fail(ctx, GPR_E_CAPACITY, "%llu / %llu markers, room for %llu: call again with a larger cap", counts[0],
-                counts[1], (unsigned long long)cap);
+  *n_opens = no, *n_closes = nc;
+  if (no > cap || nc > cap)
+    return fail(ctx, GPR_E_CAPACITY, "%llu / %llu markers, room for %llu: call again with a larger cap", (unsigned long long)no,
+                (unsigned long long)nc, (unsigned long long)cap);
   return GPR_OK;
+  GPR_CATCH(ctx)
 }
 
 int gpr_text_parse(gpr_ctx* ctx, int32_t slot, gpr_text_span* spans, uint32_t n_spans, const gpr_text_grid* grid,

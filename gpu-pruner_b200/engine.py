@@ -372,6 +372,20 @@ class IdleEngine:
             self._check(rc)
             return np.sort(opens[:no.value]), np.sort(closes[:nc.value])
 
+    def text_scan_chunks(self, text, slot: int = 0, n_bytes: Optional[int] = None, mem_kind: int = ffi.GPR_MEM_HOST):
+        """generator over the pipelined scan: yields (opens, closes, bytes_done) per 4 MB chunk while later chunks are
+        still being uploaded (gpr_text_scan_begin / gpr_text_scan_next)"""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        n = int(buf.size if n_bytes is None else n_bytes)
+        self._check(self._lib.gpr_text_scan_begin(self._h, slot, _ptr(buf), n, mem_kind))
+        cap = 1 << 14
+        opens, closes = np.empty(cap, np.uint64), np.empty(cap, np.uint64)
+        no, nc, done, more = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_int32(1)
+        while more.value:
+            self._check(self._lib.gpr_text_scan_next(self._h, _ptr(opens), _ptr(closes), cap, C.byref(no), C.byref(nc),
+                                                     C.byref(done), C.byref(more)))
+            yield opens[:no.value].copy(), closes[:nc.value].copy(), done.value
+
     def text_parse(self, spans: np.ndarray, t_end: int, step: int, T: int, n_rows: int, slot: int = 0,
                    plane: int = 0, fill: bool = True, window_seconds: Optional[int] = None,
                    resident: bool = False) -> np.ndarray:

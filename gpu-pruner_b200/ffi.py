@@ -118,6 +118,9 @@ PROTOTYPES = {
     "gpr_get_device_info": (C.c_int, [_P, C.POINTER(gpr_device_info)]),
     "gpr_text_scan": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, C.c_int32, _P, _P, C.c_uint64,
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gpr_text_scan_begin": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, C.c_int32]),
+    "gpr_text_scan_next": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "gpr_text_parse": (C.c_int, [_P, C.c_int32, _P, C.c_uint32, C.POINTER(gpr_text_grid), C.c_int32]),
     "gpr_text_planes": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "gpr_synth_fill": (C.c_int, [_P, C.c_uint64, C.c_int32, _P, C.c_uint64, C.c_uint32,

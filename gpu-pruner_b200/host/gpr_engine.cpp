@@ -167,23 +167,21 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
   void check(int rc, const char* what) {
     if (rc != GPR_OK) throw std::runtime_error(std::string(what) + " (" + std::to_string(rc) + "): " + gpr_last_error(ctx_));
   }
-  void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens, std::vector<uint64_t>* closes) override {
-    // The response sits in ordinary (pageable) memory: cudaMemcpy stages it through the driver's own
-    // pinned buffers.  Copying it into a pinned buffer of ours first costs a second pass over the text
-    // plus, the first time, the page-locking of that buffer — more than it saves for one use of the bytes.
-    // (A caller that receives the response straight into gpr_host_alloc memory gets full PCIe speed.)
-    uint64_t cap = n / 2048 + 4096, no = 0, nc = 0;  // a series is rarely shorter than 2 KB; retried if so
-    while (true) {
-      opens->resize(cap), closes->resize(cap);
-      const int rc = gpr_text_scan(ctx_, slot, text, n, GPR_MEM_HOST, opens->data(), closes->data(), cap, &no, &nc);
-      if (rc == GPR_E_CAPACITY) {
-        cap = std::max(no, nc) + 16;
-        continue;
-      }
-      check(rc, "gpr_text_scan");
-      break;
-    }
+  // The response sits in ordinary (pageable) memory: the library stages it through its pinned ring with a few
+  // producer threads and scans every chunk as it lands (gpr_text_scan_begin / _next); this thread meanwhile turns
+  // the label maps of the series it already has markers for into tensor rows.
+  // (A caller that receives the response straight into gpr_host_alloc memory skips the staging copy.)
+  void scan_begin(int slot, const char* text, size_t n) override {
+    check(gpr_text_scan_begin(ctx_, slot, text, n, GPR_MEM_HOST), "gpr_text_scan_begin");
+  }
+  bool scan_next(std::vector<uint64_t>* opens, std::vector<uint64_t>* closes, uint64_t* bytes_done) override {
+    const uint64_t cap = 1u << 14;  // markers of one kind per chunk the library can report
+    opens->resize(cap), closes->resize(cap);
+    uint64_t no = 0, nc = 0;
+    int32_t more = 0;
+    check(gpr_text_scan_next(ctx_, opens->data(), closes->data(), cap, &no, &nc, bytes_done, &more), "gpr_text_scan_next");
     opens->resize(no), closes->resize(nc);
+    return more != 0;
   }
   void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) override {
     gpr_text_grid g;

@@ -56,52 +56,83 @@ struct SeriesLoc {
   size_t mb, close_brace, vb, list_close;  // label map [mb, close_brace], list [vb, list_close]
 };
 
-// Walk the series of one response using the device's marker lists; labels -> rows through `asg`.
+// Walk the series of one response with the device's marker lists, as they arrive: the upload + scan runs as a
+// pipeline (TextDevice::scan_begin / scan_next) and every series whose markers are in is validated, its label map
+// parsed and its row assigned through `asg` while later chunks of the text are still on their way to the GPU.
 void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool is_power, bool is_prof,
                DeviceIngestReport& rep, bool remember) {
   const std::string& t = *plan.text;
-  std::vector<uint64_t> opens, closes;
-  auto t0 = std::chrono::steady_clock::now();
-  dev.scan(plan.slot, t.data(), t.size(), &opens, &closes);
-  rep.scan_ms += ms_since(t0);
-  t0 = std::chrono::steady_clock::now();
-  std::sort(opens.begin(), opens.end());
-  std::sort(closes.begin(), closes.end());
-  std::vector<SeriesLoc> locs;
-  locs.reserve(opens.size());
-
   size_t at;
   bool bare;
   if (starts_with(t, 0, kHead)) at = sizeof kHead - 1, bare = false;
   else if (starts_with(t, 0, "[")) at = 1, bare = true;
   else throw NotCompact{"response does not start with the compact success/matrix header"};
 
-  size_t walked = 0;
-  if (at < t.size() && t[at] == ']') {
-    ++at;  // empty result
-  } else {
-    while (true) {
+  std::vector<uint64_t> opens, closes, co, cc;  // all markers so far (sorted: chunks come in text order)
+  size_t oi = 0, ci = 0, walked = 0;
+  bool finished = false;  // the closing ']' of the result array has been reached
+  if (at < t.size() && t[at] == ']') ++at, finished = true;  // empty result
+  FlatLabels flat;
+
+  // consume every series that is completely covered by the markers delivered so far
+  auto drain = [&](bool final) {
+    while (!finished) {
       if (!starts_with(t, at, kMetric) || at + sizeof kMetric - 1 >= t.size() || t[at + sizeof kMetric - 1] != '{')
         throw NotCompact{"series does not start with {\"metric\":{"};
       const size_t mb = at + sizeof kMetric - 1;  // '{' of the label map
-      auto vo = std::lower_bound(opens.begin(), opens.end(), (uint64_t)mb);
-      if (vo == opens.end()) throw NotCompact{"label map without a following \"values\" list"};
-      const size_t close_brace = (size_t)*vo;  // '}' of the label map
-      const size_t vb = close_brace + 12;      // first byte after `},"values":[`
+      while (oi < opens.size() && opens[oi] < mb) ++oi;
+      if (oi == opens.size()) {
+        if (final) throw NotCompact{"label map without a following \"values\" list"};
+        return;
+      }
+      const size_t close_brace = (size_t)opens[oi];  // '}' of the label map
+      const size_t vb = close_brace + 12;            // first byte after `},"values":[`
       if (vb >= t.size()) throw NotCompact{"truncated values list"};
       size_t list_close;  // offset of the ']' closing the list
       if (t[vb] == ']') {
         list_close = vb;
       } else {
         if (t[vb] != '[') throw NotCompact{"values list does not start with a sample"};
-        auto vc = std::lower_bound(closes.begin(), closes.end(), (uint64_t)vb);
-        if (vc == closes.end()) throw NotCompact{"unterminated values list"};
-        list_close = (size_t)*vc + 2;
+        while (ci < closes.size() && closes[ci] < vb) ++ci;
+        if (ci == closes.size()) {
+          if (final) throw NotCompact{"unterminated values list"};
+          return;
+        }
+        list_close = (size_t)closes[ci] + 2;
       }
       if (list_close + 1 >= t.size() || t[list_close + 1] != '}')
         throw NotCompact{"series object has members after \"values\""};
-      locs.push_back(SeriesLoc{mb, close_brace, vb, list_close});
-      ++walked;
+      ++oi, ++walked;
+      // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON object
+      // ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and that no series
+      // without a "values" member was jumped over.  (A `},"values":[` inside a label value is impossible: a raw
+      // '"' ends a JSON string.)  Prometheus' own shape — string values, no escapes — is read in place without
+      // allocating (FlatLabels); anything else goes through the DOM parser.
+      const char* b = t.data() + mb;
+      const char* e = t.data() + close_brace + 1;
+      const bool element = list_close != vb;  // an empty list is no element (as in the CPU paths)
+      uint32_t p = 0, slot = 0;
+      Assigner::Result r = Assigner::Skipped;
+      if (flat.parse(b, e)) {
+        ++w.stats.series_in;
+        if (element)
+          r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), flat, is_power, is_prof, &p, &slot)
+                       : asg.assign(flat, is_power, is_prof, &p, &slot);
+      } else {
+        Json metric;
+        try {
+          metric = Json::parse(std::string(b, e));
+        } catch (const std::exception& ex) {
+          throw NotCompact{std::string("label map: ") + ex.what()};
+        }
+        if (!metric.is_object()) throw NotCompact{"label map is not an object"};
+        ++w.stats.series_in;
+        if (element)
+          r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), JsonMetric{metric}, is_power, is_prof, &p, &slot)
+                       : asg.assign(metric, is_power, is_prof, &p, &slot);
+      }
+      if (element && r == Assigner::Placed)
+        plan.series.push_back(DevSeries{p, slot, (uint64_t)vb, (uint64_t)list_close});
       at = list_close + 2;  // past '}'
       if (at < t.size() && t[at] == ',') {
         ++at;
@@ -109,10 +140,38 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
       }
       if (at < t.size() && t[at] == ']') {
         ++at;
+        finished = true;
         break;
       }
       throw NotCompact{"expected ',' or ']' after a series"};
     }
+  };
+
+  auto t0 = std::chrono::steady_clock::now();
+  dev.scan_begin(plan.slot, t.data(), t.size());
+  bool more = true;
+  try {
+    while (more) {
+      uint64_t ready = 0;
+      more = dev.scan_next(&co, &cc, &ready);
+      rep.scan_ms += ms_since(t0);  // time spent waiting for the upload / scan
+      t0 = std::chrono::steady_clock::now();
+      opens.insert(opens.end(), co.begin(), co.end());
+      closes.insert(closes.end(), cc.begin(), cc.end());
+      drain(!more);
+      rep.assign_ms += ms_since(t0);  // series walk + label maps -> rows, overlapped with the upload
+      t0 = std::chrono::steady_clock::now();
+    }
+  } catch (...) {
+    while (more) {  // let the pipeline run to its end: the device slot must not be left half written
+      uint64_t ready = 0;
+      try {
+        more = dev.scan_next(&co, &cc, &ready);
+      } catch (...) {
+        break;
+      }
+    }
+    throw;
   }
   if (walked != opens.size()) throw NotCompact{"values markers outside the series walk"};
   if (!bare) {
@@ -120,42 +179,6 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
     at += 2;
   }
   if (skip_trailing_ws(t, at) != t.size()) throw NotCompact{"trailing bytes after the response"};
-  rep.labels_ms += ms_since(t0);
-  t0 = std::chrono::steady_clock::now();
-
-  // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON
-  // object ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and that
-  // no series without a "values" member was jumped over.  (A `},"values":[` inside a label value is
-  // impossible: a raw '"' ends a JSON string.)  Prometheus' own shape — string values, no escapes —
-  // is read in place without allocating (FlatLabels); anything else goes through the DOM parser.
-  FlatLabels flat;
-  for (const SeriesLoc& loc : locs) {
-    const char* b = t.data() + loc.mb;
-    const char* e = t.data() + loc.close_brace + 1;
-    const bool element = loc.list_close != loc.vb;  // an empty list is no element (as in the CPU paths)
-    uint32_t p = 0, slot = 0;
-    Assigner::Result r = Assigner::Skipped;
-    if (flat.parse(b, e)) {
-      ++w.stats.series_in;
-      if (!element) continue;
-      r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), flat, is_power, is_prof, &p, &slot)
-                   : asg.assign(flat, is_power, is_prof, &p, &slot);
-    } else {
-      Json metric;
-      try {
-        metric = Json::parse(std::string(b, e));
-      } catch (const std::exception& ex) {
-        throw NotCompact{std::string("label map: ") + ex.what()};
-      }
-      if (!metric.is_object()) throw NotCompact{"label map is not an object"};
-      ++w.stats.series_in;
-      if (!element) continue;
-      r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), JsonMetric{metric}, is_power, is_prof, &p, &slot)
-                   : asg.assign(metric, is_power, is_prof, &p, &slot);
-    }
-    if (r == Assigner::Placed) plan.series.push_back(DevSeries{p, slot, (uint64_t)loc.vb, (uint64_t)loc.list_close});
-  }
-  rep.assign_ms += ms_since(t0);
 }
 
 }  // namespace

@@ -18,10 +18,13 @@ namespace gph {
 class TextDevice {
  public:
   virtual ~TextDevice() = default;
-  // upload `text` into resident slot `slot` (0..2) and report the UNSORTED offsets of every
-  // `},"values":[` ('}' position) and `"]]` ('"' position)
-  virtual void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens,
-                    std::vector<uint64_t>* closes) = 0;
+  // Upload `text` into resident slot `slot` (0..2) and scan it for `},"values":[` ('}' position) and `"]]`
+  // ('"' position), as a pipeline: scan_begin starts the upload, every scan_next blocks until the next chunk of
+  // the text has been scanned on the device and returns that chunk's markers (sorted, absolute offsets) and how
+  // much of the text is covered; false with the last chunk.  The host works on the series it already has
+  // markers for while later chunks are still crossing PCIe.
+  virtual void scan_begin(int slot, const char* text, size_t n) = 0;
+  virtual bool scan_next(std::vector<uint64_t>* opens, std::vector<uint64_t>* closes, uint64_t* bytes_done) = 0;
   // parse the samples of `spans` (sorted by begin) of the text in `slot` into plane 0 (util) / 1 (power):
   // samples with grid.t_end - grid.span < ts <= grid.t_end, bucket (t_end - ts) / step, NaN-aware max merge
   struct TextGrid {

@@ -114,9 +114,18 @@ inline void merge_cell(float& cell, float v) {
 }
 
 // ---- label set -> (pod, slot): shared by the DOM and the text path -----------------------------------
+// Hot on the ingest path (40,000 series per C2 tick, while the response is still crossing PCIe), so no
+// per-series allocation and no tree lookups: pods are found through an open-addressing table on a 64-bit
+// hash of (pod, namespace) verified against the stored strings, and a pod's handful of slots by comparing
+// the four group labels directly.
+inline uint64_t hash_bytes(uint64_t h, std::string_view s) {
+  for (unsigned char c : s) h = (h ^ c) * 0x100000001B3ull;  // FNV-1a
+  return (h ^ 0xff) * 0x100000001B3ull;                      // field separator
+}
+
 class Assigner {
  public:
-  explicit Assigner(Window& w) : w_(w) {}
+  explicit Assigner(Window& w) : w_(w) { table_.assign(1024, 0); }
   enum Result { Skipped, Shadowed, Placed };
 
   // Daemon mode: the same series comes back every tick and must keep its row.  A series is identified by the
@@ -154,33 +163,29 @@ class Assigner {
       ++w_.stats.series_skipped;
       return Skipped;
     }
-    key_.assign(std::to_string(pod.size())).append(1, ':').append(pod).append(ns);  // unambiguous (pod, ns)
-    auto it = pod_index_.find(key_);
-    uint32_t p;
-    if (it == pod_index_.end()) {
-      p = (uint32_t)w_.pods.size();
-      pod_index_[key_] = p;
-      w_.pods.push_back(PodEntry{std::string(pod), std::string(ns), {}, 0});
-      slot_index_.emplace_back();
-      pslot_index_.emplace_back();
-    } else {
-      p = it->second;
-    }
+    const uint32_t p = find_or_add_pod(pod, ns);
     m.str("Hostname", &host), m.str("gpu", &gpu);   // absent / non-string: ""
     // `sum by (Hostname, container, pod, namespace, gpu, modelName)` groups (query.promql.j2:9)
-    gkey_.assign(host).append(1, '\x1f').append(ctr).append(1, '\x1f').append(gpu).append(1, '\x1f').append(model);
     uint32_t slot;
     if (is_power) {
       // every power series is its own row: `unless on (pod, namespace)` looks at each series' max
-      // (query.promql.j2:36-44), there is no `sum by` on that side
-      auto& idx = pslot_index_[p];
-      if (!idx.emplace(gkey_, 0u).second) ++w_.stats.duplicates_merged;
+      // (query.promql.j2:36-44), there is no `sum by` on that side; the group key only feeds the statistic
+      const uint64_t gk = hash_bytes(hash_bytes(hash_bytes(hash_bytes(0xcbf29ce484222325ull, host), ctr), gpu), model);
+      std::vector<uint64_t>& seen = power_keys_[p];
+      if (std::find(seen.begin(), seen.end(), gk) != seen.end()) ++w_.stats.duplicates_merged;
+      else seen.push_back(gk);
       slot = w_.pods[p].power_slots++;
     } else {
-      auto& idx = slot_index_[p];
-      auto f = idx.find(gkey_);
-      const bool fresh = f == idx.end();
-      const uint32_t group = fresh ? (uint32_t)w_.pods[p].slots.size() : f->second;
+      std::vector<GpuSlot>& slots = w_.pods[p].slots;
+      uint32_t group = (uint32_t)slots.size();
+      for (uint32_t i = 0; i < slots.size(); ++i) {
+        const GpuSlot& g = slots[i];
+        if (g.group == i && g.gpu == gpu && g.hostname == host && g.container == ctr && g.model == model) {
+          group = i;
+          break;
+        }
+      }
+      const bool fresh = group == slots.size();
       // `A or B` (query.promql.j2:10-20) matches on the FULL label set: a UTIL element is dropped only
       // if a PROF element with identical labels exists; series that differ in any other label both
       // survive the `or` and are then added up by `sum by`
@@ -197,7 +202,7 @@ class Assigner {
       };
       if (is_prof) {
         prof_sigs_[std::make_pair(p, group)].push_back(signature());
-      } else {
+      } else if (!prof_sigs_.empty()) {
         auto ps = prof_sigs_.find(std::make_pair(p, group));
         if (ps != prof_sigs_.end()) {
           const std::string sig = signature();
@@ -206,15 +211,13 @@ class Assigner {
         }
       }
       // every series keeps its own row; members of one `sum by` group are tied together by `group`
-      slot = (uint32_t)w_.pods[p].slots.size();
-      if (fresh) idx[gkey_] = slot;
-      GpuSlot g;
-      g.hostname = std::string(host), g.container = std::string(ctr), g.gpu = std::string(gpu);
-      g.model = std::string(model);
+      slot = (uint32_t)slots.size();
+      slots.emplace_back();
+      GpuSlot& g = slots.back();
+      g.hostname.assign(host), g.container.assign(ctr), g.gpu.assign(gpu), g.model.assign(model);
       g.node_type = "unknown";  // lib.rs:176-179; the node_dmi_info join fills it in (apply_node_types)
       g.from_prof = is_prof;
       g.group = group;
-      w_.pods[p].slots.push_back(g);
       if (!fresh) w_.pods[p].has_groups = true, ++w_.stats.duplicates_merged;
     }
     *pod_out = p, *slot_out = slot;
@@ -222,6 +225,33 @@ class Assigner {
   }
 
  private:
+  uint32_t find_or_add_pod(std::string_view pod, std::string_view ns) {
+    const uint64_t h = hash_bytes(hash_bytes(0xcbf29ce484222325ull, pod), ns);
+    size_t mask = table_.size() - 1, i = (size_t)(h ^ (h >> 32)) & mask;
+    for (;; i = (i + 1) & mask) {
+      const uint32_t e = table_[i];
+      if (e == 0) break;
+      if (pod_hash_[e - 1] == h && w_.pods[e - 1].name == pod && w_.pods[e - 1].ns == ns) return e - 1;
+    }
+    const uint32_t p = (uint32_t)w_.pods.size();
+    w_.pods.emplace_back();
+    w_.pods.back().name.assign(pod), w_.pods.back().ns.assign(ns);
+    pod_hash_.push_back(h);
+    power_keys_.emplace_back();
+    table_[i] = p + 1;
+    if ((size_t)(p + 1) * 2 > table_.size()) {  // keep the load factor below 1/2
+      std::vector<uint32_t> bigger(table_.size() * 4, 0);
+      mask = bigger.size() - 1;
+      for (uint32_t q = 0; q <= p; ++q) {
+        size_t j = (size_t)(pod_hash_[q] ^ (pod_hash_[q] >> 32)) & mask;
+        while (bigger[j]) j = (j + 1) & mask;
+        bigger[j] = q + 1;
+      }
+      table_.swap(bigger);
+    }
+    return p;
+  }
+
   struct Known {
     Result result;
     uint32_t pod, slot;
@@ -229,10 +259,9 @@ class Assigner {
   std::unordered_map<std::string, Known> known_;
   std::string key_raw_;
   Window& w_;
-  std::unordered_map<std::string, uint32_t> pod_index_;
-  std::string key_, gkey_;
-  std::vector<std::map<std::string, uint32_t>> slot_index_;   // per pod: group key -> util slot
-  std::vector<std::map<std::string, uint32_t>> pslot_index_;  // per pod: group key -> power slot
+  std::vector<uint32_t> table_;                    // open addressing: pod index + 1, 0 = empty
+  std::vector<uint64_t> pod_hash_;                 // per pod
+  std::vector<std::vector<uint64_t>> power_keys_;  // per pod: group-key hashes of its power series (statistic only)
   std::map<std::pair<uint32_t, uint32_t>, std::vector<std::string>> prof_sigs_;
 };
 

@@ -354,6 +354,17 @@ typedef struct gpr_text_grid {
 GPR_API int gpr_text_scan(gpr_ctx *ctx, int32_t slot, const char *text, uint64_t n_bytes,
                           int32_t mem_kind, uint64_t *opens, uint64_t *closes, uint64_t cap,
                           uint64_t *n_opens, uint64_t *n_closes);
+/* The same, as a pipeline the caller can work alongside: gpr_text_scan_begin starts the upload (producer threads
+ * owned by the library) and returns; every gpr_text_scan_next blocks until the next chunk of the text (2 MB; 16 MB
+ * for pinned text) has landed and been scanned and returns that chunk's markers (sorted; room for `cap` of each
+ * kind — 16,384 always suffices) together with *bytes_done = how much of the text is covered so far.  *more = 0 with the last chunk
+ * (or at once for an empty text); the scan is then complete and the text ready for gpr_text_parse.  Between the
+ * calls the caller can already walk the series whose markers it has (gpu-pruner_b200/host/ingest_device.cpp turns
+ * label maps into tensor rows while later chunks are still crossing PCIe).  Dropped by the next
+ * gpr_text_scan_begin / gpr_text_scan / gpr_destroy if not run to the end.  `text` must stay valid until then. */
+GPR_API int gpr_text_scan_begin(gpr_ctx *ctx, int32_t slot, const char *text, uint64_t n_bytes, int32_t mem_kind);
+GPR_API int gpr_text_scan_next(gpr_ctx *ctx, uint64_t *opens, uint64_t *closes, uint64_t cap, uint64_t *n_opens,
+                               uint64_t *n_closes, uint64_t *bytes_done, int32_t *more);
 /* Parse the samples of spans[0..n_spans) (host array, sorted by begin, non-overlapping) of the text in
  * `slot` into plane `plane` (0 = util, 1 = power).  Out-fields of the spans are filled.  Blocking.  */
 GPR_API int gpr_text_parse(gpr_ctx *ctx, int32_t slot, gpr_text_span *spans, uint32_t n_spans,

@@ -28,20 +28,33 @@ namespace {
 
 class EmulDevice : public TextDevice {
  public:
-  void scan(int slot, const char* text, size_t n, std::vector<uint64_t>* opens,
-            std::vector<uint64_t>* closes) override {
+  // the pipelined scan, in chunks far smaller than the device's 4 MB so that series and marker patterns straddle
+  // chunk borders all the time
+  void scan_begin(int slot, const char* text, size_t n) override {
     std::vector<uint8_t>& t = text_[slot];
     t.assign(n + tx::kTextPad, 0);
     memcpy(t.data(), text, n);
     n_[slot] = n;
+    scan_slot_ = slot, scan_pos_ = 0;
+  }
+  bool scan_next(std::vector<uint64_t>* opens, std::vector<uint64_t>* closes, uint64_t* bytes_done) override {
+    opens->clear(), closes->clear();
+    const std::vector<uint8_t>& t = text_[scan_slot_];
+    const uint64_t n = n_[scan_slot_];
     struct Sink {
       std::vector<uint64_t>*o, *c;
       void values_open(uint64_t p) { o->push_back(p); }
       void values_close(uint64_t p) { c->push_back(p); }
     } sink{opens, closes};
-    const uint64_t slices = (n + tx::kScanBytes - 1) / tx::kScanBytes;
+    const uint64_t end = std::min<uint64_t>(n, scan_pos_ + kEmulChunk);
+    const uint64_t s0 = scan_pos_ / tx::kScanBytes, s1 = (end + tx::kScanBytes - 1) / tx::kScanBytes;
     // reversed slice order: nothing may depend on the order threads run in
-    for (uint64_t s = slices; s-- > 0;) tx::scan_slice(t.data(), (uint64_t)n, s, sink);
+    for (uint64_t s = s1; s-- > s0;) tx::scan_slice(t.data(), n, s, sink);
+    std::sort(opens->begin(), opens->end());
+    std::sort(closes->begin(), closes->end());
+    scan_pos_ = end;
+    *bytes_done = end;
+    return end < n;
   }
 
   void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) override {
@@ -120,8 +133,11 @@ class EmulDevice : public TextDevice {
   bool has_ring_power() const { return !ring_[1].empty(); }
 
  private:
+  static constexpr uint64_t kEmulChunk = 1024;   // a multiple of the scan slice
   std::vector<uint8_t> text_[3];
   uint64_t n_[3] = {0, 0, 0};
+  int scan_slot_ = 0;
+  uint64_t scan_pos_ = 0;
   std::vector<uint32_t> plane_[2];   // f32 bit patterns (cells start as 0xFFFFFFFF, like the device planes)
   std::vector<uint32_t> ring_[2];    // the resident window of daemon mode: [rows][T], a ring over the time axis
   uint32_t ring_T_ = 0, ring_head_ = 0, ring_rows_ = 0;

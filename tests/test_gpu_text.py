@@ -299,8 +299,9 @@ def test_parsed_planes_feed_the_decision_kernels(eng, oracle_c):
 
 
 def test_upload_paths_deliver_the_same_bytes(eng):
-    """pageable text goes up through a threaded pinned ring, pinned text and GPR_TEXT_UPLOAD_THREADS=0 through
-    plain copies: same markers, same tensor"""
+    """pageable text goes up through the threaded pinned ring (8 producers by default, 1 with
+    GPR_TEXT_UPLOAD_THREADS=1), pinned text without staging: same markers, same tensor — and the chunk-by-chunk
+    form of the scan (gpr_text_scan_begin / _next) reports the same markers, in text order, with monotone coverage"""
     import gpu_pruner_b200 as g
     lib = H.lib()
     lib.gph_synth_response.restype = C.c_longlong
@@ -323,7 +324,7 @@ def test_upload_paths_deliver_the_same_bytes(eng):
 
     o1, c1, s1, p1 = run(eng, pageable)
     o2, c2, s2, p2 = run(eng, pinned, k)
-    os.environ["GPR_TEXT_UPLOAD_THREADS"] = "0"
+    os.environ["GPR_TEXT_UPLOAD_THREADS"] = "1"
     try:
         with g.IdleEngine(device=0) as plain:
             o3, c3, s3, p3 = run(plain, pageable)
@@ -334,6 +335,17 @@ def test_upload_paths_deliver_the_same_bytes(eng):
     assert int(s1["n_in"].sum()) == P * G * n and not np.any(s1["flags"] & 2)
     assert np.array_equal(s1, s2) and np.array_equal(s1, s3)
     assert np.array_equal(p1, p2) and np.array_equal(p1, p3) and not np.isnan(p1).any()
+    po, pc, last = [], [], 0
+    for o, c, done in eng.text_scan_chunks(pageable):
+        assert done > last and (len(o) == 0 or (o.min() >= last - 16 and o.max() < done))
+        po.append(o), pc.append(c)
+        last = done
+    assert last == k and np.array_equal(np.concatenate(po), o1) and np.array_equal(np.concatenate(pc), c1)
+    # an abandoned scan is dropped by the next one
+    it = eng.text_scan_chunks(pageable)
+    next(it)
+    o4, c4 = eng.text_scan(pinned, n_bytes=k)
+    assert np.array_equal(o4, o1) and np.array_equal(c4, c1)
 
 
 def test_error_paths(eng):
