@@ -433,8 +433,9 @@ GPH_API long long gph_synth_response(unsigned P, unsigned G, unsigned n, long lo
       const bool idle = hs % 100 < 60;
       for (unsigned i = 0; i < n; ++i) {
         if (i) *p++ = ',';
-        *p++ = '[', num((unsigned long long)(t_end - (long long)n + 1 + i)), lit(",\"");
-        const unsigned long long hc = mix(hs ^ i);
+        const unsigned long long t_abs = (unsigned long long)(t_end - (long long)n + 1 + i);
+        *p++ = '[', num(t_abs), lit(",\"");
+        const unsigned long long hc = mix(hs ^ t_abs);  // a function of absolute time: slices of one timeline agree
         num(idle ? 0 : ((hc >> 10) & 1 ? 1 + (hc >> 11) % 100 : 0));
         lit("\"]");
       }

@@ -33,7 +33,7 @@ std::string usage() {
       "      --power-threshold <POWER_THRESHOLD>    Power draw threshold in watts (veto for idle candidates)\n"
       "      --honor-labels                         ServiceMonitor uses honorLabels: true (pod/namespace/container labels)\n"
       "  -r, --run-mode <RUN_MODE>                  [default: dry-run] [possible values: scale-down, dry-run]\n"
-      "      --prometheus-url <PROMETHEUS_URL>      Prometheus URL; this build also accepts file://DIR and synthetic://P,G,T[,SEED]\n"
+      "      --prometheus-url <PROMETHEUS_URL>      Prometheus URL; this build reads recorded range-query responses from file://DIR\n"
       "      --prometheus-token <PROMETHEUS_TOKEN>  Prometheus token (accepted for compatibility)\n"
       "      --prometheus-tls-mode <MODE>           [default: verify] [possible values: skip, verify]\n"
       "      --prometheus-tls-cert <CERT>           Custom .crt file to use for TLS verification\n"

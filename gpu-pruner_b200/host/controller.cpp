@@ -95,10 +95,26 @@ class FileSource : public WindowSource {
   Window load(const Cli& args, const std::string& d, int64_t slice_seconds, bool resident) {
     const std::string up = d + "/util.json";
     if (!file_exists(up)) throw std::runtime_error("Failed to run query! " + up + " not found");
-    auto slurp = [](const std::string& path) {
-      std::ifstream f(path, std::ios::binary);
+    // a recorded response can be more than a gigabyte: one sized read, not a character iterator
+    const auto read_t0 = std::chrono::steady_clock::now();
+    uint64_t read_bytes = 0;
+    auto slurp = [&read_bytes](const std::string& path) {
+      FILE* f = fopen(path.c_str(), "rb");
       if (!f) throw std::runtime_error("cannot open " + path);
-      std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      std::string s;
+      struct stat st;
+      if (fstat(fileno(f), &st) == 0 && st.st_size > 0) s.resize((size_t)st.st_size);
+      size_t got = 0;
+      while (got < s.size()) {
+        const size_t k = fread(&s[got], 1, s.size() - got, f);
+        if (k == 0) break;
+        got += k;
+      }
+      s.resize(got);
+      char tail[4096];  // a file that grew after fstat (or has no size): read on
+      for (size_t k; (k = fread(tail, 1, sizeof tail, f)) > 0;) s.append(tail, k);
+      fclose(f);
+      read_bytes += s.size();
       return s;
     };
     const std::string util = slurp(up);
@@ -116,6 +132,12 @@ class FileSource : public WindowSource {
     }
     opt.slice_seconds = slice_seconds;
     opt.resident = resident;
+    if (log_) {
+      char rbuf[160];
+      snprintf(rbuf, sizeof rbuf, "Recorded responses read from %s: %.1f MB in %.1f ms", d.c_str(), read_bytes / 1e6,
+               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - read_t0).count());
+      log_->info(rbuf);
+    }
     Window w;
     if (!ingestor_) {
       w = ingest_matrix_text(util, pprof, ppower, opt);
@@ -355,14 +377,22 @@ int Controller::run(WindowSource& src) {
       next_tick += std::chrono::seconds(args_.check_interval);
     }
     TickResult tr;
+    const auto tick_t0 = std::chrono::steady_clock::now();
+    double fetch_ms = 0;
     try {
       Window w = src.fetch(args_);
+      fetch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tick_t0).count();
       tr = run_query_and_scale(w);
     } catch (const std::exception& e) {
       tr.ok = false;
       tr.error = e.what();
     }
     if (tr.ok) {
+      const double tick_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tick_t0).count();
+      char tbuf[200];
+      snprintf(tbuf, sizeof tbuf, "Tick %d: window ready in %.2f ms, verdict and gates in %.2f ms (decision kernels %.3f ms)", ticks,
+               fetch_ms, tick_ms - fetch_ms, tr.kernel_ms);
+      log_.info(tbuf);
       consecutive_failures = 0;
       ++query_successes;
       log_.counter("INFO", "monotonic_counter.query_successes", 1, "Query succeeded");

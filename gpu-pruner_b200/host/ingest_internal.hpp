@@ -131,18 +131,37 @@ class Assigner {
   // Daemon mode: the same series comes back every tick and must keep its row.  A series is identified by the
   // bytes of its label map as the server prints them (sorted keys, so the text is canonical) plus the plane it
   // feeds; known series skip the label work altogether.
+  // (identity = two independent 64-bit hashes of those bytes: 128 bits, no copy of the label text is kept)
   template <typename M>
   Result assign_remembered(std::string_view raw_labels, const M& m, bool is_power, bool is_prof, uint32_t* pod_out,
                            uint32_t* slot_out) {
-    key_raw_.assign(1, is_power ? 'W' : (is_prof ? 'P' : 'U')).append(raw_labels);
-    auto it = known_.find(key_raw_);
-    if (it != known_.end()) {
-      *pod_out = it->second.pod, *slot_out = it->second.slot;
-      if (it->second.result == Skipped) ++w_.stats.series_skipped;
-      return it->second.result;
+    const uint64_t tag = is_power ? 0x57 : (is_prof ? 0x50 : 0x55);
+    uint64_t h1, h2;
+    hash128(raw_labels, tag, &h1, &h2);
+    if (known_.empty()) known_.assign(4096, Known{0, 0, Skipped, 0, 0});
+    size_t mask = known_.size() - 1, i = (size_t)h1 & mask;
+    for (;; i = (i + 1) & mask) {
+      const Known& k = known_[i];
+      if (k.h1 == 0 && k.h2 == 0) break;
+      if (k.h1 == h1 && k.h2 == h2) {
+        *pod_out = k.pod, *slot_out = k.slot;
+        if (k.result == Skipped) ++w_.stats.series_skipped;
+        return k.result;
+      }
     }
     const Result r = assign(m, is_power, is_prof, pod_out, slot_out);
-    known_.emplace(key_raw_, Known{r, *pod_out, *slot_out});
+    known_[i] = Known{h1, h2, r, *pod_out, *slot_out};
+    if (++n_known_ * 2 > known_.size()) {
+      std::vector<Known> bigger(known_.size() * 4, Known{0, 0, Skipped, 0, 0});
+      mask = bigger.size() - 1;
+      for (const Known& k : known_) {
+        if (k.h1 == 0 && k.h2 == 0) continue;
+        size_t j = (size_t)k.h1 & mask;
+        while (bigger[j].h1 || bigger[j].h2) j = (j + 1) & mask;
+        bigger[j] = k;
+      }
+      known_.swap(bigger);
+    }
     return r;
   }
 
@@ -253,11 +272,36 @@ class Assigner {
   }
 
   struct Known {
+    uint64_t h1, h2;  // both zero = empty (hash128 never returns that pair)
     Result result;
     uint32_t pod, slot;
   };
-  std::unordered_map<std::string, Known> known_;
-  std::string key_raw_;
+  // two multiply-mix hashes over 8-byte words with different seeds and multipliers
+  static void hash128(std::string_view s, uint64_t tag, uint64_t* h1, uint64_t* h2) {
+    uint64_t a = 0x9E3779B97F4A7C15ull ^ tag, b = 0xC2B2AE3D27D4EB4Full + tag;
+    const char* p = s.data();
+    size_t n = s.size();
+    auto mix = [](uint64_t x, uint64_t m) {
+      x *= m;
+      return x ^ (x >> 29);
+    };
+    for (; n >= 8; p += 8, n -= 8) {
+      uint64_t w;
+      memcpy(&w, p, 8);
+      a = mix(a ^ w, 0xD6E8FEB86659FD93ull);
+      b = mix(b + w, 0xA0761D6478BD642Full) ^ (b << 7);
+    }
+    uint64_t w = 0;
+    memcpy(&w, p, n);
+    w |= (uint64_t)s.size() << 56;
+    a = mix(a ^ w, 0xD6E8FEB86659FD93ull);
+    b = mix(b + w, 0xA0761D6478BD642Full) ^ (b << 7);
+    a = mix(a, 0xFF51AFD7ED558CCDull), b = mix(b, 0xC4CEB9FE1A85EC53ull);
+    if (a == 0 && b == 0) b = 1;
+    *h1 = a, *h2 = b;
+  }
+  std::vector<Known> known_;  // open addressing
+  size_t n_known_ = 0;
   Window& w_;
   std::vector<uint32_t> table_;                    // open addressing: pod index + 1, 0 = empty
   std::vector<uint64_t> pod_hash_;                 // per pod
