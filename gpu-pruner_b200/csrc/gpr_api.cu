@@ -401,7 +401,8 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   if (res->out_mem_kind != GPR_MEM_HOST && res->out_mem_kind != GPR_MEM_DEVICE)
     return fail(ctx, GPR_E_INVALID, "bad out_mem_kind %d", res->out_mem_kind);
   if (G == 0 || T == 0) return fail(ctx, GPR_E_INVALID, "n_gpus and n_samples must be > 0");
-  if (G > 32) return fail(ctx, GPR_E_UNSUPPORTED, "n_gpus %u > 32 GPUs per pod is not supported", G);
+  if (G > 256) return fail(ctx, GPR_E_UNSUPPORTED, "n_gpus %u > 256 series slots per pod is not supported", G);
+  const uint32_t MW = (G + 31u) / 32u;  // mask words per pod
   if (ld < T) return fail(ctx, GPR_E_INVALID, "row_stride %llu < n_samples %u",
                           (unsigned long long)ld, T);
   if (P > 0 && !util) return fail(ctx, GPR_E_INVALID, "util is NULL");
@@ -446,7 +447,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   }
   for (int k = 0; k < 2; ++k) {
     const size_t cap_before = ctx->masks_cap[k];
-    if ((rc = grow(ctx, &ctx->d_masks[k], &ctx->masks_cap[k], (size_t)2 * P + 16)) != GPR_OK) return rc;
+    if ((rc = grow(ctx, &ctx->d_masks[k], &ctx->masks_cap[k], (size_t)2 * P * MW + 16)) != GPR_OK) return rc;
     if (ctx->masks_cap[k] != cap_before || ctx->masks_dirty) {
       CU(cudaMemsetAsync(ctx->d_masks[k], 0, ctx->masks_cap[k] * sizeof(uint32_t), ctx->stream));
       ctx->last_was_reduce = false;
@@ -508,7 +509,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
 
   gpr::FoldParams fp;
   fp.idle_mask = masks;
-  fp.veto_mask = use_power ? masks + P : nullptr;
+  fp.veto_mask = use_power ? masks + (size_t)P * MW : nullptr;
   fp.eligible = d_elig;
   fp.created = d_created;
   fp.cutoff = win->cutoff_ts;
@@ -530,6 +531,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   fp.prev_need = ctx->uses[sset ^ 1u];
   fp.P = P;
   fp.G = G;
+  fp.mw = MW;
   fp.world = 1, fp.rank = 0;
   fp.exchange_debug = 0;
   if (fused) {
@@ -550,6 +552,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   memset(&rp, 0, sizeof rp);
   rp.T = T;
   rp.G = G;
+  rp.mw = MW;
   rp.thr = threshold_f32(win->power_threshold);
   rp.done = fp.done;
   rp.need = fp.need;
@@ -566,7 +569,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
     // ---- device-resident window: one reduce launch + the PDL-chained fold -------------------
     rp.ld = ld;
     rp.seg[0] = gpr::Segment{util, masks, smax_dev, S, 0u};
-    rp.seg[1] = gpr::Segment{power, masks + P, nullptr, use_power ? S : 0u, 1u};
+    rp.seg[1] = gpr::Segment{power, masks + (size_t)P * MW, nullptr, use_power ? S : 0u, 1u};
     rp.total_rows = S + (use_power ? S : 0u);
     rp.util_u8 = u8 ? 1u : 0u;
     const bool tma_ok = (T % 4u) == 0 && (ld % 4u) == 0 && aligned16(util) &&
@@ -614,9 +617,9 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       cudaEvent_t ev = ctx->ev_chunk[c % kMaxChunkEvents];
       CU(cudaEventRecord(ev, ctx->copy_stream));
       CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
-      rp.seg[0] = gpr::Segment{du, masks + p0, smax_dev ? smax_dev + row0 : nullptr,
+      rp.seg[0] = gpr::Segment{du, masks + (size_t)p0 * MW, smax_dev ? smax_dev + row0 : nullptr,
                                (uint32_t)n_rows, 0u};
-      rp.seg[1] = gpr::Segment{dp, masks + P + p0, nullptr,
+      rp.seg[1] = gpr::Segment{dp, masks + ((size_t)P + p0) * MW, nullptr,
                                use_power ? (uint32_t)n_rows : 0u, 1u};
       rp.total_rows = (uint32_t)n_rows * (use_power ? 2u : 1u);
       if ((rc = launch_reduce(ctx, rp, tma_ok, false)) != GPR_OK) return rc;

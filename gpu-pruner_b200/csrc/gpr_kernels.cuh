@@ -38,9 +38,9 @@ constexpr int kMaxPeers = 8;  // one NVSwitch box
 
 struct Segment {
   const float* base;   // first row of this segment (device)
-  uint32_t* mask;      // per-pod bitmask, bit g set when series (pod, g) is flagged:
-                       //   util plane -> idle_s = (max == 0), power plane -> veto_s = (max >= thr)
-                       // indexed by (first_pod + local_row / G); zero between calls (the fold
+  uint32_t* mask;      // per-pod bitmask (MW = ceil(G / 32) words per pod), bit g set when series (pod, g) is
+                       // flagged: util plane -> idle_s = (max == 0), power plane -> veto_s = (max >= thr);
+                       // word (first_pod + local_row / G) * MW + g / 32; zero between calls (the fold
                        // clears every word it reads)
   float* smax;         // optional per-row window max (util segment only)
   uint32_t n_rows;
@@ -66,6 +66,7 @@ struct FoldParams {
   unsigned long long prev_need;         // ... and the value it must have reached (previous decision
                                         // folded) before this fold may write the caller's outputs
   uint32_t P, G;
+  uint32_t mw;                // mask words per pod = ceil(G / 32)
   // ---- fused bitmap exchange over NVLink peer memory (world > 1, gpr_p2p_*) -------------------
   // Instead of a separate collective launch, the folding CTA stores this rank's packed words
   // straight into every peer's gather buffer, raises a per-source step flag on each peer with
@@ -100,6 +101,7 @@ struct ReduceParams {
   uint64_t ld;        // elements between rows
   uint32_t T;
   uint32_t G;         // rows per pod
+  uint32_t mw;        // mask words per pod = ceil(G / 32)
   uint32_t total_rows;
   float thr;          // smallest f32 >= (double) power threshold
   const unsigned long long* done;  // scratch-set guard, see wait_scratch_free
@@ -220,10 +222,17 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
     uint8_t elig[BATCH];
     long long created[BATCH];
 #pragma unroll
+    uint32_t n_idle[BATCH];
     for (int b = 0; b < BATCH; ++b) {
       const uint32_t pod = min((w0 + b * w_step) * 32u + lane, last_pod);
-      idle[b] = __ldcg(f.idle_mask + pod);
-      veto[b] = f.veto_mask ? __ldcg(f.veto_mask + pod) : 0u;
+      idle[b] = __ldcg(f.idle_mask + (size_t)pod * f.mw);
+      veto[b] = f.veto_mask ? __ldcg(f.veto_mask + (size_t)pod * f.mw) : 0u;
+      n_idle[b] = __popc(idle[b]);
+      for (uint32_t k = 1; k < f.mw; ++k) {  // pods with more than 32 series slots: further mask words
+        const uint32_t x = __ldcg(f.idle_mask + (size_t)pod * f.mw + k);
+        idle[b] |= x, n_idle[b] += __popc(x);
+        if (f.veto_mask) veto[b] |= __ldcg(f.veto_mask + (size_t)pod * f.mw + k);
+      }
       elig[b] = f.eligible ? f.eligible[pod] : (uint8_t)1;
       created[b] = f.created ? f.created[pod] : (long long)0x8000000000000000ll;
     }
@@ -238,12 +247,14 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
       const uint32_t cw = __ballot_sync(0xffffffffu, cand);
       const uint32_t dw = __ballot_sync(0xffffffffu, dec);
       const uint32_t vw = __ballot_sync(0xffffffffu, valid && veto[b] != 0u);
-      uint32_t ns = cand ? __popc(idle[b]) : 0;
+      uint32_t ns = cand ? n_idle[b] : 0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
       if (valid) {  // leave the scratch zeroed for the next call
-        if (idle[b]) f.idle_mask[pod] = 0u;
-        if (veto[b]) f.veto_mask[pod] = 0u;
+        for (uint32_t k = 0; k < f.mw; ++k) {
+          if (idle[b]) f.idle_mask[(size_t)pod * f.mw + k] = 0u;
+          if (veto[b]) f.veto_mask[(size_t)pod * f.mw + k] = 0u;
+        }
       }
       if (lane == 0) {
         f.dbits[w] = dw;
@@ -406,7 +417,10 @@ __device__ __forceinline__ void publish_row(const ReduceParams& p, uint32_t seg,
   // util: `== 0` (NaN fails, -0.0 passes); power: `>= T` (NaN fails)
   const bool flag = is_power ? (m >= p.thr) : (m == 0.0f);
   // fire-and-forget RED at L2; unflagged rows write nothing at all
-  if (flag) atomicOr(mask + local / p.G, 1u << (local % p.G));
+  if (flag) {
+    const uint32_t g = local % p.G;
+    atomicOr(mask + (size_t)(local / p.G) * p.mw + (g >> 5), 1u << (g & 31u));
+  }
   if (smax) smax[local] = m;
 }
 

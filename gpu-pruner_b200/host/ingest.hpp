@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <string>
@@ -31,6 +32,39 @@ struct PodEntry {
   bool has_groups = false;           // some `sum by` group of this pod has more than one series
 };
 
+// The pod table of a window.  Copy-on-write: daemon mode hands the controller a Window every tick while the
+// ingest session keeps the table for the next one — copying a Window shares the table (10,000 pods x a dozen
+// strings would otherwise be duplicated and freed every tick), and whoever writes to a shared table gets its own.
+class PodList {
+ public:
+  size_t size() const { return v_ ? v_->size() : 0; }
+  bool empty() const { return size() == 0; }
+  const PodEntry& operator[](size_t i) const { return (*v_)[i]; }
+  PodEntry& operator[](size_t i) { return mut()[i]; }
+  const PodEntry* begin() const { return v_ ? v_->data() : nullptr; }
+  const PodEntry* end() const { return v_ ? v_->data() + v_->size() : nullptr; }
+  PodEntry* begin() { return mut().data(); }
+  PodEntry* end() {
+    std::vector<PodEntry>& v = mut();
+    return v.data() + v.size();
+  }
+  PodEntry& emplace_back() {
+    mut().emplace_back();
+    return v_->back();
+  }
+  void push_back(PodEntry e) { mut().push_back(std::move(e)); }
+  PodEntry& back() { return mut().back(); }
+  const PodEntry& back() const { return v_->back(); }
+
+ private:
+  std::vector<PodEntry>& mut() {
+    if (!v_) v_ = std::make_shared<std::vector<PodEntry>>();
+    else if (v_.use_count() > 1) v_ = std::make_shared<std::vector<PodEntry>>(*v_);
+    return *v_;
+  }
+  std::shared_ptr<std::vector<PodEntry>> v_;
+};
+
 struct IngestStats {
   uint64_t series_in = 0, series_skipped = 0, samples_in = 0, samples_out_of_window = 0,
            duplicates_merged = 0, tiny_values_clamped = 0;
@@ -42,7 +76,7 @@ struct Window {
   // seconds.  A sample is inside iff t_end - span < ts <= t_end (the [Nm] selector evaluated at t_end,
   // left-open); column c holds the bucket (t_end - (T-c)*step, t_end - (T-1-c)*step], T = ceil(span/step)
   int64_t t_end = 0, step = 1, span = 0;
-  std::vector<PodEntry> pods;
+  PodList pods;
   std::vector<float> util;            // [P][G][T], NaN = no sample
   std::vector<float> power;           // empty, or [P][G][T]
   // device-resident planes (ingest_matrix_device): util / power above are empty then

@@ -113,11 +113,15 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
       const bool element = list_close != vb;  // an empty list is no element (as in the CPU paths)
       uint32_t p = 0, slot = 0;
       Assigner::Result r = Assigner::Skipped;
-      if (flat.parse(b, e)) {
+      const std::string_view raw(b, (size_t)(e - b));
+      if (remember && element && asg.lookup_known(raw, is_power, is_prof, &r, &p, &slot)) {
+        ++w.stats.series_in;  // a series of an earlier tick: same bytes, same row, nothing to parse
+      } else if (flat.parse(b, e)) {
         ++w.stats.series_in;
-        if (element)
-          r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), flat, is_power, is_prof, &p, &slot)
-                       : asg.assign(flat, is_power, is_prof, &p, &slot);
+        if (element) {
+          r = asg.assign(flat, is_power, is_prof, &p, &slot);
+          if (remember) asg.remember(r, p, slot);
+        }
       } else {
         Json metric;
         try {
@@ -127,9 +131,10 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
         }
         if (!metric.is_object()) throw NotCompact{"label map is not an object"};
         ++w.stats.series_in;
-        if (element)
-          r = remember ? asg.assign_remembered(std::string_view(b, (size_t)(e - b)), JsonMetric{metric}, is_power, is_prof, &p, &slot)
-                       : asg.assign(metric, is_power, is_prof, &p, &slot);
+        if (element) {
+          r = asg.assign(metric, is_power, is_prof, &p, &slot);
+          if (remember) asg.remember(r, p, slot);
+        }
       }
       if (element && r == Assigner::Placed)
         plan.series.push_back(DevSeries{p, slot, (uint64_t)vb, (uint64_t)list_close});

@@ -132,28 +132,29 @@ class Assigner {
   // bytes of its label map as the server prints them (sorted keys, so the text is canonical) plus the plane it
   // feeds; known series skip the label work altogether.
   // (identity = two independent 64-bit hashes of those bytes: 128 bits, no copy of the label text is kept)
-  template <typename M>
-  Result assign_remembered(std::string_view raw_labels, const M& m, bool is_power, bool is_prof, uint32_t* pod_out,
-                           uint32_t* slot_out) {
-    const uint64_t tag = is_power ? 0x57 : (is_prof ? 0x50 : 0x55);
-    uint64_t h1, h2;
-    hash128(raw_labels, tag, &h1, &h2);
+  // lookup_known: true = the series has been seen, *result / *pod_out / *slot_out are what assign() returned then
+  // (its label map need not even be parsed again: identical bytes were validated when it was first seen).
+  bool lookup_known(std::string_view raw_labels, bool is_power, bool is_prof, Result* result, uint32_t* pod_out,
+                    uint32_t* slot_out) {
+    hash128(raw_labels, is_power ? 0x57 : (is_prof ? 0x50 : 0x55), &probe_h1_, &probe_h2_);
     if (known_.empty()) known_.assign(4096, Known{0, 0, Skipped, 0, 0});
-    size_t mask = known_.size() - 1, i = (size_t)h1 & mask;
-    for (;; i = (i + 1) & mask) {
-      const Known& k = known_[i];
-      if (k.h1 == 0 && k.h2 == 0) break;
-      if (k.h1 == h1 && k.h2 == h2) {
-        *pod_out = k.pod, *slot_out = k.slot;
+    const size_t mask = known_.size() - 1;
+    for (probe_at_ = (size_t)probe_h1_ & mask;; probe_at_ = (probe_at_ + 1) & mask) {
+      const Known& k = known_[probe_at_];
+      if (k.h1 == 0 && k.h2 == 0) return false;
+      if (k.h1 == probe_h1_ && k.h2 == probe_h2_) {
+        *pod_out = k.pod, *slot_out = k.slot, *result = k.result;
         if (k.result == Skipped) ++w_.stats.series_skipped;
-        return k.result;
+        return true;
       }
     }
-    const Result r = assign(m, is_power, is_prof, pod_out, slot_out);
-    known_[i] = Known{h1, h2, r, *pod_out, *slot_out};
+  }
+  // records the outcome for the series of the lookup_known() call that just returned false
+  void remember(Result r, uint32_t pod, uint32_t slot) {
+    known_[probe_at_] = Known{probe_h1_, probe_h2_, r, pod, slot};
     if (++n_known_ * 2 > known_.size()) {
       std::vector<Known> bigger(known_.size() * 4, Known{0, 0, Skipped, 0, 0});
-      mask = bigger.size() - 1;
+      const size_t mask = bigger.size() - 1;
       for (const Known& k : known_) {
         if (k.h1 == 0 && k.h2 == 0) continue;
         size_t j = (size_t)k.h1 & mask;
@@ -162,7 +163,6 @@ class Assigner {
       }
       known_.swap(bigger);
     }
-    return r;
   }
 
   Result assign(const Json& m, bool is_power, bool is_prof, uint32_t* pod_out, uint32_t* slot_out) {
@@ -301,7 +301,8 @@ class Assigner {
     *h1 = a, *h2 = b;
   }
   std::vector<Known> known_;  // open addressing
-  size_t n_known_ = 0;
+  size_t n_known_ = 0, probe_at_ = 0;
+  uint64_t probe_h1_ = 0, probe_h2_ = 0;
   Window& w_;
   std::vector<uint32_t> table_;                    // open addressing: pod index + 1, 0 = empty
   std::vector<uint64_t> pod_hash_;                 // per pod

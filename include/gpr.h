@@ -113,7 +113,7 @@ typedef struct gpr_config {
 /*
  * One window = the range-vector result laid out densely.
  *
- *   n_gpus          series slots per pod, 1..32 (GPR_E_UNSUPPORTED above; the host ingest splits larger pods).
+ *   n_gpus          series slots per pod, 1..256 (GPR_E_UNSUPPORTED above).
  *   capacity        for HOST windows only the number of cells counts: n_pods * n_gpus * n_samples must not
  *                   exceed max_pods * max_gpus * max_samples of gpr_create (staging is dense).
  *   util[p][g][t]   f32, t fastest; NaN = "no sample" (stale / absent / scrape gap); or biased

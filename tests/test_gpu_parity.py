@@ -474,8 +474,35 @@ def test_gpu_slot_limit(engines):
     bits, cbits, counts, smax, _ = _device_decide(eng, u)
     assert counts == (P, P, P) and int(np.unpackbits(cbits.view(np.uint8)).sum()) == P
     with pytest.raises(g.GprError) as ei:
-        eng.decide(np.zeros((2, 33, 4), np.float32))
+        eng.decide(np.zeros((2, 257, 4), np.float32))
     assert ei.value.code == g.ffi.GPR_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("G", [33, 64, 65, 100, 256])
+def test_pods_with_more_than_32_series_slots(G, variant, engines, oracle_c):
+    """a pod may carry more than 32 series (duplicate exporters, a pod name reused across hosts): the
+    per-pod flag mask is ceil(G / 32) words; verdicts, counts and the power veto equal the oracle's"""
+    eng = engines[variant]
+    rng = np.random.default_rng(G)
+    P, T = 70, 24
+    u = rng.choice(np.array([0, 0, 3, 50], np.float32), size=(P, G, T))
+    u[rng.random((P, G)) < 0.6] = 7.0                       # most series busy
+    u[rng.random((P, G)) < 0.1] = np.nan                    # some absent
+    u[5] = 9.0
+    u[5, G - 1] = 0.0                                       # the only idle series sits in the last mask word
+    w = rng.choice(np.array([50, 60, 149, 151], np.float32), size=(P, G, T), p=[0.5, 0.47, 0.02, 0.01])
+    w[7] = 60.0
+    w[7, G - 1, 3] = 400.0                                  # the veto too
+    e = (rng.random(P) < 0.9).astype(np.uint8)
+    for thr in (0.0, 150.0):
+        d = eng.decide(u, w, e, power_threshold=thr, want_series_max=True)
+        exp = oracle_c.decide(u, w, e, power_threshold=thr)
+        _check(d.decision_bits, d.candidate_bits, (d.n_series, d.n_candidates, d.n_decisions), exp, d.series_max)
+    # device-resident window through the same kernels
+    bits, cbits, counts, smax, _ = _device_decide(eng, u)
+    exp0 = oracle_c.decide(u)
+    _check(bits, cbits, counts, exp0, smax)
 
 
 def test_memory_and_timing_helpers(engines):
