@@ -142,7 +142,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
       if (rep.on_device && opt.slice_seconds > 0)
         snprintf(buf, sizeof buf,
                  "Device ingest: %llu series lists of the last %lld s appended to the resident %ux%ux%u window in %.1f ms "
-                 "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, series walk %.1f, labels->rows %.1f, "
+                 "(%llu re-parsed on the CPU, %llu rows patched; waiting for upload+scan %.1f, label maps (parallel) %.1f, rows (sequential) %.1f, "
                  "parse %.1f ms)",
                  (unsigned long long)rep.spans, (long long)opt.slice_seconds, w.P, w.G, w.T, ms,
                  (unsigned long long)rep.hard_spans, (unsigned long long)rep.rows_patched, rep.scan_ms, rep.labels_ms,
@@ -150,7 +150,7 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
       else if (rep.on_device)
         snprintf(buf, sizeof buf,
                  "Device ingest: %llu series lists parsed on the GPU into a %s%ux%ux%u window in %.1f ms "
-                 "(%llu re-parsed on the CPU, %llu rows patched; upload+scan %.1f, series walk %.1f, labels->rows %.1f, "
+                 "(%llu re-parsed on the CPU, %llu rows patched; waiting for upload+scan %.1f, label maps (parallel) %.1f, rows (sequential) %.1f, "
                  "parse %.1f ms)",
                  (unsigned long long)rep.spans, w.resident ? "resident " : "", w.P, w.G, w.T, ms,
                  (unsigned long long)rep.hard_spans,

@@ -10,7 +10,11 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include "ingest_internal.hpp"
 
@@ -56,100 +60,217 @@ struct SeriesLoc {
   size_t mb, close_brace, vb, list_close;  // label map [mb, close_brace], list [vb, list_close]
 };
 
+// A few worker threads for the per-series label work (parse the label map, hash it, probe the table of known
+// series): independent per series, and on the critical path of a tick while the text is crossing PCIe.
+class Workers {
+ public:
+  explicit Workers(int n) : n_(std::max(1, n)) {
+    for (int i = 1; i < n_; ++i) th_.emplace_back([this, i] { loop(i); });
+  }
+  ~Workers() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (std::thread& t : th_) t.join();
+  }
+  // fn(begin, end) over [0, n) in contiguous shares; returns when all shares are done.  Exceptions are carried over.
+  void run(size_t n, const std::function<void(size_t, size_t)>& fn) {
+    if (n_ == 1 || n < 256) {
+      fn(0, n);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn, total_ = n, pending_ = n_ - 1, ++gen_, error_.clear();
+    }
+    cv_.notify_all();
+    share(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+    if (!error_.empty()) throw std::runtime_error(error_);
+  }
+
+ private:
+  void share(int i) {
+    const size_t b = total_ * (size_t)i / (size_t)n_, e = total_ * (size_t)(i + 1) / (size_t)n_;
+    try {
+      if (b < e) (*fn_)(b, e);
+    } catch (const std::exception& ex) {
+      std::lock_guard<std::mutex> lk(mu_);
+      error_ = ex.what();
+    }
+  }
+  void loop(int i) {
+    unsigned long seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    while (true) {
+      cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+      if (quit_) return;
+      seen = gen_;
+      lk.unlock();
+      share(i);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(size_t, size_t)>* fn_ = nullptr;
+  size_t total_ = 0;
+  int pending_ = 0;
+  unsigned long gen_ = 0;
+  bool quit_ = false;
+  std::string error_;
+};
+
+Workers& label_workers() {
+  static Workers w([] {
+    const char* v = getenv("GPR_LABEL_THREADS");
+    const int n = v && *v ? atoi(v) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    return std::max(1, std::min(64, n));
+  }());
+  return w;
+}
+
 // Walk the series of one response with the device's marker lists, as they arrive: the upload + scan runs as a
-// pipeline (TextDevice::scan_begin / scan_next) and every series whose markers are in is validated, its label map
-// parsed and its row assigned through `asg` while later chunks of the text are still on their way to the GPU.
+// pipeline (TextDevice::scan_begin / scan_next).  Every batch of series whose markers are in goes through three steps
+// while later chunks of the text are still on their way to the GPU:
+//   walk    (this thread, markers only)   series i <-> i-th `},"values":[`; its list ends at the first `"]]` behind
+//                                         it, or is empty when that lies beyond the next series' marker
+//   labels  (worker threads, per series)  check the framing bytes around the markers, then either recognise the
+//                                         series by the hash of its label bytes (daemon mode) or parse the label
+//                                         map in place and pull out the six labels the assignment needs
+//   assign  (this thread, in text order)  label set -> (pod, slot) through `asg`
 void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool is_power, bool is_prof,
                DeviceIngestReport& rep, bool remember) {
   const std::string& t = *plan.text;
-  size_t at;
+  size_t at0;
   bool bare;
-  if (starts_with(t, 0, kHead)) at = sizeof kHead - 1, bare = false;
-  else if (starts_with(t, 0, "[")) at = 1, bare = true;
+  if (starts_with(t, 0, kHead)) at0 = sizeof kHead - 1, bare = false;
+  else if (starts_with(t, 0, "[")) at0 = 1, bare = true;
   else throw NotCompact{"response does not start with the compact success/matrix header"};
 
+  struct Loc {
+    size_t at, close_brace, list_close;  // series object starts at `at`; '}' of the label map; ']' closing the list
+    bool empty;                          // "values":[]
+  };
+  struct Rec {
+    const char* err = nullptr;  // framing violation (a string literal)
+    bool known = false, flat = false;
+    Assigner::Result r = Assigner::Skipped;
+    uint32_t pod = 0, slot = 0;
+    uint64_t h1 = 0, h2 = 0;
+    LabelFields f;
+  };
   std::vector<uint64_t> opens, closes, co, cc;  // all markers so far (sorted: chunks come in text order)
-  size_t oi = 0, ci = 0, walked = 0;
-  bool finished = false;  // the closing ']' of the result array has been reached
-  if (at < t.size() && t[at] == ']') ++at, finished = true;  // empty result
-  FlatLabels flat;
+  std::vector<Loc> locs;
+  std::vector<Rec> recs;
+  size_t oi = 0, ci = 0;     // next series' open marker; cursor into closes
+  size_t at = at0;           // where the next series object starts
+  const size_t kM = sizeof kMetric - 1;
 
   // consume every series that is completely covered by the markers delivered so far
   auto drain = [&](bool final) {
-    while (!finished) {
-      if (!starts_with(t, at, kMetric) || at + sizeof kMetric - 1 >= t.size() || t[at + sizeof kMetric - 1] != '{')
-        throw NotCompact{"series does not start with {\"metric\":{"};
-      const size_t mb = at + sizeof kMetric - 1;  // '{' of the label map
-      while (oi < opens.size() && opens[oi] < mb) ++oi;
-      if (oi == opens.size()) {
-        if (final) throw NotCompact{"label map without a following \"values\" list"};
-        return;
-      }
-      const size_t close_brace = (size_t)opens[oi];  // '}' of the label map
-      const size_t vb = close_brace + 12;            // first byte after `},"values":[`
-      if (vb >= t.size()) throw NotCompact{"truncated values list"};
-      size_t list_close;  // offset of the ']' closing the list
-      if (t[vb] == ']') {
-        list_close = vb;
-      } else {
-        if (t[vb] != '[') throw NotCompact{"values list does not start with a sample"};
-        while (ci < closes.size() && closes[ci] < vb) ++ci;
-        if (ci == closes.size()) {
-          if (final) throw NotCompact{"unterminated values list"};
-          return;
+    // ---- walk: markers only ----------------------------------------------------------------------------------------
+    const auto tw = std::chrono::steady_clock::now();
+    locs.clear();
+    while (oi < opens.size()) {
+      if (!final && oi + 1 >= opens.size()) break;  // emptiness of list i is decided by where series i + 1 begins
+      const size_t close_brace = (size_t)opens[oi], vb = close_brace + 12;
+      if (close_brace < at + kM) throw NotCompact{"values marker inside the framing of a series"};
+      while (ci < closes.size() && closes[ci] < vb) ++ci;
+      const uint64_t next_open = oi + 1 < opens.size() ? opens[oi + 1] : (uint64_t)t.size();
+      Loc l;
+      l.at = at, l.close_brace = close_brace;
+      l.empty = ci == closes.size() || closes[ci] > next_open;
+      l.list_close = l.empty ? vb : (size_t)closes[ci] + 2;
+      if (l.list_close + 3 > t.size()) throw NotCompact{"truncated values list"};
+      locs.push_back(l);
+      at = l.list_close + 3;  // past `]},`
+      ++oi;
+    }
+    // ---- labels: per series, in parallel --------------------------------------------------------------------------
+    recs.resize(locs.size());  // (every worker resets the records of its share)
+    label_workers().run(locs.size(), [&](size_t b, size_t e) {
+      FlatLabels flat;
+      for (size_t i = b; i < e; ++i) {
+        const Loc& l = locs[i];
+        Rec& r = recs[i];
+        r = Rec();
+        const size_t mb = l.at + kM, vb = l.close_brace + 12;
+        if (!starts_with(t, l.at, kMetric) || t[mb] != '{') r.err = "series does not start with {\"metric\":{";
+        else if (t[vb] != (l.empty ? ']' : '[')) r.err = l.empty ? "unterminated values list" : "values list does not start with a sample";
+        else if (t[l.list_close + 1] != '}') r.err = "series object has members after \"values\"";
+        if (r.err) continue;
+        const char* lb = t.data() + mb;
+        const char* le = t.data() + l.close_brace + 1;
+        if (remember && !l.empty) {
+          Assigner::series_identity(std::string_view(lb, (size_t)(le - lb)), is_power, is_prof, &r.h1, &r.h2);
+          r.known = asg.find_known(r.h1, r.h2, &r.r, &r.pod, &r.slot);
+          if (r.known) continue;  // same bytes as in an earlier tick: validated then, same row now
         }
-        list_close = (size_t)closes[ci] + 2;
+        // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON object ending
+        // exactly at the marker's '}' proves that [mb, close_brace] is the whole map and that no series without a
+        // "values" member was jumped over.  (A `},"values":[` inside a label value is impossible: a raw '"' ends a
+        // JSON string.)  Prometheus' own shape — string values, no escapes — is read in place without allocating.
+        r.flat = flat.parse(lb, le);
+        if (r.flat && !l.empty) r.f = extract_fields(flat);
       }
-      if (list_close + 1 >= t.size() || t[list_close + 1] != '}')
-        throw NotCompact{"series object has members after \"values\""};
-      ++oi, ++walked;
-      // The label map is parsed for EVERY series (also the ones whose list is empty): a complete JSON object
-      // ending exactly at the marker's '}' proves that [mb, close_brace] is the whole map and that no series
-      // without a "values" member was jumped over.  (A `},"values":[` inside a label value is impossible: a raw
-      // '"' ends a JSON string.)  Prometheus' own shape — string values, no escapes — is read in place without
-      // allocating (FlatLabels); anything else goes through the DOM parser.
-      const char* b = t.data() + mb;
-      const char* e = t.data() + close_brace + 1;
-      const bool element = list_close != vb;  // an empty list is no element (as in the CPU paths)
-      uint32_t p = 0, slot = 0;
-      Assigner::Result r = Assigner::Skipped;
-      const std::string_view raw(b, (size_t)(e - b));
-      if (remember && element && asg.lookup_known(raw, is_power, is_prof, &r, &p, &slot)) {
-        ++w.stats.series_in;  // a series of an earlier tick: same bytes, same row, nothing to parse
-      } else if (flat.parse(b, e)) {
-        ++w.stats.series_in;
-        if (element) {
-          r = asg.assign(flat, is_power, is_prof, &p, &slot);
-          if (remember) asg.remember(r, p, slot);
+    });
+    rep.labels_ms += ms_since(tw);  // walk + parallel label phase
+    // ---- assign: in text order ----------------------------------------------------------------------------------------
+    const auto ta = std::chrono::steady_clock::now();
+    FlatLabels flat;
+    for (size_t i = 0; i < locs.size(); ++i) {
+      const Loc& l = locs[i];
+      Rec& r = recs[i];
+      if (r.err) throw NotCompact{r.err};
+      // between series exactly one ',' ; the last one is followed by the ']' of the result array
+      const char sep = t[l.list_close + 2];
+      const bool last = final && oi == opens.size() && i + 1 == locs.size();
+      if (sep != (last ? ']' : ',')) throw NotCompact{"expected ',' or ']' after a series"};
+      ++w.stats.series_in;
+      if (l.empty) {
+        if (!r.flat) {  // still has to be a label map
+          try {
+            if (!Json::parse(std::string(t.data() + l.at + kM, t.data() + l.close_brace + 1)).is_object())
+              throw NotCompact{"label map is not an object"};
+          } catch (const std::exception& ex) {
+            throw NotCompact{std::string("label map: ") + ex.what()};
+          }
         }
+        continue;  // an empty list is no element (as in the CPU paths)
+      }
+      const char* lb = t.data() + l.at + kM;
+      const char* le = t.data() + l.close_brace + 1;
+      if (r.known) {
+        if (r.r == Assigner::Skipped) asg.count_skipped();
+      } else if (r.flat) {
+        r.r = asg.assign_fields(r.f, is_power, is_prof, [&]() {
+          flat.parse(lb, le);
+          return label_signature(flat);
+        }, &r.pod, &r.slot);
+        if (remember) asg.insert_known(r.h1, r.h2, r.r, r.pod, r.slot);
       } else {
         Json metric;
         try {
-          metric = Json::parse(std::string(b, e));
+          metric = Json::parse(std::string(lb, le));
         } catch (const std::exception& ex) {
           throw NotCompact{std::string("label map: ") + ex.what()};
         }
         if (!metric.is_object()) throw NotCompact{"label map is not an object"};
-        ++w.stats.series_in;
-        if (element) {
-          r = asg.assign(metric, is_power, is_prof, &p, &slot);
-          if (remember) asg.remember(r, p, slot);
-        }
+        r.r = asg.assign(metric, is_power, is_prof, &r.pod, &r.slot);
+        if (remember) asg.insert_known(r.h1, r.h2, r.r, r.pod, r.slot);
       }
-      if (element && r == Assigner::Placed)
-        plan.series.push_back(DevSeries{p, slot, (uint64_t)vb, (uint64_t)list_close});
-      at = list_close + 2;  // past '}'
-      if (at < t.size() && t[at] == ',') {
-        ++at;
-        continue;
-      }
-      if (at < t.size() && t[at] == ']') {
-        ++at;
-        finished = true;
-        break;
-      }
-      throw NotCompact{"expected ',' or ']' after a series"};
+      if (r.r == Assigner::Placed)
+        plan.series.push_back(DevSeries{r.pod, r.slot, (uint64_t)l.close_brace + 12, (uint64_t)l.list_close});
     }
+    rep.assign_ms += ms_since(ta);
   };
 
   auto t0 = std::chrono::steady_clock::now();
@@ -163,8 +284,8 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
       t0 = std::chrono::steady_clock::now();
       opens.insert(opens.end(), co.begin(), co.end());
       closes.insert(closes.end(), cc.begin(), cc.end());
-      drain(!more);
-      rep.assign_ms += ms_since(t0);  // series walk + label maps -> rows, overlapped with the upload
+      // batches of a few thousand series keep the workers' hand-over cost negligible
+      if (!more || opens.size() - oi >= 4096) drain(!more);  // (timed inside: labels_ms / assign_ms)
       t0 = std::chrono::steady_clock::now();
     }
   } catch (...) {
@@ -178,7 +299,11 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
     }
     throw;
   }
-  if (walked != opens.size()) throw NotCompact{"values markers outside the series walk"};
+  // the result array closes right behind the last series (or at once when there is none)
+  if (opens.empty()) {
+    if (at0 >= t.size() || t[at0] != ']') throw NotCompact{"label map without a following \"values\" list"};
+    at = at0 + 1;
+  }
   if (!bare) {
     if (!starts_with(t, at, "}}")) throw NotCompact{"response has members after \"result\""};
     at += 2;

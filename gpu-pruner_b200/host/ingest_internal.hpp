@@ -123,10 +123,69 @@ inline uint64_t hash_bytes(uint64_t h, std::string_view s) {
   return (h ^ 0xff) * 0x100000001B3ull;                      // field separator
 }
 
+// the labels the row assignment looks at, as views into the label map (text or DOM)
+struct LabelFields {
+  std::string_view pod, ns, ctr, model, host, gpu;
+  bool has_pod = false, has_ns = false, has_ctr = false, has_model = false;
+  uint64_t pod_hash = 0;
+};
+template <typename M>
+inline LabelFields extract_fields(const M& m) {
+  LabelFields f;
+  f.has_pod = label(m, "exported_pod", "pod", &f.pod);
+  f.has_ns = label(m, "exported_namespace", "namespace", &f.ns);
+  f.has_ctr = label(m, "exported_container", "container", &f.ctr);
+  f.has_model = m.str("modelName", &f.model);
+  m.str("Hostname", &f.host), m.str("gpu", &f.gpu);   // absent / non-string: ""
+  f.pod_hash = hash_bytes(hash_bytes(0xcbf29ce484222325ull, f.pod), f.ns);
+  return f;
+}
+// full label set of a series without the metric name, canonical: what `A or B` compares (query.promql.j2:10-20)
+template <typename M>
+inline std::string label_signature(const M& m) {
+  std::vector<std::string> parts;
+  m.each([&](std::string_view k, std::string_view v) {
+    if (k != "__name__") parts.push_back(std::string(k) + "\x1f" + std::string(v));
+  });
+  std::sort(parts.begin(), parts.end());
+  std::string sig;
+  for (const std::string& x : parts) sig += x + "\x1e";
+  return sig;
+}
+
 class Assigner {
  public:
   explicit Assigner(Window& w) : w_(w) { table_.assign(1024, 0); }
   enum Result { Skipped, Shadowed, Placed };
+
+  // identity of a series across ticks: see lookup_known.  The two-step form below lets worker threads hash and
+  // probe (find_known is read-only) while the single assigning thread inserts afterwards.
+  static void series_identity(std::string_view raw_labels, bool is_power, bool is_prof, uint64_t* h1, uint64_t* h2) {
+    hash128(raw_labels, is_power ? 0x57 : (is_prof ? 0x50 : 0x55), h1, h2);
+  }
+  bool find_known(uint64_t h1, uint64_t h2, Result* result, uint32_t* pod_out, uint32_t* slot_out) const {
+    if (known_.empty()) return false;
+    const size_t mask = known_.size() - 1;
+    for (size_t i = (size_t)h1 & mask;; i = (i + 1) & mask) {
+      const Known& k = known_[i];
+      if (k.h1 == 0 && k.h2 == 0) return false;
+      if (k.h1 == h1 && k.h2 == h2) {
+        *pod_out = k.pod, *slot_out = k.slot, *result = k.result;
+        return true;
+      }
+    }
+  }
+  void insert_known(uint64_t h1, uint64_t h2, Result r, uint32_t pod, uint32_t slot) {
+    if (known_.empty()) known_.assign(4096, Known{0, 0, Skipped, 0, 0});
+    size_t mask = known_.size() - 1, i = (size_t)h1 & mask;
+    while (known_[i].h1 || known_[i].h2) {
+      if (known_[i].h1 == h1 && known_[i].h2 == h2) return;
+      i = (i + 1) & mask;
+    }
+    probe_at_ = i, probe_h1_ = h1, probe_h2_ = h2;
+    remember(r, pod, slot);
+  }
+  void count_skipped() { ++w_.stats.series_skipped; }
 
   // Daemon mode: the same series comes back every tick and must keep its row.  A series is identified by the
   // bytes of its label map as the server prints them (sorted keys, so the text is canonical) plus the plane it
@@ -171,35 +230,37 @@ class Assigner {
 
   template <typename M>
   Result assign(const M& m, bool is_power, bool is_prof, uint32_t* pod_out, uint32_t* slot_out) {
-    std::string_view pod, ns, ctr, model, host, gpu;
-    const bool has_pod = label(m, "exported_pod", "pod", &pod);
-    const bool has_ns = label(m, "exported_namespace", "namespace", &ns);
-    const bool has_ctr = label(m, "exported_container", "container", &ctr);
-    const bool has_model = m.str("modelName", &model);
+    return assign_fields(extract_fields(m), is_power, is_prof, [&]() { return label_signature(m); }, pod_out, slot_out);
+  }
+
+  // `signature` is only called when a PROF series is involved (never for the usual UTIL-only tick)
+  template <typename Sig>
+  Result assign_fields(const LabelFields& f, bool is_power, bool is_prof, Sig&& signature, uint32_t* pod_out,
+                       uint32_t* slot_out) {
     // the selector demands pod != "" (query.promql.j2:11,17,40); a series that cannot be turned into
     // PodMetricData is skipped with a log line (main.rs:423-428)
-    if (!has_pod || pod.empty() || !has_ns || (!is_power && (!has_ctr || !has_model))) {
+    if (!f.has_pod || f.pod.empty() || !f.has_ns || (!is_power && (!f.has_ctr || !f.has_model))) {
       ++w_.stats.series_skipped;
       return Skipped;
     }
-    const uint32_t p = find_or_add_pod(pod, ns);
-    m.str("Hostname", &host), m.str("gpu", &gpu);   // absent / non-string: ""
+    const uint32_t p = find_or_add_pod(f.pod, f.ns, f.pod_hash);
+    PodEntry& pe = w_.pods[p];
     // `sum by (Hostname, container, pod, namespace, gpu, modelName)` groups (query.promql.j2:9)
     uint32_t slot;
     if (is_power) {
       // every power series is its own row: `unless on (pod, namespace)` looks at each series' max
       // (query.promql.j2:36-44), there is no `sum by` on that side; the group key only feeds the statistic
-      const uint64_t gk = hash_bytes(hash_bytes(hash_bytes(hash_bytes(0xcbf29ce484222325ull, host), ctr), gpu), model);
+      const uint64_t gk = hash_bytes(hash_bytes(hash_bytes(hash_bytes(0xcbf29ce484222325ull, f.host), f.ctr), f.gpu), f.model);
       std::vector<uint64_t>& seen = power_keys_[p];
       if (std::find(seen.begin(), seen.end(), gk) != seen.end()) ++w_.stats.duplicates_merged;
       else seen.push_back(gk);
-      slot = w_.pods[p].power_slots++;
+      slot = pe.power_slots++;
     } else {
-      std::vector<GpuSlot>& slots = w_.pods[p].slots;
+      std::vector<GpuSlot>& slots = pe.slots;
       uint32_t group = (uint32_t)slots.size();
       for (uint32_t i = 0; i < slots.size(); ++i) {
         const GpuSlot& g = slots[i];
-        if (g.group == i && g.gpu == gpu && g.hostname == host && g.container == ctr && g.model == model) {
+        if (g.group == i && g.gpu == f.gpu && g.hostname == f.host && g.container == f.ctr && g.model == f.model) {
           group = i;
           break;
         }
@@ -208,17 +269,6 @@ class Assigner {
       // `A or B` (query.promql.j2:10-20) matches on the FULL label set: a UTIL element is dropped only
       // if a PROF element with identical labels exists; series that differ in any other label both
       // survive the `or` and are then added up by `sum by`
-      // (the signature is only built when a PROF series is involved: never for the usual UTIL-only tick)
-      auto signature = [&]() {
-        std::vector<std::string> parts;
-        m.each([&](std::string_view k, std::string_view v) {
-          if (k != "__name__") parts.push_back(std::string(k) + "\x1f" + std::string(v));
-        });
-        std::sort(parts.begin(), parts.end());
-        std::string sig;
-        for (const std::string& x : parts) sig += x + "\x1e";
-        return sig;
-      };
       if (is_prof) {
         prof_sigs_[std::make_pair(p, group)].push_back(signature());
       } else if (!prof_sigs_.empty()) {
@@ -233,28 +283,29 @@ class Assigner {
       slot = (uint32_t)slots.size();
       slots.emplace_back();
       GpuSlot& g = slots.back();
-      g.hostname.assign(host), g.container.assign(ctr), g.gpu.assign(gpu), g.model.assign(model);
+      g.hostname.assign(f.host), g.container.assign(f.ctr), g.gpu.assign(f.gpu), g.model.assign(f.model);
       g.node_type = "unknown";  // lib.rs:176-179; the node_dmi_info join fills it in (apply_node_types)
       g.from_prof = is_prof;
       g.group = group;
-      if (!fresh) w_.pods[p].has_groups = true, ++w_.stats.duplicates_merged;
+      if (!fresh) pe.has_groups = true, ++w_.stats.duplicates_merged;
     }
     *pod_out = p, *slot_out = slot;
     return Placed;
   }
 
  private:
-  uint32_t find_or_add_pod(std::string_view pod, std::string_view ns) {
-    const uint64_t h = hash_bytes(hash_bytes(0xcbf29ce484222325ull, pod), ns);
+  uint32_t find_or_add_pod(std::string_view pod, std::string_view ns, uint64_t h) {
     size_t mask = table_.size() - 1, i = (size_t)(h ^ (h >> 32)) & mask;
+    const PodList& known = w_.pods;  // read-only view: no copy-on-write check per probe
     for (;; i = (i + 1) & mask) {
       const uint32_t e = table_[i];
       if (e == 0) break;
-      if (pod_hash_[e - 1] == h && w_.pods[e - 1].name == pod && w_.pods[e - 1].ns == ns) return e - 1;
+      if (pod_hash_[e - 1] == h && known[e - 1].name == pod && known[e - 1].ns == ns) return e - 1;
     }
     const uint32_t p = (uint32_t)w_.pods.size();
     w_.pods.emplace_back();
     w_.pods.back().name.assign(pod), w_.pods.back().ns.assign(ns);
+    w_.pods.back().slots.reserve(8);  // a pod rarely has more GPUs: no regrowth while its series arrive
     pod_hash_.push_back(h);
     power_keys_.emplace_back();
     table_[i] = p + 1;
