@@ -354,6 +354,7 @@ def run_cuda(args):
     st = step_stats(durs)
     per_step = {k: (reduce_max(v) if v is not None else None) for k, v in st.items()}
     per_step["first_us"] = reduce_max(float(durs[0])) if len(durs) else None
+    per_step["first_steps_us_rank0"] = [round(float(x), 2) for x in durs[:8]]
     per_step["note"] = ("device %globaltimer stamps written by the fold kernel when a decision (exchange "
                         "included) completes; differences of consecutive stamps; each statistic is the max over ranks")
     # the LAST timed step's global bitmap and counts (catches a stale double buffer under PDL overlap)

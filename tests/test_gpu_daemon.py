@@ -88,3 +88,34 @@ def test_cpu_ingest_in_daemon_mode_takes_the_full_range_every_tick(tmp_path, ora
         n_series, n_pods = _expected(root, k, dur, None, oracle_np)
         assert v == f"Query returned {n_series} series across {n_pods} unique pods", (k, v)
     assert len(verdicts) == n and not any("resident" in m for m in msgs)
+
+
+def test_prof_metric_through_the_device_ingest(tmp_path, oracle_np):
+    """a4 / VERDICT r1 #6: DCGM_FI_PROF_GR_ENGINE_ACTIVE ratios (shortest-round-trip doubles, up to 17 digits) go
+    through the binary's device ingest without a single span falling back to the CPU, and PROF shadows UTIL on
+    identical label sets (query.promql.j2:10-20): the verdict equals the oracle's on the CPU-ingested window"""
+    rng = random.Random(77)
+    N, step, dur = 120, 1, 2
+    t0 = 1_700_000_000
+    t_end = t0 + N
+    store = []
+    for p in range(30):
+        for g in range(2):
+            lab = TK.labels(f"pod-{p}", g)
+            busy_util = rng.random() < 0.5
+            store.append(("DCGM_FI_DEV_GPU_UTIL", lab, [(t, rng.choice([0, 0, 40]) if busy_util else 0) for t in range(t0, t_end + 1)]))
+            r = rng.random()
+            if r < 0.4:        # PROF with the identical label set: it decides, whatever UTIL says
+                idle = rng.random() < 0.5
+                store.append(("DCGM_FI_PROF_GR_ENGINE_ACTIVE", lab,
+                              [(t, 0.0 if idle else rng.random()) for t in range(t0, t_end + 1)]))
+            elif r < 0.5:      # PROF with another label: both survive the `or`, `sum by` adds them
+                store.append(("DCGM_FI_PROF_GR_ENGINE_ACTIVE", dict(lab, profiled="yes"),
+                              [(t, rng.random() * 1e-7) for t in range(t0, t_end + 1)]))   # Go prints these as 5.1e-08
+    TK.write_ticks(str(tmp_path), lambda k: store, [t_end], N, step)
+    msgs = _run(str(tmp_path), 1, dur)
+    note = [m for m in msgs if m.startswith("Device ingest")][0]
+    assert "parsed on the GPU" in note and "(0 re-parsed on the CPU, 0 rows patched" in note, note
+    n_series, n_pods = _expected(str(tmp_path), 0, dur, None, oracle_np)
+    assert f"Query returned {n_series} series across {n_pods} unique pods" in msgs
+    assert 0 < n_pods < 30
