@@ -151,6 +151,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// poll with relaxed loads, order with one fence at the end (an acquire per poll costs an L1 invalidate each time)
+__device__ __forceinline__ void spin_until_gpu(const unsigned long long* p, unsigned long long want) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  while (v < want) {
+    __nanosleep(64);
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -168,18 +178,27 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 // skipped a collective call) must not hang this GPU: after kPeerTimeoutNs the wait gives up, raises
 // the host-visible error word (gpr_sync then fails with GPR_E_STATE) and the kernel runs to completion.
 constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Polls with RELAXED loads and fences once when the value has arrived: an acquire per poll would put a
+// system-scope fence into the loop, on an SM that is streaming the next decision's window at the same time.
 __device__ __forceinline__ void spin_until_sys(const unsigned long long* p, unsigned long long want,
                                                unsigned int* err) {
-  if (ld_acquire_sys_u64(p) >= want) return;
-  const unsigned long long t0 = gtime();
-  unsigned int polls = 0;
-  while (ld_acquire_sys_u64(p) < want) {
-    __nanosleep(64);
-    if ((++polls & 1023u) == 0 && gtime() - t0 > kPeerTimeoutNs) {
-      if (err) *err = 1u;
-      return;
+  if (ld_relaxed_sys_u64(p) < want) {
+    const unsigned long long t0 = gtime();
+    unsigned int polls = 0;
+    while (ld_relaxed_sys_u64(p) < want) {
+      __nanosleep(100);
+      if ((++polls & 1023u) == 0 && gtime() - t0 > kPeerTimeoutNs) {
+        if (err) *err = 1u;
+        return;
+      }
     }
   }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");  // the peer's words are ordered before its flag
 }
 
 __device__ __forceinline__ float nan_f() { return __int_as_float(0x7fffffff); }
@@ -334,8 +353,7 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
   pdl_wait_prior_grids();    // reduce grid of THIS decision complete, masks visible
   // the caller's output buffers may still be written by the previous decision's fold
-  if (threadIdx.x == 0)
-    while (ld_acquire_u64(f.prev_done) < f.prev_need) __nanosleep(64);
+  if (threadIdx.x == 0) spin_until_gpu(f.prev_done, f.prev_need);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t warps_per_cta = blockDim.x >> 5;
@@ -405,9 +423,7 @@ __device__ __forceinline__ uint32_t cta_row_count(uint32_t total_rows) {
 }
 
 // before a warp's first publish: the decision that last used this scratch set must have folded
-__device__ __forceinline__ void wait_scratch_free(const ReduceParams& p) {
-  while (ld_acquire_u64(p.done) < p.need) __nanosleep(64);
-}
+__device__ __forceinline__ void wait_scratch_free(const ReduceParams& p) { spin_until_gpu(p.done, p.need); }
 
 __device__ __forceinline__ void publish_row(const ReduceParams& p, uint32_t seg, uint32_t local,
                                             float m) {

@@ -37,6 +37,7 @@ class Decision:
     decision_bits: np.ndarray            # uint32[ceil(P/32)] (x world with a communicator)
     candidate_bits: Optional[np.ndarray]
     series_max: Optional[np.ndarray]     # float32[P, G]
+    veto_bits: Optional[np.ndarray] = None   # uint32[ceil(P/32)]: pods vetoed by the power clause (this rank's pods)
     n_series: int                        # QueryResponse.num_pods (series, pre-dedup; main.rs:418)
     n_candidates: int
     n_decisions: int
@@ -148,7 +149,7 @@ class IdleEngine:
                eligible: Optional[np.ndarray] = None, created_ts: Optional[np.ndarray] = None,
                cutoff_ts: int = 0, power_threshold: Optional[float] = 0.0,
                want_candidates: bool = True, want_series_max: bool = False,
-               world: int = 1) -> Decision:
+               world: int = 1, want_veto: bool = False) -> Decision:
         """Blocking decision over a HOST window ``util[P, G, T]`` (float32, NaN = no sample; or
         uint8 in the biased byte format GPR_FMT_U8B, see :func:`to_biased_u8`)."""
         fmt = ffi.GPR_FMT_U8B if getattr(util, "dtype", None) == np.uint8 else ffi.GPR_FMT_F32
@@ -170,17 +171,21 @@ class IdleEngine:
         dbits = np.zeros(max(W, 1), dtype=np.uint32)
         cbits = np.zeros(max(W, 1), dtype=np.uint32) if want_candidates else None
         smax = np.zeros((P, G), dtype=np.float32) if want_series_max else None
+        vbits = np.zeros(max((P + 31) // 32, 1), dtype=np.uint32) if want_veto else None
         r = ffi.gpr_result()
         r.struct_size = C.sizeof(ffi.gpr_result)
         r.out_mem_kind = ffi.GPR_MEM_HOST
         r.decision_bits, r.candidate_bits, r.series_max = _ptr(dbits), _ptr(cbits), _ptr(smax)
+        r.veto_bits = _ptr(vbits)
         self._check(self._lib.gpr_decide(self._h, C.byref(w), C.byref(r)))
-        return Decision(P, dbits[:W], None if cbits is None else cbits[:W], smax, r.n_series,
-                        r.n_candidates, r.n_decisions, r.kernel_ms)
+        d = Decision(P, dbits[:W], None if cbits is None else cbits[:W], smax, r.n_series,
+                     r.n_candidates, r.n_decisions, r.kernel_ms)
+        d.veto_bits = None if vbits is None else vbits[:(P + 31) // 32]
+        return d
 
     def decide_ptr(self, util, P: int, G: int, T: int, decision_bits, *, power=None, eligible=None,
                    created_ts=None, cutoff_ts: int = 0, power_threshold: Optional[float] = 0.0,
-                   candidate_bits=None, series_max=None, row_stride: int = 0,
+                   candidate_bits=None, series_max=None, veto_bits=None, row_stride: int = 0,
                    in_kind: int = ffi.GPR_MEM_DEVICE, out_kind: int = ffi.GPR_MEM_DEVICE,
                    blocking: bool = True, resident: bool = False,
                    util_format: int = ffi.GPR_FMT_F32) -> ffi.gpr_result:
@@ -193,6 +198,7 @@ class IdleEngine:
         r.out_mem_kind = out_kind
         r.decision_bits, r.candidate_bits, r.series_max = (_ptr(decision_bits), _ptr(candidate_bits),
                                                            _ptr(series_max))
+        r.veto_bits = _ptr(veto_bits)
         if resident:
             self._check(self._lib.gpr_decide_resident(self._h, C.byref(w), C.byref(r)))
         elif blocking:

@@ -563,3 +563,28 @@ def test_step_stamps(variant, engines):
     with pytest.raises(g.GprError):
         eng.p2p_debug(7)
     eng.p2p_debug(0)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_veto_bits_output(variant, engines, oracle_np):
+    """gpr_result.veto_bits: the pods with a power series at or above the threshold (query.promql.j2:36-44), whether or
+    not they have an idle GPU — what the host needs to re-derive a pod's verdict (exact `sum by`)"""
+    eng = engines[variant]
+    rng = np.random.default_rng(17)
+    P, G, T = 333, 3, 64
+    u = rng.choice(np.array([0, 0, 9], np.float32), size=(P, G, T))
+    w = rng.choice(np.array([50, 149.5, 150, 700], np.float32), size=(P, G, T), p=[0.9, 0.08, 0.01, 0.01])
+    w[rng.random((P, G)) < 0.2] = np.nan
+    exp = oracle_np.decide(u, w, power_threshold=150.0)
+    d = eng.decide(u, w, power_threshold=150.0, want_veto=True)
+    assert np.array_equal(d.veto_bits, exp["veto_bits"]) and np.array_equal(d.candidate_bits, exp["candidate_bits"])
+    assert 0 < int(exp["veto"].sum()) < P
+    d0 = eng.decide(u, w, power_threshold=0.0, want_veto=True)          # clause absent: nobody is vetoed
+    assert not d0.veto_bits.any()
+    # device window, device output
+    vb = torch.full(((P + 31) // 32,), 0x5A5A5A5A, dtype=torch.int32, device="cuda:0")
+    db = torch.zeros((P + 31) // 32, dtype=torch.int32, device="cuda:0")
+    ut, wt = torch.from_numpy(u).cuda(), torch.from_numpy(w).cuda()
+    torch.cuda.synchronize()
+    eng.decide_ptr(ut, P, G, T, db, power=wt, power_threshold=150.0, veto_bits=vb)
+    assert np.array_equal(vb.cpu().numpy().view(np.uint32), exp["veto_bits"])
