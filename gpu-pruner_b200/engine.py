@@ -37,11 +37,11 @@ class Decision:
     decision_bits: np.ndarray            # uint32[ceil(P/32)] (x world with a communicator)
     candidate_bits: Optional[np.ndarray]
     series_max: Optional[np.ndarray]     # float32[P, G]
-    veto_bits: Optional[np.ndarray] = None   # uint32[ceil(P/32)]: pods vetoed by the power clause (this rank's pods)
     n_series: int                        # QueryResponse.num_pods (series, pre-dedup; main.rs:418)
     n_candidates: int
     n_decisions: int
     kernel_ms: float
+    veto_bits: Optional[np.ndarray] = None   # uint32[ceil(P/32)]: pods vetoed by the power clause (this rank's pods)
 
     def pods(self, bits: Optional[np.ndarray] = None) -> np.ndarray:
         """Indices of set bits (the idle-pod set), ascending."""
