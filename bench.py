@@ -329,6 +329,8 @@ def run_cuda(args):
     eng.sync()
     sampler.start()
 
+    phases = []
+
     def timed_pass(n_steps):
         """K steps in chunks; returns (device ms, per-step durations in us, launches, last results array,
         steps in the last chunk)"""
@@ -343,6 +345,10 @@ def run_cuda(args):
             launches += eng.launch_count() - l0 - 1   # the rendezvous kernel is outside the event pair
             t0, st = eng.step_stamps()
             durs.extend(np.diff(np.concatenate([np.array([t0], np.uint64), st]).astype(np.int64)) / 1e3)
+            ph = eng.phase_stamps().astype(np.int64)
+            if len(ph) == len(st):      # fold kernel phases of every step: start -> folded -> flags raised -> peers in -> done
+                phases.append(np.stack([ph[:, 1] - ph[:, 0], ph[:, 2] - ph[:, 1], ph[:, 3] - ph[:, 2],
+                                        st.astype(np.int64) - np.where(ph[:, 3] > 0, ph[:, 3], ph[:, 1])], axis=1) / 1e3)
             done += n
         return ms, durs, launches, ress, n
 
@@ -355,6 +361,13 @@ def run_cuda(args):
     per_step = {k: (reduce_max(v) if v is not None else None) for k, v in st.items()}
     per_step["first_us"] = reduce_max(float(durs[0])) if len(durs) else None
     per_step["first_steps_us_rank0"] = [round(float(x), 2) for x in durs[:8]]
+    if phases:
+        ph = np.concatenate(phases)[:args.steps]
+        med = np.median(ph, axis=0)
+        per_step["fold_kernel_phases_us"] = {
+            "fold": reduce_max(float(med[0])), "push_and_fence": reduce_max(float(med[1])) if world > 1 else None,
+            "wait_for_peers": reduce_max(float(med[2])) if world > 1 else None, "assemble_and_publish": reduce_max(float(med[3])),
+            "note": "median over the timed steps of the first pass, max over ranks; the fold kernel's critical path per step"}
     per_step["note"] = ("device %globaltimer stamps written by the fold kernel when a decision (exchange "
                         "included) completes; differences of consecutive stamps; each statistic is the max over ranks")
     # the LAST timed step's global bitmap and counts (catches a stale double buffer under PDL overlap)

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -142,6 +143,7 @@ struct gpr_ctx {
   unsigned int* h_err = nullptr;           // raised by a kernel whose peer wait timed out
   std::vector<Pending> pending;
   std::vector<uint64_t> stamps;            // completion stamps of the decisions retired by the last gpr_sync
+  std::vector<uint64_t> phase_stamps;      // 4 per decision: fold start, folded, flags raised, peers arrived
   unsigned long long rdv_seq = 0;          // rendezvous sequence number (same on all ranks)
 
   void* d_flush = nullptr;
@@ -200,9 +202,13 @@ struct gpr_ctx {
   unsigned char* p2p_block = nullptr;            // [flags u64 x kMaxPeers | pad | gather[2][world][stride]]
   unsigned char* p2p_peer[gpr::kMaxPeers] = {};  // peer-mapped base of every rank's block (self = local)
   size_t p2p_gather_off[2] = {0, 0};
+  size_t p2p_ll_off[2] = {0, 0};                 // tagged 64-bit slot arrays [world][stride], one per parity
+  bool exchange_ll = true;                       // tagged 64-bit slots (default); GPR_EXCHANGE=flags: data + fence + flag
+  int fold_threads = 256;                        // GPR_FOLD_THREADS: 64 / 128 / 256 threads per fold CTA
   uint32_t p2p_stride = 0;                       // words per rank slot = 2 * W_max
   bool p2p_ready = false;
   int exchange_debug = 0;                        // GPR_DEBUG_EXCHANGE (developer timing switch)
+  unsigned int poll_ns = 4000;                   // GPR_POLL_NS: longest pause between polls of the peers' flags
   unsigned long long p2p_step = 0;
 
   uint64_t launches = 0;
@@ -519,7 +525,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   // single-launch path: the last CTA stores the three counters straight into this call's
   // pinned (device-mapped, UVA) host slot, so no copy operation separates back-to-back steps
   const int slot = (int)ctx->pending.size();
-  unsigned long long* h_slot = ctx->h_counts + (size_t)slot * 4;
+  unsigned long long* h_slot = ctx->h_counts + (size_t)slot * 8;
   fp.counts = h_slot;
   fp.stamp = h_slot + 3;
   fp.err = ctx->h_err;
@@ -534,6 +540,9 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   fp.mw = MW;
   fp.world = 1, fp.rank = 0;
   fp.exchange_debug = 0;
+  fp.poll_ns = ctx->poll_ns;
+  fp.my_ll = nullptr;
+  for (int r = 0; r < gpr::kMaxPeers; ++r) fp.peer_ll[r] = nullptr;
   if (fused) {
     fp.exchange_debug = ctx->exchange_debug;
     fp.world = ctx->world, fp.rank = ctx->rank;
@@ -543,6 +552,11 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       fp.peer_flag[r] = reinterpret_cast<unsigned long long*>(ctx->p2p_peer[r]) + ctx->rank;
     }
     fp.my_flags = reinterpret_cast<const unsigned long long*>(ctx->p2p_block);
+    if (ctx->exchange_ll) {
+      for (int r = 0; r < ctx->world; ++r)
+        fp.peer_ll[r] = reinterpret_cast<unsigned long long*>(ctx->p2p_peer[r] + ctx->p2p_ll_off[sset]);
+      fp.my_ll = reinterpret_cast<unsigned long long*>(ctx->p2p_block + ctx->p2p_ll_off[sset]);
+    }
     fp.step = ++ctx->p2p_step;
     fp.out_dbits = host_out ? nullptr : res->decision_bits;
     fp.out_cbits = host_out ? nullptr : res->candidate_bits;
@@ -558,7 +572,10 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   rp.need = fp.need;
   const bool can_pdl = ctx->pdl_enabled && ctx->own_stream;
   // the fold grid: 32 bitmap words per CTA and round; a handful of CTAs even at millions of pods
-  const uint32_t fold_grid = std::max<uint32_t>(1u, std::min<uint32_t>((W + 31u) / 32u, 64u));
+  // one bitmap word per warp and round, 4 words per warp in flight (fold_words<4>): small CTAs spread the fold's
+  // loads over many SMs — each SM's path to L2 is busy with the next decision's reduce CTA
+  const uint32_t fold_threads = (uint32_t)ctx->fold_threads, fold_warps = fold_threads / 32u;
+  const uint32_t fold_grid = std::max<uint32_t>(1u, std::min<uint32_t>((W + 4u * fold_warps - 1u) / (4u * fold_warps), 148u));
 
   if (!async) {
     CU(cudaEventRecord(ctx->ev_k0, ctx->stream));
@@ -581,7 +598,7 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       // scratch set (series_max would go straight to the caller's buffer).
       const bool pdl = can_pdl && ctx->last_was_reduce && !want_smax;
       if ((rc = launch_reduce(ctx, rp, tma_ok, pdl)) != GPR_OK) return rc;
-      CU(launch_ex(gpr::k_fold, fold_grid, 256, 0, ctx->stream, can_pdl, fp));
+      CU(launch_ex(gpr::k_fold, fold_grid, fold_threads, 0, ctx->stream, can_pdl, fp));
       ctx->launches++;
       ctx->uses[sset]++;
       ctx->last_was_reduce = true;
@@ -625,12 +642,12 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       if ((rc = launch_reduce(ctx, rp, tma_ok, false)) != GPR_OK) return rc;
     }
     if (P > 0) {
-      CU(launch_ex(gpr::k_fold, fold_grid, 256, 0, ctx->stream, false, fp));
+      CU(launch_ex(gpr::k_fold, fold_grid, fold_threads, 0, ctx->stream, false, fp));
       ctx->launches++;
       ctx->uses[sset]++;
     }
   }
-  if (P == 0) h_slot[0] = h_slot[1] = h_slot[2] = h_slot[3] = 0;  // slot is not in flight
+  if (P == 0) memset(h_slot, 0, 8 * sizeof(unsigned long long));  // slot is not in flight
 
   // ---- the one collective: allgather of the packed bitmap over NVLink ----------------------
   if ((comm && !fused) || host_out || !async) ctx->last_was_reduce = false;  // something follows
@@ -684,12 +701,14 @@ int sync_impl(gpr_ctx* ctx) {
     return fail(ctx, GPR_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
   }
   ctx->stamps.clear();
+  ctx->phase_stamps.clear();
   for (const Pending& p : ctx->pending) {
-    const unsigned long long* c = ctx->h_counts + (size_t)p.slot * 4;
+    const unsigned long long* c = ctx->h_counts + (size_t)p.slot * 8;
     p.res->n_series = c[0];
     p.res->n_candidates = c[1];
     p.res->n_decisions = c[2];
     ctx->stamps.push_back(c[3]);
+    for (int k = 4; k < 8; ++k) ctx->phase_stamps.push_back(c[k]);
   }
   ctx->pending.clear();
   if (*ctx->h_err) {
@@ -830,7 +849,10 @@ void scan_producer(gpr_ctx* ctx, ScanPipe* sp, int k) {
   cudaStream_t st = ctx->up_stream[k];
   for (uint64_t c = (uint64_t)k; c < sp->n_chunks && e == cudaSuccess && !sp->stop.load(); c += (uint64_t)sp->nt) {
     // the marker block of this chunk is free once the consumer has taken chunk c - NB
-    while (c >= sp->consumed.load(std::memory_order_acquire) + NB && !sp->stop.load()) std::this_thread::yield();
+    for (int spins = 0; c >= sp->consumed.load(std::memory_order_acquire) + NB && !sp->stop.load(); ++spins) {
+      if (spins < 64) std::this_thread::yield();
+      else std::this_thread::sleep_for(std::chrono::microseconds(50));  // a slow consumer: do not burn the core
+    }
     if (sp->stop.load()) break;
     const uint64_t off = c * sp->chunk;
     const uint64_t len = std::min<uint64_t>(sp->chunk, sp->n - off);
@@ -1019,10 +1041,14 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     c->up_chunk = (size_t)std::max(1, std::min(16, env_int("GPR_TEXT_CHUNK_MB", 2))) << 20;
     c->up_slot_bytes = c->up_chunk + 4096;
     c->exchange_debug = env_int("GPR_DEBUG_EXCHANGE", 0);
+    c->poll_ns = (unsigned int)std::max(100, std::min(100000, env_int("GPR_POLL_NS", 4000)));
+    if (const char* x = getenv("GPR_EXCHANGE")) c->exchange_ll = strcmp(x, "flags") != 0;
+    c->fold_threads = env_int("GPR_FOLD_THREADS", 256);
+    if (c->fold_threads != 64 && c->fold_threads != 128 && c->fold_threads != 256) c->fold_threads = 256;
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
-                      ((size_t)kSlots * 4 + 2) * sizeof(unsigned long long)));
-    memset(c->h_counts, 0, ((size_t)kSlots * 4 + 2) * sizeof(unsigned long long));
-    c->h_mark = c->h_counts + (size_t)kSlots * 4;
+                      ((size_t)kSlots * 8 + 2) * sizeof(unsigned long long)));
+    memset(c->h_counts, 0, ((size_t)kSlots * 8 + 2) * sizeof(unsigned long long));
+    c->h_mark = c->h_counts + (size_t)kSlots * 8;
     c->h_err = reinterpret_cast<unsigned int*>(c->h_mark + 1);
     c->pending.reserve(kSlots);
     c->stamps.reserve(kSlots);
@@ -1345,7 +1371,10 @@ int gpr_p2p_init(gpr_ctx* ctx, int rank, int world, uint32_t max_pods_per_rank, 
   const size_t gather_bytes = ((size_t)world * ctx->p2p_stride * 4u + 255u) & ~(size_t)255u;
   ctx->p2p_gather_off[0] = 256;
   ctx->p2p_gather_off[1] = 256 + gather_bytes;
-  const size_t total = 256 + 2 * gather_bytes;
+  const size_t ll_bytes = ((size_t)world * ctx->p2p_stride * 8u + 255u) & ~(size_t)255u;
+  ctx->p2p_ll_off[0] = 256 + 2 * gather_bytes;
+  ctx->p2p_ll_off[1] = ctx->p2p_ll_off[0] + ll_bytes;
+  const size_t total = 256 + 2 * gather_bytes + 2 * ll_bytes;
   CU(cudaMalloc(reinterpret_cast<void**>(&ctx->p2p_block), total));
   CU(cudaMemset(ctx->p2p_block, 0, total));
   cudaIpcMemHandle_t h;
@@ -1456,6 +1485,13 @@ int gpr_step_stamps(gpr_ctx* ctx, uint64_t* ns, uint32_t cap, uint32_t* n, uint6
   if (begin_ns) *begin_ns = *ctx->h_mark;
   if (ns)
     for (uint32_t i = 0; i < cap && i < *n; ++i) ns[i] = ctx->stamps[i];
+  return GPR_OK;
+}
+int gpr_phase_stamps(gpr_ctx* ctx, uint64_t* ns, uint32_t cap, uint32_t* n) {
+  if (!ctx || !n) return GPR_E_INVALID;
+  *n = (uint32_t)ctx->phase_stamps.size();
+  if (ns)
+    for (uint32_t i = 0; i < cap && i < *n; ++i) ns[i] = ctx->phase_stamps[i];
   return GPR_OK;
 }
 int gpr_p2p_debug(gpr_ctx* ctx, int32_t mode) {

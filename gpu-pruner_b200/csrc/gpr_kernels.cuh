@@ -82,8 +82,14 @@ struct FoldParams {
   uint32_t* out_cbits;
   int exchange_debug;                    // 0 normal; timing switches (gpr_p2p_debug): 1 = do not wait for the
                                          // peers, 2 = no push at all (results are then NOT global)
-  unsigned long long* stamp;             // host-mapped: %globaltimer (ns) when this decision completed
+  unsigned long long* stamp;             // host-mapped [5]: %globaltimer (ns) when this decision completed, then
+                                         // fold start / folded / flags raised / peers arrived (exchange phases)
   unsigned int* err;                     // host-mapped: set to 1 when a peer never showed up (see spin_until)
+  unsigned int poll_ns;                  // longest pause between two polls of the peers' flags
+  // tagged-slot form of the exchange (GPR_EXCHANGE=ll): every word travels as one 64-bit store {step tag, word} into
+  // the receiver's slot array, so there is no fence and no flag — a slot is valid when its tag says so
+  unsigned long long* peer_ll[kMaxPeers];  // slot array (this call's parity) on rank r; null = flag protocol
+  unsigned long long* my_ll;               // local slot array (this call's parity)
 };
 
 // One rank's view of the exchange block header, for the stand-alone rendezvous (gpr_timer_begin)
@@ -183,16 +189,20 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// Polls with RELAXED loads and fences once when the value has arrived: an acquire per poll would put a
-// system-scope fence into the loop, on an SM that is streaming the next decision's window at the same time.
+// Polls with RELAXED loads, fences once when the value has arrived, and polls RARELY: the CTA that waits shares
+// the chip with the next decision's reduce kernel, and every system-scope poll of a peer-written line costs that
+// kernel bandwidth (measured at 8 GPUs: polling every 0.3 us cost 5.5 us per step, every ~1.5 us 1.8 us).  The
+// exchange has a whole step of slack before anything depends on it, so a late wake-up is free.
 __device__ __forceinline__ void spin_until_sys(const unsigned long long* p, unsigned long long want,
-                                               unsigned int* err) {
+                                               unsigned int* err, unsigned int poll_ns) {
   if (ld_relaxed_sys_u64(p) < want) {
     const unsigned long long t0 = gtime();
-    unsigned int polls = 0;
-    while (ld_relaxed_sys_u64(p) < want) {
-      __nanosleep(100);
-      if ((++polls & 1023u) == 0 && gtime() - t0 > kPeerTimeoutNs) {
+    unsigned int polls = 0, sleep_ns = 200;
+    while (true) {
+      __nanosleep(sleep_ns);
+      if (ld_relaxed_sys_u64(p) >= want) break;
+      if (sleep_ns < poll_ns) sleep_ns = min(poll_ns, sleep_ns * 2);
+      if ((++polls & 255u) == 0 && gtime() - t0 > kPeerTimeoutNs) {
         if (err) *err = 1u;
         return;
       }
@@ -236,6 +246,7 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
                                            uint32_t w_step, int lane, unsigned long long& n_series,
                                            unsigned long long& n_cand, unsigned long long& n_dec) {
   const uint32_t last_pod = f.P - 1u;  // callers guarantee P > 0
+  bool waited = false;  // (the CTA-wide barrier below: every warp passes it exactly once, see the end)
   for (uint32_t w0 = w_begin; w0 < w_end; w0 += w_step * BATCH) {
     uint32_t idle[BATCH], veto[BATCH];
     uint8_t elig[BATCH];
@@ -254,6 +265,13 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
       }
       elig[b] = f.eligible ? f.eligible[pod] : (uint8_t)1;
       created[b] = f.created ? f.created[pod] : (long long)0x8000000000000000ll;
+    }
+    if (!waited) {
+      // The caller's output buffers may still be written by the previous decision's fold.  That wait comes AFTER
+      // the loads above are in flight: while the next reduce kernel streams, every trip to L2 costs microseconds.
+      if (threadIdx.x == 0) spin_until_gpu(f.prev_done, f.prev_need);
+      __syncthreads();
+      waited = true;
     }
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) {
@@ -275,6 +293,16 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
           if (veto[b]) f.veto_mask[(size_t)pod * f.mw + k] = 0u;
         }
       }
+      if (f.my_ll && f.exchange_debug != 2) {
+        // tagged-slot exchange: the word leaves for every peer the moment it exists — lane 2 i sends the decision
+        // word to the i-th peer, lane 2 i + 1 the candidate word (one 64-bit NVLink store each, no fence, no flag)
+        const int peer = lane >> 1, r = peer + (peer >= f.rank ? 1 : 0);
+        if (peer < f.world - 1) {
+          const unsigned long long v = ((f.step & 0xffffffffull) << 32) | (unsigned long long)((lane & 1) ? cw : dw);
+          unsigned long long* dst = f.peer_ll[r] + (size_t)f.rank * f.rank_stride + ((lane & 1) ? (f.P + 31u) / 32u : 0u) + w;
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+        }
+      }
       if (lane == 0) {
         f.dbits[w] = dw;
         if (f.cbits) f.cbits[w] = cw;
@@ -284,6 +312,10 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
         n_dec += __popc(dw);
       }
     }
+  }
+  if (!waited) {  // a warp without a word of its own still takes part in the barrier
+    if (threadIdx.x == 0) spin_until_gpu(f.prev_done, f.prev_need);
+    __syncthreads();
   }
 }
 
@@ -299,9 +331,10 @@ __device__ __forceinline__ void block_counts(unsigned long long* sh3, unsigned l
 
 // The one exchange of the multi-GPU path, fused into the folding CTA.  f.dbits / f.cbits point at
 // this rank's slot of the LOCAL gather buffer; the same 2*W words are pushed to every peer.
-__device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n_words) {
+// `mine` = this rank's 2 * n_words words [decision | candidate]: its slot of the local gather buffer, or the
+// copy the single-CTA fold keeps in shared memory (no second trip to L2 before the push)
+__device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n_words, const uint32_t* mine) {
   __syncthreads();  // the fold's word stores are visible to the whole CTA
-  const uint32_t* mine = f.peer_gather[f.rank] + (size_t)f.rank * f.rank_stride;
   const uint32_t span = 2u * n_words;  // [decision | candidate], candidate slot always present
   // each word is read once and fanned out to every peer (a per-peer reload would put world-1
   // dependent L2 round trips per word on this CTA's critical path)
@@ -310,7 +343,7 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t w = w0 + k * blockDim.x;
-      v[k] = w < span ? __ldcg(mine + w) : 0u;
+      v[k] = w < span ? mine[w] : 0u;
     }
     for (int r = 0; r < f.world; ++r) {
       if (r == f.rank) continue;
@@ -327,9 +360,11 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
   __syncthreads();
   if ((int)threadIdx.x < f.world && (int)threadIdx.x != f.rank && f.exchange_debug != 2) {
     st_release_sys_u64(f.peer_flag[threadIdx.x], f.step);             // "rank's words of step k are there"
-    if (f.exchange_debug == 0) spin_until_sys(f.my_flags + threadIdx.x, f.step, f.err);
+    if (f.stamp && threadIdx.x == (f.rank == 0 ? 1u : 0u)) f.stamp[3] = gtime();   // flags raised (fence included)
+    if (f.exchange_debug == 0) spin_until_sys(f.my_flags + threadIdx.x, f.step, f.err, f.poll_ns);
   }
   __syncthreads();
+  if (threadIdx.x == 0 && f.stamp) f.stamp[4] = gtime();             // every peer's words have arrived
   // assemble the caller's rank-major global bitmaps from the local gather buffer
   if (f.out_dbits) {
     const uint32_t* g = f.peer_gather[f.rank];
@@ -337,6 +372,62 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
       const uint32_t r = i / n_words, w = i - r * n_words;
       f.out_dbits[i] = __ldcg(g + (size_t)r * f.rank_stride + w);
       if (f.out_cbits) f.out_cbits[i] = __ldcg(g + (size_t)r * f.rank_stride + n_words + w);
+    }
+  }
+}
+
+// Tagged-slot form of the same exchange: no system-scope fence on the sender (under load the fence has to wait for
+// the acknowledgements of stores into seven busy GPUs), no flags, and no funnel through the last CTA on the sending
+// side: every fold CTA sends its words as it produces them (fold_words); here the last CTA only reads every peer's
+// slots until their tags match and assembles the result.
+__device__ __forceinline__ void exchange_bitmaps_ll(const FoldParams& f, uint32_t n_words, const uint32_t* mine) {
+  __syncthreads();  // the fold's word stores are visible to the whole CTA
+  uint32_t* g = f.peer_gather[f.rank];  // local gather buffer: [rank][decision | candidate]
+  const uint32_t span = 2u * n_words;
+  const unsigned long long tag = (f.step & 0xffffffffull) << 32;
+  (void)mine;  // every fold CTA has already sent its own words (fold_words)
+  if (threadIdx.x == 0 && f.stamp) f.stamp[3] = gtime();
+  if (f.exchange_debug == 0) {
+    // every slot of every peer: issue a batch of loads, re-poll only what has not arrived
+    const uint32_t total = (uint32_t)f.world * span;
+    const unsigned long long t0 = gtime();
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += 4u * blockDim.x) {
+      unsigned int pending = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = i0 + k * blockDim.x;
+        if (i < total && (int)(i / span) != f.rank) pending |= 1u << k;
+      }
+      unsigned int polls = 0;
+      while (pending) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!(pending >> k & 1u)) continue;
+          const uint32_t i = i0 + k * blockDim.x;
+          const uint32_t r = i / span, w = i - r * span;
+          const unsigned long long v = ld_relaxed_sys_u64(f.my_ll + (size_t)r * f.rank_stride + w);
+          if ((v >> 32) == (tag >> 32)) {
+            g[(size_t)r * f.rank_stride + w] = (uint32_t)v;   // the local gather buffer holds every rank's words again
+            pending &= ~(1u << k);
+          }
+        }
+        if (pending) {
+          __nanosleep(100);
+          if ((++polls & 1023u) == 0 && gtime() - t0 > kPeerTimeoutNs) {
+            if (f.err) *f.err = 1u;
+            break;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && f.stamp) f.stamp[4] = gtime();
+  if (f.out_dbits) {
+    for (uint32_t i = threadIdx.x; i < n_words * (uint32_t)f.world; i += blockDim.x) {
+      const uint32_t r = i / n_words, w = i - r * n_words;
+      f.out_dbits[i] = g[(size_t)r * f.rank_stride + w];
+      if (f.out_cbits) f.out_cbits[i] = g[(size_t)r * f.rank_stride + n_words + w];
     }
   }
 }
@@ -352,9 +443,7 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   pdl_launch_dependents();   // the next decision's reduce kernel may start streaming right away
   if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
   pdl_wait_prior_grids();    // reduce grid of THIS decision complete, masks visible
-  // the caller's output buffers may still be written by the previous decision's fold
-  if (threadIdx.x == 0) spin_until_gpu(f.prev_done, f.prev_need);
-  __syncthreads();
+  const unsigned long long t_start = gtime();
   const int lane = threadIdx.x & 31;
   const uint32_t warps_per_cta = blockDim.x >> 5;
   const uint32_t gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
@@ -362,8 +451,7 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   unsigned long long a = 0, b = 0, c = 0;
   fold_words<4>(f, gw, n_words, gridDim.x * warps_per_cta, lane, a, b, c);
   block_counts(s_cnt, a, b, c, lane);
-  __threadfence();
-  __syncthreads();
+  __syncthreads();  // (thread 0's fence below is cumulative over what the CTA stored before this barrier)
   if (threadIdx.x == 0) {
     if (s_cnt[0] | s_cnt[1] | s_cnt[2]) {
       atomicAdd(&f.acc[0], s_cnt[0]);
@@ -376,7 +464,13 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (f.world > 1) exchange_bitmaps(f, n_words);
+  if (threadIdx.x == 0 && f.stamp) f.stamp[1] = t_start, f.stamp[2] = gtime(), f.stamp[3] = f.stamp[4] = 0;
+  if (f.world > 1) {
+    // (other CTAs wrote most of the words: read them at L2)
+    const uint32_t* mine = f.peer_gather[f.rank] + (size_t)f.rank * f.rank_stride;
+    if (f.my_ll) exchange_bitmaps_ll(f, n_words, mine);
+    else exchange_bitmaps(f, n_words, mine);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     f.counts[0] = __ldcg(&f.acc[0]);
@@ -397,7 +491,7 @@ __global__ void __launch_bounds__(32) k_rendezvous(RendezvousParams q) {
   const int t = threadIdx.x;
   if (t < q.world && t != q.rank) {
     st_release_sys_u64(q.peer_flag[t], q.seq);
-    spin_until_sys(q.my_flags + t, q.seq, q.err);
+    spin_until_sys(q.my_flags + t, q.seq, q.err, 200u);  // the rendezvous wants a prompt release
   }
   __syncwarp();
   if (t == 0 && q.stamp) *q.stamp = gtime();

@@ -334,6 +334,14 @@ class IdleEngine:
         self._check(self._lib.gpr_step_stamps(self._h, _ptr(out), n.value, C.byref(n), C.byref(t0)))
         return int(t0.value), out[:n.value]
 
+    def phase_stamps(self) -> np.ndarray:
+        """[n, 4] ns: fold start, folded, flags raised, peers arrived — per decision retired by the last sync"""
+        n = C.c_uint32()
+        self._check(self._lib.gpr_phase_stamps(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 4), np.uint64)
+        self._check(self._lib.gpr_phase_stamps(self._h, _ptr(out), n.value, C.byref(n)))
+        return out[:n.value].reshape(-1, 4)
+
     def p2p_debug(self, mode: int):
         self._check(self._lib.gpr_p2p_debug(self._h, mode))
 

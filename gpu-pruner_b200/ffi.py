@@ -113,6 +113,7 @@ PROTOTYPES = {
     "gpr_timer_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "gpr_step_stamps": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "gpr_p2p_debug": (C.c_int, [_P, C.c_int32]),
+    "gpr_phase_stamps": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "gpr_flush_l2": (C.c_int, [_P]),
     "gpr_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "gpr_get_device_info": (C.c_int, [_P, C.POINTER(gpr_device_info)]),

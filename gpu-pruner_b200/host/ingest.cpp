@@ -239,13 +239,21 @@ void apply_node_types(Window& w, const Json& dmi) {
       throw std::runtime_error("Failed to run query! found duplicate series for the match group {Hostname=\"" + host +
                                "\"} on the right hand-side of the operation (node_dmi_info)");
   }
-  for (PodEntry& pe : w.pods)
-    for (GpuSlot& g : pe.slots) {
-      auto it = by_host.find(g.hostname);
-      // no DMI series for the host: `or on (...)` restores the element without the label; a DMI series
-      // without product_name: group_left copies an absent label.  Both read back as "unknown" (lib.rs:176-179)
-      g.node_type = it != by_host.end() && !it->second.empty() ? it->second : "unknown";
-    }
+  // no DMI series for the host: `or on (...)` restores the element without the label; a DMI series
+  // without product_name: group_left copies an absent label.  Both read back as "unknown" (lib.rs:176-179)
+  auto type_of = [&](const GpuSlot& g) -> const std::string& {
+    static const std::string unknown = "unknown";
+    auto it = by_host.find(g.hostname);
+    return it != by_host.end() && !it->second.empty() ? it->second : unknown;
+  };
+  // the pod table may be shared with the ingest session of daemon mode (copy-on-write): write only what changes
+  const PodList& current = w.pods;
+  for (size_t p = 0; p < current.size(); ++p)
+    for (size_t g = 0; g < current[p].slots.size(); ++g)
+      if (current[p].slots[g].node_type != type_of(current[p].slots[g])) {
+        GpuSlot& slot = w.pods[p].slots[g];
+        slot.node_type = type_of(slot);
+      }
 }
 
 // =====================================================================================================

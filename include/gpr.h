@@ -269,6 +269,10 @@ GPR_API int gpr_timer_end(gpr_ctx *ctx, double *ms);
  * decisions retired (may exceed cap).  Differences of consecutive stamps are the per-step device times
  * SURVEY.md §8(d) asks the median of.                                                              */
 GPR_API int gpr_step_stamps(gpr_ctx *ctx, uint64_t *ns, uint32_t cap, uint32_t *n, uint64_t *begin_ns);
+/* Four more stamps per retired decision, for attributing the time of the fold / exchange kernel: the fold kernel's
+ * start (the reduce has completed and the previous fold is done), fold finished, peer flags raised (stores and
+ * system-scope fence done; 0 without an exchange), all peers' words arrived (0 without an exchange).           */
+GPR_API int gpr_phase_stamps(gpr_ctx *ctx, uint64_t *ns, uint32_t cap, uint32_t *n);
 /* writes > L2-size bytes so the next launch starts with a cold L2                          */
 GPR_API int gpr_flush_l2(gpr_ctx *ctx);
 /* number of kernels this context has launched since creation                               */

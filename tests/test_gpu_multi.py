@@ -26,6 +26,8 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
     import gpu_pruner_b200 as g
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    # the fused exchange has two wire protocols: tagged 64-bit slots (default) and data + fence + flag
+    os.environ["GPR_EXCHANGE"] = "flags" if mode == "p2p-flags" else "ll"
     eng = g.IdleEngine(device=rank, max_pods=20000, max_gpus=G, max_samples=T)
     sh = g.shard_pods(total, rank, world)
     P = sh.pods_per_rank
@@ -84,7 +86,7 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p-flags"])
 @pytest.mark.parametrize("total", [5000, 64 * 1000 + 7])
 def test_sharded_decision_allgather(total, mode, tmp_path, oracle_c):
     if torch.cuda.device_count() < 2:
