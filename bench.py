@@ -538,7 +538,8 @@ def run_cuda(args):
             "config": workload_config(world),
             "engine": {"kernel": kname,
                        "exchange": None if world == 1 else (
-                           "fused NVLink peer stores in the fold kernel" if args.collective == "p2p" else "ncclAllGather"),
+                           "fused NVLink peer stores in the fold kernel, protocol "
+                           + os.environ.get("GPR_EXCHANGE", "default") if args.collective == "p2p" else "ncclAllGather"),
                        "timing": "K steps in one CUDA-event region after a device-side rendezvous of all ranks, "
                                  "max over ranks"},
             "per_step": per_step,

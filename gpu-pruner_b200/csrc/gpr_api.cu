@@ -36,6 +36,7 @@ constexpr int kLdgUnroll = 8;
 constexpr size_t kTmaSmemBudget = 208 * 1024;
 constexpr int kSlots = 256;      // outstanding async results
 constexpr int kMaxChunkEvents = 64;
+constexpr int kExchangeDepth = 4;  // exchange buffer sets of the fused multi-GPU path = 2 x scratch sets
 
 std::mutex g_err_mu;
 char g_create_err[512] = "";
@@ -201,9 +202,13 @@ struct gpr_ctx {
   // fused exchange over peer memory (gpr_p2p_init / gpr_p2p_attach)
   unsigned char* p2p_block = nullptr;            // [flags u64 x kMaxPeers | pad | gather[2][world][stride]]
   unsigned char* p2p_peer[gpr::kMaxPeers] = {};  // peer-mapped base of every rank's block (self = local)
-  size_t p2p_gather_off[2] = {0, 0};
-  size_t p2p_ll_off[2] = {0, 0};                 // tagged 64-bit slot arrays [world][stride], one per parity
+  // Exchange buffers are kExchangeDepth deep (step % depth), twice the number of scratch sets: with the late
+  // output ordering a rank may push step n + 4 only after every peer has consumed step n (see k_fold)
+  size_t p2p_gather_off[kExchangeDepth] = {};
+  size_t p2p_ll_off[kExchangeDepth] = {};        // tagged 64-bit slot arrays [world][stride], one per step % depth
   bool exchange_ll = true;                       // tagged 64-bit slots (default); GPR_EXCHANGE=flags: data + fence + flag
+  bool exchange_late = false;                    // GPR_EXCHANGE=pipelined: tagged slots, and a fold waits for its
+                                                 // predecessor only before it writes the caller's outputs
   int fold_threads = 256;                        // GPR_FOLD_THREADS: 64 / 128 / 256 threads per fold CTA
   uint32_t p2p_stride = 0;                       // words per rank slot = 2 * W_max
   bool p2p_ready = false;
@@ -506,8 +511,9 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   // pods vetoed by the power clause: never exchanged (this rank's pods only)
   uint32_t* vbits_dev = res->veto_bits ? (host_out ? ctx->d_bits + 2 * (size_t)W : res->veto_bits) : nullptr;
   uint32_t* my_gather = nullptr;  // local gather buffer of this call (fused exchange)
+  const unsigned xset = (unsigned)((ctx->p2p_step + 1ull) % kExchangeDepth);  // exchange buffers of this step
   if (fused) {
-    my_gather = reinterpret_cast<uint32_t*>(ctx->p2p_block + ctx->p2p_gather_off[sset]);
+    my_gather = reinterpret_cast<uint32_t*>(ctx->p2p_block + ctx->p2p_gather_off[xset]);
     dbits_dev = my_gather + (size_t)ctx->rank * ctx->p2p_stride;   // this rank's slot: [decision | candidate]
     cbits_dev = dbits_dev + W;
   }
@@ -542,20 +548,23 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
   fp.exchange_debug = 0;
   fp.poll_ns = ctx->poll_ns;
   fp.my_ll = nullptr;
+  fp.late_order = 0;
   for (int r = 0; r < gpr::kMaxPeers; ++r) fp.peer_ll[r] = nullptr;
   if (fused) {
     fp.exchange_debug = ctx->exchange_debug;
     fp.world = ctx->world, fp.rank = ctx->rank;
     fp.rank_stride = ctx->p2p_stride;
     for (int r = 0; r < ctx->world; ++r) {
-      fp.peer_gather[r] = reinterpret_cast<uint32_t*>(ctx->p2p_peer[r] + ctx->p2p_gather_off[sset]);
+      fp.peer_gather[r] = reinterpret_cast<uint32_t*>(ctx->p2p_peer[r] + ctx->p2p_gather_off[xset]);
       fp.peer_flag[r] = reinterpret_cast<unsigned long long*>(ctx->p2p_peer[r]) + ctx->rank;
     }
     fp.my_flags = reinterpret_cast<const unsigned long long*>(ctx->p2p_block);
     if (ctx->exchange_ll) {
       for (int r = 0; r < ctx->world; ++r)
-        fp.peer_ll[r] = reinterpret_cast<unsigned long long*>(ctx->p2p_peer[r] + ctx->p2p_ll_off[sset]);
-      fp.my_ll = reinterpret_cast<unsigned long long*>(ctx->p2p_block + ctx->p2p_ll_off[sset]);
+        fp.peer_ll[r] = reinterpret_cast<unsigned long long*>(ctx->p2p_peer[r] + ctx->p2p_ll_off[xset]);
+      fp.my_ll = reinterpret_cast<unsigned long long*>(ctx->p2p_block + ctx->p2p_ll_off[xset]);
+      // (veto bits go straight to the caller's buffer from every fold CTA, so that call keeps the early wait)
+      fp.late_order = ctx->exchange_late && vbits_dev == nullptr ? 1 : 0;
     }
     fp.step = ++ctx->p2p_step;
     fp.out_dbits = host_out ? nullptr : res->decision_bits;
@@ -1042,7 +1051,10 @@ int gpr_create(const gpr_config* cfg, gpr_ctx** out) {
     c->up_slot_bytes = c->up_chunk + 4096;
     c->exchange_debug = env_int("GPR_DEBUG_EXCHANGE", 0);
     c->poll_ns = (unsigned int)std::max(100, std::min(100000, env_int("GPR_POLL_NS", 4000)));
-    if (const char* x = getenv("GPR_EXCHANGE")) c->exchange_ll = strcmp(x, "flags") != 0;
+    if (const char* x = getenv("GPR_EXCHANGE")) {
+      c->exchange_ll = strcmp(x, "flags") != 0;
+      c->exchange_late = strcmp(x, "pipelined") == 0;
+    }
     c->fold_threads = env_int("GPR_FOLD_THREADS", 256);
     if (c->fold_threads != 64 && c->fold_threads != 128 && c->fold_threads != 256) c->fold_threads = 256;
     CU(cudaMallocHost(reinterpret_cast<void**>(&c->h_counts),
@@ -1369,12 +1381,12 @@ int gpr_p2p_init(gpr_ctx* ctx, int rank, int world, uint32_t max_pods_per_rank, 
   const uint32_t w_max = (max_pods_per_rank + 31u) / 32u;
   ctx->p2p_stride = 2u * std::max<uint32_t>(w_max, 1u);
   const size_t gather_bytes = ((size_t)world * ctx->p2p_stride * 4u + 255u) & ~(size_t)255u;
-  ctx->p2p_gather_off[0] = 256;
-  ctx->p2p_gather_off[1] = 256 + gather_bytes;
   const size_t ll_bytes = ((size_t)world * ctx->p2p_stride * 8u + 255u) & ~(size_t)255u;
-  ctx->p2p_ll_off[0] = 256 + 2 * gather_bytes;
-  ctx->p2p_ll_off[1] = ctx->p2p_ll_off[0] + ll_bytes;
-  const size_t total = 256 + 2 * gather_bytes + 2 * ll_bytes;
+  for (int k = 0; k < kExchangeDepth; ++k) {
+    ctx->p2p_gather_off[k] = 256 + (size_t)k * gather_bytes;
+    ctx->p2p_ll_off[k] = 256 + (size_t)kExchangeDepth * gather_bytes + (size_t)k * ll_bytes;
+  }
+  const size_t total = 256 + (size_t)kExchangeDepth * (gather_bytes + ll_bytes);
   CU(cudaMalloc(reinterpret_cast<void**>(&ctx->p2p_block), total));
   CU(cudaMemset(ctx->p2p_block, 0, total));
   cudaIpcMemHandle_t h;

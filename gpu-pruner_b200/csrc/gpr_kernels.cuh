@@ -90,6 +90,13 @@ struct FoldParams {
   // the receiver's slot array, so there is no fence and no flag — a slot is valid when its tag says so
   unsigned long long* peer_ll[kMaxPeers];  // slot array (this call's parity) on rank r; null = flag protocol
   unsigned long long* my_ll;               // local slot array (this call's parity)
+  // 1 (tagged slots only): this fold's words are produced, sent and collected without waiting for the previous
+  // decision's fold; only the CTA that assembles the caller's outputs waits for it.  The peers' wait — the long part
+  // of an exchange — then overlaps with the predecessor's instead of queueing behind it.  Safe because the exchange
+  // buffers are 2 x (scratch sets) deep: my push of step n + 4 follows my fold n + 2 (its scratch set is reused by
+  // reduce n + 4), which saw every peer's step n + 2 words, which a peer sends only after its reduce n + 2 ran, which
+  // waited for that peer's fold n — so nobody still polls for step n when its slots are overwritten.
+  int late_order;
 };
 
 // One rank's view of the exchange block header, for the stand-alone rendezvous (gpr_timer_begin)
@@ -269,7 +276,8 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
     if (!waited) {
       // The caller's output buffers may still be written by the previous decision's fold.  That wait comes AFTER
       // the loads above are in flight: while the next reduce kernel streams, every trip to L2 costs microseconds.
-      if (threadIdx.x == 0) spin_until_gpu(f.prev_done, f.prev_need);
+      // (late_order: nothing written here is the caller's — the assembling CTA waits instead, see k_fold)
+      if (threadIdx.x == 0 && !f.late_order) spin_until_gpu(f.prev_done, f.prev_need);
       __syncthreads();
       waited = true;
     }
@@ -314,7 +322,7 @@ __device__ __forceinline__ void fold_words(const FoldParams& f, uint32_t w_begin
     }
   }
   if (!waited) {  // a warp without a word of its own still takes part in the barrier
-    if (threadIdx.x == 0) spin_until_gpu(f.prev_done, f.prev_need);
+    if (threadIdx.x == 0 && !f.late_order) spin_until_gpu(f.prev_done, f.prev_need);
     __syncthreads();
   }
 }
@@ -422,7 +430,12 @@ __device__ __forceinline__ void exchange_bitmaps_ll(const FoldParams& f, uint32_
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && f.stamp) f.stamp[4] = gtime();
+  if (threadIdx.x == 0) {
+    if (f.stamp) f.stamp[4] = gtime();
+    // the caller's buffers belong to the previous decision until its fold has finished
+    if (f.late_order) spin_until_gpu(f.prev_done, f.prev_need);
+  }
+  __syncthreads();
   if (f.out_dbits) {
     for (uint32_t i = threadIdx.x; i < n_words * (uint32_t)f.world; i += blockDim.x) {
       const uint32_t r = i / n_words, w = i - r * n_words;

@@ -4,6 +4,7 @@ run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`.""
 import os
 import socket
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -27,7 +28,7 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     # the fused exchange has two wire protocols: tagged 64-bit slots (default) and data + fence + flag
-    os.environ["GPR_EXCHANGE"] = "flags" if mode == "p2p-flags" else "ll"
+    os.environ["GPR_EXCHANGE"] = {"p2p-flags": "flags", "p2p-pipelined": "pipelined"}.get(mode, "ll")
     eng = g.IdleEngine(device=rank, max_pods=20000, max_gpus=G, max_samples=T)
     sh = g.shard_pods(total, rank, world)
     P = sh.pods_per_rank
@@ -57,6 +58,26 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
         eng.decide_ptr(u, P, G, T, db2, eligible=e, blocking=False)
     eng.sync()
     assert torch.equal(db, db2)
+    # ... and in order: two different windows alternate into ONE output buffer, the last one launched must be the
+    # one that stays (a fold may produce, send and collect its words while its predecessor is still exchanging, but
+    # it writes the caller's buffers after it); one rank launches late so that the ranks run steps apart
+    u2 = torch.full((P, G, T), float("nan"), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    eng.synth_fill(seed + 1, 0, u2, sh.pod_begin, sh.pods_real, G, T)
+    db_b = torch.zeros_like(db)
+    eng.decide_ptr(u2, P, G, T, db_b, eligible=e)
+    assert not torch.equal(db, db_b)
+    for n_calls, want in ((9, db), (12, db_b)):
+        db3 = torch.zeros_like(db)
+        torch.cuda.synchronize()
+        dist.barrier()
+        for it in range(n_calls):
+            if rank == world - 1 and it in (3, 4, 7):
+                time.sleep(0.003)
+            eng.decide_ptr(u if it % 2 == 0 else u2, P, G, T, db3, eligible=e, blocking=False)
+        eng.sync()
+        assert torch.equal(db3, want), (mode, n_calls)
+    del u2
     # the collective timer: device-side rendezvous, then per-decision completion stamps
     eng.timer_begin()
     for it in range(5):
@@ -86,7 +107,7 @@ def _rank(rank, world, port, total, G, T, seed, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p-flags"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p-flags", "p2p-pipelined"])
 @pytest.mark.parametrize("total", [5000, 64 * 1000 + 7])
 def test_sharded_decision_allgather(total, mode, tmp_path, oracle_c):
     if torch.cuda.device_count() < 2:
