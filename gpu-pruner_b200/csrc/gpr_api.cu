@@ -607,7 +607,8 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       // scratch set (series_max would go straight to the caller's buffer).
       const bool pdl = can_pdl && ctx->last_was_reduce && !want_smax;
       if ((rc = launch_reduce(ctx, rp, tma_ok, pdl)) != GPR_OK) return rc;
-      CU(launch_ex(gpr::k_fold, fold_grid, fold_threads, 0, ctx->stream, can_pdl, fp));
+      CU(fused ? launch_ex(gpr::k_fold<true>, fold_grid, fold_threads, 0, ctx->stream, can_pdl, fp)
+               : launch_ex(gpr::k_fold<false>, fold_grid, fold_threads, 0, ctx->stream, can_pdl, fp));
       ctx->launches++;
       ctx->uses[sset]++;
       ctx->last_was_reduce = true;
@@ -651,7 +652,8 @@ int decide_impl(gpr_ctx* ctx, const gpr_window* win, gpr_result* res, bool resid
       if ((rc = launch_reduce(ctx, rp, tma_ok, false)) != GPR_OK) return rc;
     }
     if (P > 0) {
-      CU(launch_ex(gpr::k_fold, fold_grid, fold_threads, 0, ctx->stream, false, fp));
+      CU(fused ? launch_ex(gpr::k_fold<true>, fold_grid, fold_threads, 0, ctx->stream, false, fp)
+               : launch_ex(gpr::k_fold<false>, fold_grid, fold_threads, 0, ctx->stream, false, fp));
       ctx->launches++;
       ctx->uses[sset]++;
     }

@@ -388,6 +388,8 @@ __device__ __forceinline__ void exchange_bitmaps(const FoldParams& f, uint32_t n
 // the acknowledgements of stores into seven busy GPUs), no flags, and no funnel through the last CTA on the sending
 // side: every fold CTA sends its words as it produces them (fold_words); here the last CTA only reads every peer's
 // slots until their tags match and assembles the result.
+constexpr int kCollectBatch = 16;   // slots per thread and polling round (8 ranks x 10,000 pods: 20 per thread, two rounds)
+constexpr int kAssembleBatch = 8;   // output words per thread and round (same case: 10 per thread)
 __device__ __forceinline__ void exchange_bitmaps_ll(const FoldParams& f, uint32_t n_words, const uint32_t* mine) {
   __syncthreads();  // the fold's word stores are visible to the whole CTA
   uint32_t* g = f.peer_gather[f.rank];  // local gather buffer: [rank][decision | candidate]
@@ -396,26 +398,31 @@ __device__ __forceinline__ void exchange_bitmaps_ll(const FoldParams& f, uint32_
   (void)mine;  // every fold CTA has already sent its own words (fold_words)
   if (threadIdx.x == 0 && f.stamp) f.stamp[3] = gtime();
   if (f.exchange_debug == 0) {
-    // every slot of every peer: issue a batch of loads, re-poll only what has not arrived
+    // Every slot of every peer.  All loads of a round are in flight before the first one is looked at: while the
+    // next reduce kernel streams, a dependent trip to L2 costs ~0.7 us, and a load-compare-store chain per slot (20
+    // slots per thread at 8 ranks and 10,000 pods) was the 14 us "wait for the peers" of the first version.
     const uint32_t total = (uint32_t)f.world * span;
     const unsigned long long t0 = gtime();
-    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += 4u * blockDim.x) {
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += (uint32_t)kCollectBatch * blockDim.x) {
       unsigned int pending = 0;
+      uint32_t off[kCollectBatch];  // r * rank_stride + w (< 2^32: at most 8 ranks x 2^28 words)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t i = i0 + k * blockDim.x;
-        if (i < total && (int)(i / span) != f.rank) pending |= 1u << k;
+      for (int k = 0; k < kCollectBatch; ++k) {
+        const uint32_t i = i0 + (uint32_t)k * blockDim.x;
+        const uint32_t r = i / span, w = i - r * span;
+        off[k] = r * f.rank_stride + w;
+        if (i < total && (int)r != f.rank) pending |= 1u << k;
       }
       unsigned int polls = 0;
       while (pending) {
+        unsigned long long v[kCollectBatch];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!(pending >> k & 1u)) continue;
-          const uint32_t i = i0 + k * blockDim.x;
-          const uint32_t r = i / span, w = i - r * span;
-          const unsigned long long v = ld_relaxed_sys_u64(f.my_ll + (size_t)r * f.rank_stride + w);
-          if ((v >> 32) == (tag >> 32)) {
-            g[(size_t)r * f.rank_stride + w] = (uint32_t)v;   // the local gather buffer holds every rank's words again
+        for (int k = 0; k < kCollectBatch; ++k)
+          v[k] = (pending >> k & 1u) ? ld_relaxed_sys_u64(f.my_ll + off[k]) : 0ull;
+#pragma unroll
+        for (int k = 0; k < kCollectBatch; ++k) {
+          if ((pending >> k & 1u) && (v[k] >> 32) == (tag >> 32)) {
+            g[off[k]] = (uint32_t)v[k];   // the local gather buffer holds every rank's words again
             pending &= ~(1u << k);
           }
         }
@@ -437,10 +444,28 @@ __device__ __forceinline__ void exchange_bitmaps_ll(const FoldParams& f, uint32_
   }
   __syncthreads();
   if (f.out_dbits) {
-    for (uint32_t i = threadIdx.x; i < n_words * (uint32_t)f.world; i += blockDim.x) {
-      const uint32_t r = i / n_words, w = i - r * n_words;
-      f.out_dbits[i] = g[(size_t)r * f.rank_stride + w];
-      if (f.out_cbits) f.out_cbits[i] = g[(size_t)r * f.rank_stride + n_words + w];
+    // same rule for the copy into the caller's rank-major bitmaps: loads first, then stores
+    const uint32_t n_out = n_words * (uint32_t)f.world;
+    for (uint32_t i0 = threadIdx.x; i0 < n_out; i0 += (uint32_t)kAssembleBatch * blockDim.x) {
+      uint32_t d[kAssembleBatch], c[kAssembleBatch];
+#pragma unroll
+      for (int k = 0; k < kAssembleBatch; ++k) {
+        const uint32_t i = i0 + (uint32_t)k * blockDim.x;
+        d[k] = c[k] = 0u;
+        if (i < n_out) {
+          const uint32_t r = i / n_words, w = i - r * n_words;
+          d[k] = g[(size_t)r * f.rank_stride + w];
+          if (f.out_cbits) c[k] = g[(size_t)r * f.rank_stride + n_words + w];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kAssembleBatch; ++k) {
+        const uint32_t i = i0 + (uint32_t)k * blockDim.x;
+        if (i < n_out) {
+          f.out_dbits[i] = d[k];
+          if (f.out_cbits) f.out_cbits[i] = c[k];
+        }
+      }
     }
   }
 }
@@ -450,6 +475,9 @@ __device__ __forceinline__ void exchange_bitmaps_ll(const FoldParams& f, uint32_
 // in griddepcontrol.wait (no polling) and run the moment the reduce grid has completed and its
 // mask updates are visible.  Grid = a handful of CTAs (32 words each); the last one to finish
 // (ticket) performs the multi-GPU exchange, publishes the counters and releases the scratch set.
+// kExchange = false is the single-GPU instantiation: the exchange (and the registers its batched loads need) is
+// compiled out, so that path is the same code as before the exchange existed.
+template <bool kExchange>
 __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   __shared__ unsigned long long s_cnt[3];
   __shared__ unsigned int s_last;
@@ -478,7 +506,7 @@ __global__ void __launch_bounds__(256) k_fold(FoldParams f) {
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x == 0 && f.stamp) f.stamp[1] = t_start, f.stamp[2] = gtime(), f.stamp[3] = f.stamp[4] = 0;
-  if (f.world > 1) {
+  if (kExchange && f.world > 1) {
     // (other CTAs wrote most of the words: read them at L2)
     const uint32_t* mine = f.peer_gather[f.rank] + (size_t)f.rank * f.rank_stride;
     if (f.my_ll) exchange_bitmaps_ll(f, n_words, mine);
