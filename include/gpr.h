@@ -238,7 +238,8 @@ GPR_API int gpr_comm_destroy(gpr_ctx *ctx);
  * in lock-step) but launches no collective: the fold kernel's CTAs store this rank's words into every peer's
  * buffer as 64-bit {step tag, word} slots the moment they exist (no fence, no flag), and its last CTA reads the
  * peers' slots until their tags match and assembles the result.  (GPR_EXCHANGE=flags selects the older protocol:
- * words, one system-scope fence, one flag per peer.)  At most 8 ranks.  A peer that never arrives does not hang the
+ * words, one system-scope fence, one flag per peer; GPR_EXCHANGE=pipelined lets a decision's exchange overlap
+ * with its predecessor's — only the write of the caller's outputs stays ordered.)  At most 8 ranks.  A peer that never arrives does not hang the
  * GPU: the wait gives up after 20 s and the next gpr_sync / blocking call returns GPR_E_STATE.                  */
 #define GPR_P2P_HANDLE_BYTES 64
 GPR_API int gpr_p2p_init(gpr_ctx *ctx, int rank, int world, uint32_t max_pods_per_rank,
