@@ -126,3 +126,28 @@ def test_fuzz_timelines(driver, tmp_path):
         TK.write_ticks(str(d), lambda k: store, times, N, step, with_power=True,
                        skip_delta={rng.randrange(1, len(times))} if rng.random() < 0.3 else ())
         _run(driver, d, duration_min)
+
+
+def test_many_series_worker_pool_under_thread_sanitizer(tmp_path):
+    """More series than the worker pool's threshold (256): the label maps of a tick are parsed on several threads
+    (ingest_device.cpp Workers / plan_text).  Same invariant as everywhere in this file — the ring equals a fresh
+    full-range ingest at every tick — with the emulator built under ThreadSanitizer."""
+    exe = tmp_path / "text_emul_tsan"
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-fno-omit-frame-pointer",
+                           "-I", HOST, os.path.join(ROOT, "tests", "cpp", "text_emul.cpp"),
+                           os.path.join(HOST, "ingest.cpp"), os.path.join(HOST, "ingest_device.cpp"),
+                           os.path.join(HOST, "json.cpp"), "-o", str(exe), "-lpthread"])
+    rng = random.Random(77)
+    N, step, interval = 60, 5, 15
+    t0 = 1_700_000_000
+    times = [t0 + N + k * interval for k in range(4)]
+    horizon = times[-1] + 5
+    store = [_series(rng, f"pod-{p}", g, t0, horizon, step, rng.choice(["idle", "busy"])) for p in range(150) for g in range(4)]
+    store.append(_series(rng, "joiner", 0, times[1] + 1, horizon, step, "idle"))
+    root = tmp_path / "ticks"
+    TK.write_ticks(str(root), lambda k: store, times, N, step)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1", GPR_LABEL_THREADS="6")
+    r = subprocess.run([str(exe), "--ticks", "1", str(root)], capture_output=True, text=True, timeout=900, env=env)
+    lines = r.stdout.splitlines()
+    assert r.returncode == 0 and len(lines) == 4 and all(l.startswith("OK ") for l in lines), (r.stdout[-2000:], r.stderr[-3000:])
+    assert "ThreadSanitizer" not in r.stderr
