@@ -357,6 +357,10 @@ Window DeviceIngestSession::ingest(const std::string& util, const std::string* p
       st.valid = false;
       throw NeedFullWindow(why);
     }
+    // From here on the session's rows and the ring are being changed: whatever interrupts this tick (a device error
+    // in the parse, a malformed slice) must not leave a ring that claims to hold the window ending at this tick —
+    // a slice that never arrived reads as "no samples", and a busy GPU would look idle.  result() sets it again.
+    st.valid = false;
   } else {
     st.w = Window();
     st.asg.reset(new Assigner(st.w));

@@ -57,7 +57,13 @@ class EmulDevice : public TextDevice {
     return end < n;
   }
 
+  // fault injection for the tick tests: the first parse of tick `fail_at_tick` dies like a CUDA error would
+  int fail_at_tick = -1, current_tick = 0;
   void parse(int slot, std::vector<gpr_text_span>& spans, const TextGrid& grid, int plane) override {
+    if (current_tick == fail_at_tick) {
+      fail_at_tick = -1;
+      throw std::runtime_error("injected device failure");
+    }
     std::vector<uint32_t>& pl = grid.resident ? ring_[plane] : plane_[plane];
     const uint32_t T = grid.T;
     if (grid.resident) {
@@ -194,9 +200,11 @@ bool rows_equal(const std::vector<float>& a, const float* b) {
 
 int run_ticks(int64_t duration_min, const std::string& dir) {
   EmulDevice dev;
+  if (const char* f = getenv("EMUL_FAIL_PARSE_TICK")) dev.fail_at_tick = atoi(f);
   DeviceIngestSession session(dev);
   int bad = 0;
   for (int k = 0;; ++k) {
+    dev.current_tick = k;
     char name[32];
     snprintf(name, sizeof name, "/tick-%04d", k);
     const std::string base = dir + name;
@@ -226,6 +234,10 @@ int run_ticks(int64_t duration_min, const std::string& dir) {
             mode = "delta", done = true;
           } catch (const NeedFullWindow& e) {
             why = e.what();
+          } catch (const std::runtime_error& e) {
+            // the tick fails (the controller logs "Failed to run query!" and waits for the next one)
+            printf("OK tick=%d mode=failed %s\n", k, e.what());
+            continue;
           }
         } else {
           why = "delta does not continue the resident window";

@@ -151,3 +151,24 @@ def test_many_series_worker_pool_under_thread_sanitizer(tmp_path):
     lines = r.stdout.splitlines()
     assert r.returncode == 0 and len(lines) == 4 and all(l.startswith("OK ") for l in lines), (r.stdout[-2000:], r.stderr[-3000:])
     assert "ThreadSanitizer" not in r.stderr
+
+
+def test_failed_tick_invalidates_the_resident_window(driver, tmp_path):
+    """A tick whose slice dies half-way (device error in the parse) has already advanced the ring; the next tick must
+    not append to it — the slice that never arrived would read as "no samples" and a busy GPU as idle.  The session
+    forgets the ring and the next tick rebuilds it from the full range."""
+    rng = random.Random(21)
+    N, step, interval = 60, 1, 15
+    t0 = 1_700_000_000
+    times = [t0 + N + k * interval for k in range(6)]
+    horizon = times[-1] + 5
+    # busy only inside the slice of tick 2: lose that slice and these pods look idle
+    store = [(m, l, [(t, (50 if times[1] < t <= times[2] else 0)) for t, _ in smp])
+             for m, l, smp in (_series(rng, f"pod-{p}", g, t0, horizon, step, "idle") for p in range(5) for g in range(2))]
+    TK.write_ticks(str(tmp_path), lambda k: store, times, N, step)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", EMUL_FAIL_PARSE_TICK="2")
+    r = subprocess.run([driver, "--ticks", "1", str(tmp_path)], capture_output=True, text=True, timeout=600, env=env)
+    lines = r.stdout.splitlines()
+    assert r.returncode == 0 and all(l.startswith("OK ") for l in lines), (r.stdout[-3000:], r.stderr[-2000:])
+    modes = [l.split()[2].split("=", 1)[1] for l in lines]
+    assert modes == ["full", "delta", "failed", "full", "delta", "delta"], lines
