@@ -200,7 +200,7 @@ struct gpr_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   // fused exchange over peer memory (gpr_p2p_init / gpr_p2p_attach)
-  unsigned char* p2p_block = nullptr;            // [flags u64 x kMaxPeers | pad | gather[2][world][stride]]
+  unsigned char* p2p_block = nullptr;            // [flags u64 x kMaxPeers | rendezvous flags | gather[4][world][stride] | slots[4][world][stride]]
   unsigned char* p2p_peer[gpr::kMaxPeers] = {};  // peer-mapped base of every rank's block (self = local)
   // Exchange buffers are kExchangeDepth deep (step % depth), twice the number of scratch sets: with the late
   // output ordering a rank may push step n + 4 only after every peer has consumed step n (see k_fold)
