@@ -62,6 +62,30 @@ def test_struct_layout_matches_a_c_compiler(tmp_path):
     assert got == want
 
 
+def test_every_struct_field_matches_the_ctypes_mirror(tmp_path):
+    """all six structs of include/gpr.h: sizeof and the offset of every field, gcc vs gpu_pruner_b200/ffi.py"""
+    import abi_parse
+    from gpu_pruner_b200 import ffi
+    structs = abi_parse.structs()
+    assert set(structs) == {"gpr_config", "gpr_window", "gpr_result", "gpr_device_info", "gpr_text_span", "gpr_text_grid"}
+    lines = []
+    for name, fields in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for _, _, f, _ in fields:
+            lines.append(f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    prog = tmp_path / "fields.c"
+    prog.write_text("#include <stdio.h>\n#include <stddef.h>\n#include \"gpr.h\"\nint main(void) {\n" + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "fields"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for name, fields in structs.items():
+        mirror = getattr(ffi, name)
+        assert int(got[name]) == C.sizeof(mirror), name
+        assert [f for _, _, f, _ in fields] == [f[0] for f in mirror._fields_], name
+        for _, _, f, _ in fields:
+            assert int(got[f"{name}.{f}"]) == getattr(mirror, f).offset, (name, f)
+
+
 def test_header_is_plain_c():
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER])
 
