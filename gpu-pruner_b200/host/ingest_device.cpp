@@ -137,6 +137,33 @@ Workers& label_workers() {
   return w;
 }
 
+// [[ts,"v"],[ts,"v"],...] exactly as Prometheus prints it: digits with an optional fraction, a quoted value without
+// quotes or escapes inside, no white space.  (Anything else is for the CPU parser to judge.)
+bool samples_are_compact(const char* p, const char* e) {
+  if (p >= e || *p++ != '[') return false;
+  if (p < e && *p == ']') return p + 1 == e;
+  while (true) {
+    if (p >= e || *p++ != '[') return false;
+    const char* d = p;
+    while (p < e && *p >= '0' && *p <= '9') ++p;
+    if (p == d) return false;
+    if (p < e && *p == '.') {
+      d = ++p;
+      while (p < e && *p >= '0' && *p <= '9') ++p;
+      if (p == d) return false;
+    }
+    if (e - p < 2 || p[0] != ',' || p[1] != '"') return false;
+    p += 2;
+    d = p;
+    while (p < e && *p != '"' && *p != '\\' && (unsigned char)*p >= 0x20) ++p;
+    if (p == d || e - p < 2 || p[0] != '"' || p[1] != ']') return false;
+    p += 2;
+    if (p >= e) return false;
+    if (*p == ']') return p + 1 == e;
+    if (*p++ != ',') return false;
+  }
+}
+
 // Walk the series of one response with the device's marker lists, as they arrive: the upload + scan runs as a
 // pipeline (TextDevice::scan_begin / scan_next).  Every batch of series whose markers are in goes through three steps
 // while later chunks of the text are still on their way to the GPU:
@@ -269,6 +296,13 @@ void plan_text(TextDevice& dev, TextPlan& plan, Assigner& asg, Window& w, bool i
       }
       if (r.r == Assigner::Placed)
         plan.series.push_back(DevSeries{r.pod, r.slot, (uint64_t)l.close_brace + 12, (uint64_t)l.list_close});
+      // A series that gets no row (no workload-pod label, lib.rs:161-175) is never seen by the device parser, so its
+      // samples are checked here: a response that is malformed there is malformed, and the CPU parser — which reads
+      // every sample — has to be the one to say so.  Such series are rare by construction (the selector asks for a
+      // non-empty pod label).  Series shadowed by a PROF series of the same label set are NOT walked: there can be as
+      // many of them as there are series, and nothing in them can reach the verdict.
+      else if (r.r == Assigner::Skipped && !samples_are_compact(t.data() + l.close_brace + 11, t.data() + l.list_close + 1))
+        throw NotCompact{"values list of a skipped series is not in the compact encoding"};
     }
     rep.assign_ms += ms_since(ta);
   };

@@ -235,3 +235,29 @@ def test_mutated_responses_agree_or_are_rejected(driver, tmp_path):
     assert rc == 0, [l for l in lines if l.startswith("MISMATCH")][:5]
     verdicts = [l.split()[0] for l in lines]
     assert verdicts.count("OK") >= 30 and verdicts.count("REJECT") >= 30
+
+
+def test_samples_of_series_without_a_row_are_still_checked(driver, tmp_path):
+    """A series that gets no tensor row (no workload-pod label) never reaches the device parser; garbage inside its
+    values list must not slip through — the CPU parser reads every sample and rejects such a response.  (Found by an
+    extended run of the mutation fuzz: one mutation hit a label key, a second one a sample of the same series.)"""
+    ok_series = {"metric": dict(_labels(1, 0), __name__="DCGM_FI_DEV_GPU_UTIL"), "values": [[T_END - 1, "0"], [T_END, "7"]]}
+    orphan = {"metric": {"Hostname": "node-9", "gpu": "0", "modelName": "NVIDIA B200", "__name__": "DCGM_FI_DEV_GPU_UTIL"},
+              "values": [[T_END - 2, "0.5"], [T_END - 1, "NaN"], [T_END, "1e2"]]}
+    good = _resp([ok_series, orphan])
+    cases = {"fine": good,
+             "quote": good.replace('"NaN"]', '"NaN]]'),
+             "bracket": good.replace(f'[{T_END - 2},"0.5"]', f'{T_END - 2},"0.5"]'),
+             "junk": good.replace('"1e2"]]', '"1e2"]x]')}
+    dirs = []
+    for name, text in cases.items():
+        d = tmp_path / name
+        d.mkdir()
+        (d / "util.json").write_text(text)
+        dirs.append(d)
+    rc, lines = _run(driver, dirs)
+    assert rc == 0, lines
+    assert lines[0].startswith("OK") and " device=1 " in lines[0], lines[0]
+    # the device path never accepts them: the CPU parser is the judge (it rejects two and is lenient about one)
+    assert all(" device=1 " not in l for l in lines[1:]), lines
+    assert sum(l.startswith("REJECT") for l in lines[1:]) >= 2, lines
