@@ -1,5 +1,5 @@
 """Long differential run of the device text parser's number conversion (gpr_text.cuh compiled for the host by
-tests/cpp/number_check.cpp) against Python's correctly rounded float():  numbers.py SEED N_CASES
+tests/cpp/number_check.cpp) against Python's correctly rounded float():  number_conversion.py SEED N_CASES
 Build first:  g++ -O2 -std=c++17 tests/cpp/number_check.cpp -o /tmp/numf/number_check"""
 import os
 import random, struct, subprocess, sys, numpy as np
