@@ -179,7 +179,10 @@ class GprVerdictEngine : public VerdictEngine, public TextIngestor, private Text
     opens->resize(cap), closes->resize(cap);
     uint64_t no = 0, nc = 0;
     int32_t more = 0;
-    check(gpr_text_scan_next(ctx_, opens->data(), closes->data(), cap, &no, &nc, bytes_done, &more), "gpr_text_scan_next");
+    const int rc = gpr_text_scan_next(ctx_, opens->data(), closes->data(), cap, &no, &nc, bytes_done, &more);
+    // more series markers in one chunk than the scan holds: not an error of the response — the CPU parser takes it
+    if (rc == GPR_E_CAPACITY) throw DeviceDeclined(std::string("device scan: ") + gpr_last_error(ctx_));
+    check(rc, "gpr_text_scan_next");
     opens->resize(no), closes->resize(nc);
     return more != 0;
   }

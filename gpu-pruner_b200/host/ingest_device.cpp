@@ -422,6 +422,8 @@ Window DeviceIngestSession::ingest(const std::string& util, const std::string* p
     if (pl_power) plan_text(dev_, *pl_power, asg, w, true, false, rep, remember);
   } catch (const NotCompact& e) {
     return cpu(e.why);
+  } catch (const DeviceDeclined& e) {
+    return cpu(e.what());
   }
   std::vector<std::pair<uint32_t, uint32_t>> prof_rows;
   if (pl_prof)

@@ -6,6 +6,7 @@
 // cell for cell (tests/test_text_device_cpu.py on an emulated device, tests/test_gpu_text.py on the GPU).
 #pragma once
 #include <cstdint>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,13 @@
 namespace gph {
 
 // What the orchestration needs from the device; implemented over libgpr.so in gpr_engine.cpp.
+// Thrown by a TextDevice that cannot take a response although nothing is wrong with the response (more series
+// markers in one upload chunk than the scan has room for — label sets a tenth of DCGM's size): the session hands the
+// response to the CPU parser instead of failing the tick.
+struct DeviceDeclined : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
 class TextDevice {
  public:
   virtual ~TextDevice() = default;

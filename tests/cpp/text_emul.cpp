@@ -38,6 +38,7 @@ class EmulDevice : public TextDevice {
     scan_slot_ = slot, scan_pos_ = 0;
   }
   bool scan_next(std::vector<uint64_t>* opens, std::vector<uint64_t>* closes, uint64_t* bytes_done) override {
+    if (getenv("EMUL_DECLINE_SCAN") && scan_pos_ > 0) throw DeviceDeclined("emulated: too many markers in one chunk");
     opens->clear(), closes->clear();
     const std::vector<uint8_t>& t = text_[scan_slot_];
     const uint64_t n = n_[scan_slot_];

@@ -261,3 +261,17 @@ def test_samples_of_series_without_a_row_are_still_checked(driver, tmp_path):
     # the device path never accepts them: the CPU parser is the judge (it rejects two and is lenient about one)
     assert all(" device=1 " not in l for l in lines[1:]), lines
     assert sum(l.startswith("REJECT") for l in lines[1:]) >= 2, lines
+
+
+def test_a_device_that_declines_hands_the_response_to_the_cpu_parser(driver, tmp_path):
+    """The scan has room for a fixed number of series markers per upload chunk; a response that exceeds it (label sets
+    a tenth of DCGM's size) is not malformed, so the tick must not fail: the device declines, the CPU parser produces
+    the window.  The emulated device declines in the middle of the upload pipeline here."""
+    rng = random.Random(3)
+    dirs = [_case(rng, tmp_path, f"d{i}", n_pods=4, T=60, prof=i == 1, power=i == 2) for i in range(3)]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", EMUL_DECLINE_SCAN="1")
+    r = subprocess.run([driver, str(T_END), "1", "1"] + [str(d) for d in dirs], capture_output=True, text=True,
+                       timeout=600, env=env)
+    lines = r.stdout.splitlines()
+    assert r.returncode == 0 and len(lines) == 3, (r.stdout, r.stderr[-2000:])
+    assert all(l.startswith("OK") and " device=0 " in l and "too many markers" in l for l in lines), lines
