@@ -131,7 +131,7 @@ constexpr int kDepth = 4;   // exchange buffer sets (gpr_api.cu kExchangeDepth)
 struct Rank {
   int rank = 0;
   uint32_t P = 0, W = 0, stride = 0;
-  std::vector<uint32_t> masks[2];                 // [idle P]
+  std::vector<uint32_t> masks[2];                 // [idle P | veto P]
   std::vector<uint8_t> eligible;
   unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};
   unsigned int tickets[2] = {0, 0};
@@ -151,8 +151,15 @@ struct Scenario {
   int protocol;       // 0 tagged slots in order, 1 tagged slots pipelined, 2 flags
   int shared_output;  // 1: every decision writes the same output buffer (the last one must stay)
   int slow_rank;      // >= 0: that rank's loads of peer-written slots are slow, so its collector lags steps behind
+  int with_veto;      // 1: a power plane vetoes pods and the caller asks for veto_bits (decide_impl then keeps the
+                      //    early wait even under the pipelined protocol: veto words go straight to the caller)
 };
 
+static uint32_t veto_bits_of(uint64_t seed, int rank, int step, uint32_t pod) {
+  uint64_t x = (seed * 0x9e3779b97f4a7c15ull) ^ ((uint64_t)rank << 40) ^ ((uint64_t)step << 24) ^ ((uint64_t)pod * 0x100000001b3ull);
+  x ^= x >> 29, x *= 0xbf58476d1ce4e5b9ull, x ^= x >> 32;
+  return (x % 10u) == 0 ? 1u + (uint32_t)(x >> 40) % 15u : 0u;   // every tenth pod has a GPU drawing power
+}
 static uint32_t idle_bits(uint64_t seed, int rank, int step, uint32_t pod) {
   uint64_t x = seed ^ ((uint64_t)rank << 48) ^ ((uint64_t)step << 32) ^ pod;
   x ^= x >> 33, x *= 0xff51afd7ed558ccdull, x ^= x >> 33, x *= 0xc4ceb9fe1a85ec53ull, x ^= x >> 33;
@@ -167,7 +174,7 @@ static int run(const Scenario& sc, uint64_t seed) {
   for (int r = 0; r < world; ++r) {
     auto R = std::make_unique<Rank>();
     R->rank = r, R->P = P, R->W = W, R->stride = stride;
-    for (auto& m : R->masks) m.assign(P, 0u);
+    for (auto& m : R->masks) m.assign(2 * (size_t)P, 0u);
     R->eligible.resize(P);
     for (auto& e : R->eligible) e = (rng() % 10) != 0;
     R->flags.assign(world, 0ull);
@@ -180,10 +187,12 @@ static int run(const Scenario& sc, uint64_t seed) {
   const int n_out = sc.shared_output ? 1 : K + 1;
   std::vector<std::vector<uint32_t>> out_d(world), out_c(world);
   std::vector<std::vector<unsigned long long>> counts(world), stamps(world);
+  std::vector<std::vector<uint32_t>> out_v(world);   // veto words: this rank's pods only, one buffer per decision
   std::vector<std::vector<std::atomic<int>>> reduce_complete(world);
   for (int r = 0; r < world; ++r) {
     out_d[r].assign((size_t)n_out * world * W, 0xdeadbeefu);
     out_c[r].assign((size_t)n_out * world * W, 0xdeadbeefu);
+    out_v[r].assign((size_t)(K + 1) * W, 0xdeadbeefu);
     counts[r].assign((size_t)(K + 1) * 3, ~0ull);
     stamps[r].assign((size_t)(K + 1) * 5, 0ull);
     reduce_complete[r] = std::vector<std::atomic<int>>(K + 1);
@@ -202,6 +211,7 @@ static int run(const Scenario& sc, uint64_t seed) {
       memset(&fp, 0, sizeof fp);
       fp.idle_mask = me.masks[sset].data();
       fp.eligible = me.eligible.data();
+      if (sc.with_veto) fp.veto_mask = me.masks[sset].data() + P, fp.vbits = out_v[r].data() + (size_t)n * W;
       fp.dbits = me.gather[xset].data() + (size_t)r * stride;
       fp.cbits = fp.dbits + W;
       fp.counts = &counts[r][(size_t)n * 3];
@@ -220,7 +230,7 @@ static int run(const Scenario& sc, uint64_t seed) {
       }
       fp.my_flags = me.flags.data();
       fp.my_ll = sc.protocol == 2 ? nullptr : me.ll[xset].data();
-      fp.late_order = sc.protocol == 1;
+      fp.late_order = sc.protocol == 1 && fp.vbits == nullptr;
       fp.step = (unsigned long long)n;
       const size_t o = sc.shared_output ? 0 : (size_t)n * world * W;
       fp.out_dbits = out_d[r].data() + o, fp.out_cbits = out_c[r].data() + o;
@@ -231,6 +241,8 @@ static int run(const Scenario& sc, uint64_t seed) {
       for (uint32_t pod = 0; pod < P; ++pod) {
         const uint32_t b = idle_bits(seed, r, n, pod);
         if (b) __atomic_fetch_or(&me.masks[sset][pod], b, __ATOMIC_RELAXED);
+        const uint32_t v = sc.with_veto ? veto_bits_of(seed, r, n, pod) : 0u;
+        if (v) __atomic_fetch_or(&me.masks[sset][P + pod], v, __ATOMIC_RELAXED);
       }
       // ---- fold n: resident already, runs once the reduce has completed; nothing orders it behind fold n - 1
       for (uint32_t c = 0; c < grid; ++c) {
@@ -264,7 +276,10 @@ static int run(const Scenario& sc, uint64_t seed) {
     for (int q = 0; q < world; ++q)
       for (uint32_t pod = 0; pod < P; ++pod) {
         const uint32_t b = idle_bits(seed, q, n, pod);
-        const bool cand = b != 0, dec = cand && ranks[q]->eligible[pod];
+        const bool veto = sc.with_veto && veto_bits_of(seed, q, n, pod) != 0;
+        if (veto && (out_v[q][(size_t)n * W + pod / 32] >> (pod & 31) & 1u) == 0) bad++;
+        if (!veto && sc.with_veto && (out_v[q][(size_t)n * W + pod / 32] >> (pod & 31) & 1u) != 0) bad++;
+        const bool cand = b != 0 && !veto, dec = cand && ranks[q]->eligible[pod];
         if (cand) want_c[(size_t)q * W + pod / 32] |= 1u << (pod & 31), cnt[q * 3 + 0] += __builtin_popcount(b), cnt[q * 3 + 1]++;
         if (dec) want_d[(size_t)q * W + pod / 32] |= 1u << (pod & 31), cnt[q * 3 + 2]++;
       }
@@ -284,7 +299,7 @@ static int run(const Scenario& sc, uint64_t seed) {
     if (me.err) bad++;
     for (int s = 0; s < 2; ++s) {
       if (me.done[s] != me.uses[s] || me.tickets[s] != 0) bad++;
-      for (uint32_t m : me.masks[s]) if (m) { bad++; break; }
+      for (uint32_t m : me.masks[s]) if (m) { bad++; break; }   // idle and veto planes
     }
     for (unsigned long long a : me.acc) if (a) bad++;
     // completion stamps are in launch order: outputs of decision n are written after those of decision n - 1
@@ -296,13 +311,15 @@ static int run(const Scenario& sc, uint64_t seed) {
 
 int main(int argc, char** argv) {
   const Scenario all[] = {
-      {3, 12, 64, 10, 0, 0, -1}, {3, 12, 64, 10, 1, 0, -1}, {3, 12, 64, 10, 2, 0, -1},   // the three protocols
-      {3, 12, 64, 11, 0, 1, -1}, {3, 12, 64, 11, 1, 1, -1},   // shared output buffer: the last decision stays
-      {2, 40, 128, 8, 1, 0, -1}, {8, 4, 64, 8, 0, 0, -1},  {8, 4, 64, 9, 1, 1, -1},      // 2 and 8 ranks
-      {4, 9, 32, 8, 1, 0, -1},   {1, 20, 64, 6, 0, 0, -1},    // odd word count; a single GPU (no exchange)
+      {3, 12, 64, 10, 0, 0, -1, 0}, {3, 12, 64, 10, 1, 0, -1, 0}, {3, 12, 64, 10, 2, 0, -1, 0},   // the three protocols
+      {3, 12, 64, 11, 0, 1, -1, 0}, {3, 12, 64, 11, 1, 1, -1, 0},   // shared output buffer: the last decision stays
+      {2, 40, 128, 8, 1, 0, -1, 0}, {8, 4, 64, 8, 0, 0, -1, 0},  {8, 4, 64, 9, 1, 1, -1, 0},      // 2 and 8 ranks
+      {4, 9, 32, 8, 1, 0, -1, 0},   {1, 20, 64, 6, 0, 0, -1, 0},    // odd word count; a single GPU (no exchange)
       // one rank's collector lags: the others run ahead as far as the scratch sets let them and overwrite its
       // slots — which is only safe because the exchange buffers are four deep (with two, this case times out)
-      {3, 6, 64, 14, 1, 0, 1},   {3, 6, 64, 14, 0, 0, 2},
+      {3, 6, 64, 14, 1, 0, 1, 0},   {3, 6, 64, 14, 0, 0, 2, 0},
+      // power veto + veto_bits requested: both tagged-slot protocols and one GPU
+      {3, 12, 64, 9, 1, 1, -1, 1},  {3, 12, 64, 9, 0, 0, -1, 1}, {1, 20, 64, 6, 0, 0, -1, 1},
   };
   const int only = argc > 1 ? atoi(argv[1]) : -1;
   int bad = 0, i = 0;
@@ -311,6 +328,7 @@ int main(int argc, char** argv) {
     const int b = run(sc, 0x5EED0000ull + 17u * (unsigned)sc.world + (unsigned)sc.protocol);
     printf("world %d words %u threads %u steps %d protocol %d shared %d slow rank %d: %s\n", sc.world, sc.words_per_rank,
            sc.fold_threads, sc.steps, sc.protocol, sc.shared_output, sc.slow_rank, b ? "FAIL" : "ok");
+    if (sc.with_veto) printf("  (with power veto)\n");
     fflush(stdout);
     bad += b;
   }
