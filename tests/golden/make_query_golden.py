@@ -25,6 +25,15 @@ def main():
         args = {"duration": duration, "namespace": ns, "model_name": model,
                 "power_threshold": power, "honor_labels": honor}
         cases.append({"args": args, "text": tpl.render(args=args)})
+    # a second, sparse grid: strings are inserted into the PromQL verbatim (no escaping in the template), regex
+    # alternations and dots included; a few more float spellings of the threshold; extreme look-backs
+    odd_ns = ("ml-team|prod", "team.with.dots", "ns-[0-9]+", 'we"ird', "x" * 70)
+    odd_model = ("NVIDIA A100-SXM4-80GB", ".*H100.*", "Tesla V100|Tesla T4", "A\\d+")
+    odd_power = (99.9, 0.5, 250.25, 1000.0, 1.0)
+    for i, (ns, model) in enumerate(itertools.product(odd_ns, odd_model)):
+        args = {"duration": (1, 5, 60, 1440)[i % 4], "namespace": ns, "model_name": model if i % 3 else None,
+                "power_threshold": odd_power[i % len(odd_power)] if i % 2 else None, "honor_labels": bool(i % 5 == 0)}
+        cases.append({"args": args, "text": tpl.render(args=args)})
     json.dump(cases, open(OUT, "w"), indent=1)
     print(f"wrote {len(cases)} renderings to {OUT}")
     print(cases[0]["text"])
