@@ -1,0 +1,297 @@
+// Host emulation of the whole decision path: the three reduce kernels (k_reduce_ldg, k_reduce_tma, k_reduce_u8) and
+// the fold kernel, compiled from the SOURCE TEXT of gpu-pruner_b200/csrc/gpr_kernels.cuh.
+//
+// tests/test_hotpath_emul.py cuts the body of `namespace gpr` out of the kernel header, removes the small helper
+// functions that are nothing but inline PTX (loads with cache hints, mbarrier / bulk-copy instructions, scoped
+// atomics, %globaltimer) and rewrites the three inline-PTX statements and the __shared__ declarations inside the
+// kernels to shim calls -> hotpath_extract.inc.  This file supplies those helpers and the CUDA built-ins on top of
+// std::thread: a CTA is a group of threads with a barrier, a warp 32 of them with emulated shuffles / ballots /
+// reductions, a bulk copy is a memcpy that completes an emulated mbarrier phase.
+//
+// For every case directory given on the command line (files written by the test: util.f32, [power.f32], [elig.u8],
+// [created.i64], [util.u8], params.txt) it runs each applicable reduce variant + the fold, twice on the same
+// scratch set, and prints one line per variant:   <dir> <variant> <dbits hex> <cbits hex> <vbits hex> <n_series>
+// <n_cand> <n_dec> <smax hex...>.  The test compares them with the hand-derived known answers and with the oracle.
+// It validates the SOURCE logic of the kernels (row tails, NaN rules, ANY-GPU fold, veto, gates, counters, scratch
+// reuse) — not the generated machine code; tests/test_gpu_parity.py does that on a B200.
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+using std::max;
+using std::min;
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(x)
+#define __restrict__
+#define __align__(x)
+
+struct float4 { float x, y, z, w; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
+
+struct Dim3 { unsigned x; };
+struct WarpCtx {
+  std::barrier<> bar{32};
+  uint32_t slot[32];
+};
+struct CtaCtx {
+  CtaCtx(unsigned threads, size_t smem_bytes) : bar((std::ptrdiff_t)threads), warps(threads / 32), smem_store(smem_bytes + 256) {
+    smem = smem_store.data();
+    smem += (128 - reinterpret_cast<uintptr_t>(smem) % 128) % 128;
+  }
+  std::barrier<> bar;
+  std::vector<WarpCtx> warps;
+  std::vector<unsigned char> smem_store;
+  unsigned char* smem = nullptr;
+  unsigned long long s_cnt[3] = {0, 0, 0};
+  unsigned int s_last = 0, s_next = 0;
+};
+static thread_local Dim3 threadIdx, blockIdx, blockDim, gridDim;
+static thread_local CtaCtx* tl_cta = nullptr;
+
+static inline WarpCtx& warp_ctx() { return tl_cta->warps[threadIdx.x >> 5]; }
+static inline uint32_t xchg(uint32_t mine, int from_lane) {   // every lane publishes, then reads one lane's word
+  WarpCtx& w = warp_ctx();
+  w.slot[threadIdx.x & 31] = mine;
+  w.bar.arrive_and_wait();
+  const uint32_t r = w.slot[from_lane & 31];
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline void __syncthreads() { tl_cta->bar.arrive_and_wait(); }
+static inline void __syncwarp() { warp_ctx().bar.arrive_and_wait(); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline float __int_as_float(int x) { return u2f((uint32_t)x); }
+static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int o) { return xchg(v, (threadIdx.x & 31) ^ o); }
+static inline float __shfl_xor_sync(unsigned, float v, int o) { return u2f(xchg(f2u(v), (threadIdx.x & 31) ^ o)); }
+static inline uint32_t __shfl_sync(unsigned, uint32_t v, int lane) { return xchg(v, lane); }
+static inline uint32_t __ballot_sync(unsigned, bool pred) {
+  WarpCtx& w = warp_ctx();
+  w.slot[threadIdx.x & 31] = pred ? 1u : 0u;
+  w.bar.arrive_and_wait();
+  uint32_t r = 0;
+  for (int l = 0; l < 32; ++l) r |= w.slot[l] << l;
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline uint32_t __reduce_or_sync(unsigned, uint32_t v) {
+  WarpCtx& w = warp_ctx();
+  w.slot[threadIdx.x & 31] = v;
+  w.bar.arrive_and_wait();
+  uint32_t r = 0;
+  for (int l = 0; l < 32; ++l) r |= w.slot[l];
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline uint32_t __reduce_max_sync(unsigned, uint32_t v) {
+  WarpCtx& w = warp_ctx();
+  w.slot[threadIdx.x & 31] = v;
+  w.bar.arrive_and_wait();
+  uint32_t r = 0;
+  for (int l = 0; l < 32; ++l) r = std::max(r, w.slot[l]);
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline uint32_t __vmaxu4(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+  for (int k = 0; k < 4; ++k) r |= std::max((a >> (8 * k)) & 0xffu, (b >> (8 * k)) & 0xffu) << (8 * k);
+  return r;
+}
+template <class T> static inline T __ldcg(const T* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned int atomicOr(unsigned int* p, unsigned int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+
+// ---- the helpers that are inline PTX in the header -------------------------------------------------------------
+static inline unsigned long long gtime() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static inline void pdl_launch_dependents() {}
+static inline void pdl_wait_prior_grids() {}   // the driver joins the reduce grid before it starts the fold grid
+static inline void spin_until_gpu(const unsigned long long* p, unsigned long long want) {
+  while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < want) std::this_thread::yield();
+}
+static inline void spin_until_sys(const unsigned long long* p, unsigned long long want, unsigned int*, unsigned) {
+  spin_until_gpu(p, want);
+}
+static inline void st_release_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline void st_release_sys_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline float4 ldg_stream(const float4* p) { return *p; }
+static inline uint4 ldg_stream_u4(const uint4* p) { return *p; }
+// an mbarrier is emulated by the number of completed phases; a bulk copy completes its phase when the bytes are there
+static inline void mbar_init(uint64_t* bar, uint32_t) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_RELEASE); }
+static inline void mbar_expect_tx(uint64_t*, uint32_t) {}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
+}
+static inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
+  if (bytes % 16u != 0 || reinterpret_cast<uintptr_t>(src) % 16u != 0 || reinterpret_cast<uintptr_t>(dst) % 16u != 0) {
+    fprintf(stderr, "bulk copy with unaligned address or size (%u bytes)\n", bytes);   // what the hardware rejects
+    abort();
+  }
+  memcpy(dst, src, bytes);
+  __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_RELEASE);
+}
+static inline uint64_t l2_evict_first_policy() { return 0; }
+
+namespace gpr {
+#include "hotpath_extract.inc"
+}
+
+// ---- driver --------------------------------------------------------------------------------------------------------
+template <class T>
+static bool slurp(const std::string& path, std::vector<T>* out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  f.seekg(0, std::ios::end);
+  const size_t n = (size_t)f.tellg();
+  f.seekg(0);
+  out->resize(n / sizeof(T));
+  f.read(reinterpret_cast<char*>(out->data()), (std::streamsize)(out->size() * sizeof(T)));
+  return true;
+}
+
+template <class Fn>
+static void launch(unsigned grid, unsigned threads, size_t smem, Fn&& kernel) {
+  std::vector<std::unique_ptr<CtaCtx>> ctas;
+  std::vector<std::thread> th;
+  for (unsigned c = 0; c < grid; ++c) ctas.push_back(std::make_unique<CtaCtx>(threads, smem));
+  for (unsigned c = 0; c < grid; ++c)
+    for (unsigned t = 0; t < threads; ++t)
+      th.emplace_back([&, c, t] {
+        threadIdx.x = t, blockIdx.x = c, blockDim.x = threads, gridDim.x = grid;
+        tl_cta = ctas[c].get();
+        kernel();
+      });
+  for (auto& t : th) t.join();
+}
+
+struct Case {
+  uint32_t P = 0, G = 0, T = 0;
+  uint64_t ld = 0;
+  int use_power = 0;
+  uint32_t thr_bits = 0;
+  int64_t cutoff = 0;
+  std::vector<float> util, power;
+  std::vector<uint8_t> elig, util_u8;
+  std::vector<int64_t> created;
+};
+
+static void print_words(const std::vector<uint32_t>& w) {
+  for (uint32_t x : w) printf("%08x", x);
+  if (w.empty()) printf("-");
+}
+
+static void run_variant(const std::string& dir, const char* name, const Case& c, int variant, size_t shift_floats) {
+  const uint32_t P = c.P, G = c.G, T = c.T, S = P * G, MW = (G + 31) / 32, W = (P + 31) / 32;
+  // the planes, 16-byte aligned plus an optional shift (the vectorised kernels peel to alignment themselves)
+  std::vector<float> ubuf((size_t)S * c.ld + 16 + shift_floats), pbuf(c.use_power ? (size_t)S * c.ld + 16 + shift_floats : 0);
+  auto aligned = [&](std::vector<float>& b) {
+    float* p = b.data();
+    while (reinterpret_cast<uintptr_t>(p) % 16u) ++p;
+    return p + shift_floats;
+  };
+  float* util = aligned(ubuf);
+  memcpy(util, c.util.data(), c.util.size() * 4);
+  float* power = nullptr;
+  if (c.use_power) power = aligned(pbuf), memcpy(power, c.power.data(), c.power.size() * 4);
+  std::vector<uint32_t> masks((size_t)2 * P * MW + 16, 0u);
+  unsigned long long acc[3] = {0, 0, 0}, done = 0, other_done = 0;
+  unsigned int ticket = 0, err = 0;
+  for (int rep = 0; rep < 2; ++rep) {   // the second decision reuses the scratch set the first one must have zeroed
+    std::vector<uint32_t> dbits(W, 0xdeadbeefu), cbits(W, 0xdeadbeefu), vbits(W, 0xdeadbeefu);
+    std::vector<float> smax(S, -12345.f);
+    unsigned long long counts[3] = {~0ull, ~0ull, ~0ull};
+    gpr::ReduceParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.seg[0] = gpr::Segment{variant == 2 ? reinterpret_cast<const float*>(c.util_u8.data()) : util, masks.data(),
+                             smax.data(), S, 0u};
+    rp.seg[1] = gpr::Segment{power, masks.data() + (size_t)P * MW, nullptr, c.use_power ? S : 0u, 1u};
+    rp.ld = c.ld, rp.T = T, rp.G = G, rp.mw = MW;
+    rp.total_rows = S + (c.use_power ? S : 0u);
+    memcpy(&rp.thr, &c.thr_bits, 4);
+    rp.done = &done, rp.need = (unsigned long long)rep;
+    rp.util_u8 = variant == 2 ? 1u : 0u;
+    const unsigned grid_r = 3;
+    if (variant == 0) {
+      launch(grid_r, 2 * 32, 0, [&] { gpr::k_reduce_ldg<2, 2>(rp); });
+    } else if (variant == 1) {
+      gpr::TmaLayout L;
+      L.chunk_elems = 64, L.stage_bytes = 256, L.depth = 2, L.n_chunks = (T + 63) / 64;   // several chunks per row
+      launch(grid_r, 4 * 32, (size_t)4 * L.depth * L.stage_bytes + 4 * L.depth * 8, [&] { gpr::k_reduce_tma<4>(rp, L); });
+    } else {
+      launch(grid_r, 2 * 32, 0, [&] { gpr::k_reduce_u8<2, 2>(rp); });
+    }
+    gpr::FoldParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.idle_mask = masks.data();
+    fp.veto_mask = c.use_power ? masks.data() + (size_t)P * MW : nullptr;
+    fp.eligible = c.elig.empty() ? nullptr : c.elig.data();
+    fp.created = c.created.empty() ? nullptr : c.created.data();
+    fp.cutoff = c.cutoff;
+    fp.dbits = dbits.data(), fp.cbits = cbits.data(), fp.vbits = vbits.data();
+    fp.counts = counts, fp.acc = acc, fp.ticket = &ticket;
+    fp.done = &done, fp.need = (unsigned long long)rep;
+    fp.prev_done = &other_done, fp.prev_need = 0;
+    fp.P = P, fp.G = G, fp.mw = MW;
+    fp.world = 1, fp.rank = 0;
+    fp.err = &err;
+    const unsigned fold_threads = 64, fold_warps = 2;
+    launch(std::max(1u, (W + 4 * fold_warps - 1) / (4 * fold_warps)), fold_threads, 0, [&] { gpr::k_fold<false>(fp); });
+    bool clean = done == (unsigned long long)rep + 1 && ticket == 0 && !acc[0] && !acc[1] && !acc[2];
+    for (uint32_t m : masks) clean = clean && m == 0;
+    printf("%s %s%s %s ", dir.c_str(), name, rep ? "#2" : "", clean ? "clean" : "DIRTY");
+    print_words(dbits), printf(" "), print_words(cbits), printf(" "), print_words(vbits);
+    printf(" %llu %llu %llu ", counts[0], counts[1], counts[2]);
+    for (float v : smax) printf("%08x", f2u(v));
+    printf("\n");
+  }
+}
+
+int main(int argc, char** argv) {
+  for (int a = 1; a < argc; ++a) {
+    const std::string dir = argv[a];
+    Case c;
+    {
+      std::ifstream f(dir + "/params.txt");
+      unsigned long long ld;
+      f >> c.P >> c.G >> c.T >> ld >> c.use_power >> c.thr_bits >> c.cutoff;
+      c.ld = ld;
+    }
+    slurp(dir + "/util.f32", &c.util);
+    if (c.use_power) slurp(dir + "/power.f32", &c.power);
+    slurp(dir + "/elig.u8", &c.elig);
+    slurp(dir + "/created.i64", &c.created);
+    const bool has_u8 = slurp(dir + "/util.u8", &c.util_u8);
+    if (c.P == 0) continue;
+    run_variant(dir, "ldg", c, 0, 0);
+    run_variant(dir, "ldg+1", c, 0, 1);   // rows start 4 bytes off 16-byte alignment
+    if (c.T % 4 == 0 && c.ld % 4 == 0) run_variant(dir, "tma", c, 1, 0);
+    if (has_u8) run_variant(dir, "u8", c, 2, 0);
+    fflush(stdout);
+  }
+  return 0;
+}
