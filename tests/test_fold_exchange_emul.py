@@ -43,3 +43,19 @@ def test_fold_and_exchange_source_under_host_shim(tmp_path):
                    check=True, capture_output=True, text=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_no_data_race_under_thread_sanitizer(tmp_path):
+    """The same source under ThreadSanitizer: with CTAs, warps and ranks on real threads and the CUDA barriers / scoped
+    atomics mapped to C++ ones, a missing __syncthreads or fence in the kernel text is a reported race (removing the two
+    barriers between collecting and assembling, for instance, is).  All protocols, 2 to 8 ranks, the lagging rank."""
+    (tmp_path / "fold_extract.inc").write_text(_extract())
+    exe = tmp_path / "fold_emul_tsan"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-Wno-unknown-pragmas",
+                    "-I", str(tmp_path), os.path.join(ROOT, "tests", "cpp", "fold_emul.cpp"), "-o", str(exe)],
+                   check=True, capture_output=True, text=True)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1")
+    for scenario in (0, 1, 2, 4, 7, 10, 12):
+        out = subprocess.run([str(exe), str(scenario)], capture_output=True, text=True, timeout=900, env=env)
+        assert out.returncode == 0 and "ALL OK" in out.stdout and "ThreadSanitizer" not in out.stderr, \
+            (scenario, out.stdout, out.stderr[-3000:])

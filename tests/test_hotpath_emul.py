@@ -191,3 +191,26 @@ def test_random_windows_equal_the_oracle(emul, tmp_path, oracle_np):
             assert r["counts"] == (want["n_series"], want["n_candidates"], want["n_decisions"]), tag
             assert KAT.smax_equal(r["smax"].reshape(want["series_max"].shape), want["series_max"]), tag
     assert seen == {"ldg", "ldg+1", "tma", "u8"}
+
+
+def test_no_data_race_under_thread_sanitizer(tmp_path):
+    """reduce kernels + fold under ThreadSanitizer (see tests/test_fold_exchange_emul.py): publishing rows with atomics
+    into the pod masks, the scratch-set guard, the warp-private bulk-copy rings, the fold's ticket"""
+    (tmp_path / "hotpath_extract.inc").write_text(_extract())
+    exe = tmp_path / "hotpath_emul_tsan"
+    subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-Wno-unknown-pragmas",
+                    "-Wno-unused-function", "-I", str(tmp_path), os.path.join(ROOT, "tests", "cpp", "hotpath_emul.cpp"),
+                    "-o", str(exe)], check=True, capture_output=True, text=True)
+    kats = [k for k in KAT.all_kats() if k.util.shape[0] > 0]
+    pick = [k for k in kats if k.name in ("K1_all_zero", "K9_any_gpu", "K10_power_veto", "K11_age_phase_gate", "K12_pack_P65_G4")]
+    pick += [k for k in kats if k.name in ("K2_single_one_T37", "K2_single_one_T128", "K2_single_one_T450")]
+    assert len(pick) == 8, [k.name for k in kats]
+    dirs = []
+    for k in pick:
+        d = tmp_path / k.name
+        _write_case(str(d), k.util, k.power, k.power_threshold, k.eligible, k.created_ts, k.cutoff_ts)
+        dirs.append(str(d))
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1")
+    r = subprocess.run([str(exe)] + dirs, capture_output=True, text=True, timeout=1200, env=env)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+    assert len(r.stdout.splitlines()) >= 6 * len(dirs)
