@@ -214,3 +214,23 @@ def test_no_data_race_under_thread_sanitizer(tmp_path):
     r = subprocess.run([str(exe)] + dirs, capture_output=True, text=True, timeout=1200, env=env)
     assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
     assert len(r.stdout.splitlines()) >= 6 * len(dirs)
+
+
+def test_config_1_fixture_through_the_kernel_source(emul, tmp_path, oracle_np):
+    """BASELINE config #1 (100 pods x 4 GPUs x 1800 samples, the reference's own CPU-runnable case): the checked-in
+    idle set tests/golden/c1_idle_set.npz, reproduced by every kernel variant's source, with and without power."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_idle_set.npz"))
+    seed, P, G, T = int(g["seed"]), int(g["P"]), int(g["G"]), int(g["T"])
+    u = oracle_np.synth_fill(seed, 0, 0, P, G, T)
+    w = oracle_np.synth_fill(seed, 1, 0, P, G, T)
+    e = oracle_np.synth_eligible(seed, 0, P)
+    _write_case(str(tmp_path / "c1"), u, None, 0.0, e)
+    _write_case(str(tmp_path / "c1p"), u, w, float(g["power_threshold"]), e)
+    res = _run(emul, [tmp_path / "c1", tmp_path / "c1p"])
+    for name, dkey, nkey in (("c1", "decision_bits", "n_series"), ("c1p", "decision_bits_power", "n_series_power")):
+        runs = res[str(tmp_path / name)]
+        assert {r["variant"] for r in runs} >= {"ldg", "ldg+1", "tma", "u8", "tma#2"}
+        for r in runs:
+            assert r["clean"] and np.array_equal(r["d"], g[dkey]) and r["counts"][0] == int(g[nkey]), (name, r["variant"])
+            if name == "c1":
+                assert np.array_equal(r["c"], g["candidate_bits"]), r["variant"]
