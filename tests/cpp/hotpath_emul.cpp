@@ -157,8 +157,10 @@ static inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint6
 }
 static inline uint64_t l2_evict_first_policy() { return 0; }
 
+#define __host__
 namespace gpr {
 #include "hotpath_extract.inc"
+#include "synth_extract.inc"   // gpr_synth.cuh: the device generator of the synthetic windows (no PTX in it)
 }
 
 // ---- driver --------------------------------------------------------------------------------------------------------
@@ -272,6 +274,22 @@ static void run_variant(const std::string& dir, const char* name, const Case& c,
 }
 
 int main(int argc, char** argv) {
+  // --synth SEED P G T OUT_PREFIX : run the device generator's source, write <prefix>.util.f32 / .power.f32 / .elig.u8
+  if (argc == 7 && std::string(argv[1]) == "--synth") {
+    const uint64_t seed = strtoull(argv[2], nullptr, 0);
+    const uint32_t P = (uint32_t)atoi(argv[3]), G = (uint32_t)atoi(argv[4]), T = (uint32_t)atoi(argv[5]);
+    const std::string prefix = argv[6];
+    std::vector<float> buf((size_t)P * G * T);
+    for (int plane = 0; plane < 2; ++plane) {
+      launch(5, 64, 0, [&] { gpr::k_synth_fill(buf.data(), seed, plane, 0, P * G, T, T); });
+      std::ofstream(prefix + (plane ? ".power.f32" : ".util.f32"), std::ios::binary)
+          .write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)(buf.size() * 4));
+    }
+    std::vector<uint8_t> e(P);
+    launch(2, 64, 0, [&] { gpr::k_synth_eligible(e.data(), seed, 0, P); });
+    std::ofstream(prefix + ".elig.u8", std::ios::binary).write(reinterpret_cast<const char*>(e.data()), (std::streamsize)e.size());
+    return 0;
+  }
   for (int a = 1; a < argc; ++a) {
     const std::string dir = argv[a];
     Case c;

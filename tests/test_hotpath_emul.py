@@ -59,10 +59,18 @@ def _extract():
     return body
 
 
+def _extract_synth():
+    src = open(os.path.join(ROOT, "gpu-pruner_b200", "csrc", "gpr_synth.cuh")).read()
+    body = src[src.index("namespace gpr {") + len("namespace gpr {"):src.rindex("}  // namespace gpr")]
+    assert "asm" not in body
+    return body
+
+
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     d = tmp_path_factory.mktemp("hotpath")
     (d / "hotpath_extract.inc").write_text(_extract())
+    (d / "synth_extract.inc").write_text(_extract_synth())
     exe = d / "hotpath_emul"
     subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
                     "-I", str(d), os.path.join(ROOT, "tests", "cpp", "hotpath_emul.cpp"), "-o", str(exe)],
@@ -197,6 +205,7 @@ def test_no_data_race_under_thread_sanitizer(tmp_path):
     """reduce kernels + fold under ThreadSanitizer (see tests/test_fold_exchange_emul.py): publishing rows with atomics
     into the pod masks, the scratch-set guard, the warp-private bulk-copy rings, the fold's ticket"""
     (tmp_path / "hotpath_extract.inc").write_text(_extract())
+    (tmp_path / "synth_extract.inc").write_text(_extract_synth())
     exe = tmp_path / "hotpath_emul_tsan"
     subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-Wno-unknown-pragmas",
                     "-Wno-unused-function", "-I", str(tmp_path), os.path.join(ROOT, "tests", "cpp", "hotpath_emul.cpp"),
@@ -234,3 +243,19 @@ def test_config_1_fixture_through_the_kernel_source(emul, tmp_path, oracle_np):
             assert r["clean"] and np.array_equal(r["d"], g[dkey]) and r["counts"][0] == int(g[nkey]), (name, r["variant"])
             if name == "c1":
                 assert np.array_equal(r["c"], g["candidate_bits"]), r["variant"]
+
+
+def test_device_generator_source_equals_the_oracle_generators(emul, tmp_path, oracle_np, oracle_c):
+    """bench.py's parity check compares the decision on device-generated windows with the oracle's decision on
+    oracle-generated windows: the generators (gpr_synth.cuh, oracle/gpr_oracle.c, oracle/oracle_np.py) must produce
+    identical cells.  Checked on the GPU by tests/test_gpu_parity.py; here from the device generator's source."""
+    for seed, P, G, T in ((0x5EED0001, 100, 4, 1800), (0x5EED0002, 37, 8, 61), (7, 5, 1, 1)):
+        prefix = str(tmp_path / f"s{seed:x}")
+        subprocess.run([emul, "--synth", str(seed), str(P), str(G), str(T), prefix], check=True, timeout=600)
+        for plane, name in ((0, "util"), (1, "power")):
+            got = np.fromfile(f"{prefix}.{name}.f32", np.float32).reshape(P, G, T)
+            for orc in (oracle_np, oracle_c):
+                want = orc.synth_fill(seed, plane, 0, P, G, T)
+                assert np.array_equal(got.view(np.uint32) & 0x7fffffff >= 0x7f800001, np.isnan(want)), (seed, name)
+                assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(want, nan=-1.0)), (seed, name)
+        assert np.array_equal(np.fromfile(prefix + ".elig.u8", np.uint8), oracle_np.synth_eligible(seed, 0, P).astype(np.uint8))
