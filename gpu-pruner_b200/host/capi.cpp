@@ -107,10 +107,10 @@ GPH_API int gph_ingest(const char* util_json, const char* prof_json, const char*
       w = gph::ingest_matrix_text(us, prof_json ? &ps : nullptr, power_json ? &ws : nullptr, o,
                                   g_ingest_threads);
     } else {
-      gph::Json u = gph::Json::parse(util_json), pf, pw;
+      gph::Json u = gph::Json::parse(util_json, 2), pf, pw;   // (2: the response envelope is a struct)
       const gph::Json *ppf = nullptr, *ppw = nullptr;
-      if (prof_json) pf = gph::Json::parse(prof_json), ppf = &pf;
-      if (power_json) pw = gph::Json::parse(power_json), ppw = &pw;
+      if (prof_json) pf = gph::Json::parse(prof_json, 2), ppf = &pf;
+      if (power_json) pw = gph::Json::parse(power_json, 2), ppw = &pw;
       w = gph::ingest_matrix(u, ppf, ppw, o);
     }
     if (!g_dmi_json.empty()) gph::apply_node_types(w, gph::Json::parse(g_dmi_json));

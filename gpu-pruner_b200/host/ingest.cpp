@@ -31,7 +31,12 @@ const Json& result_array(const Json& resp) {
 }
 
 double sample_value(const Json& v) {
-  if (v.is_string()) return strtod(v.as_string().c_str(), nullptr);  // "NaN", "+Inf", "0.37"
+  if (v.is_string()) {  // "NaN", "+Inf", "0.37" — and nothing that is not a number (see strict_sample_value)
+    const std::string& t = v.as_string();
+    double d;
+    if (!detail::strict_sample_value(t.data(), t.data() + t.size(), &d)) detail::bad("sample value is not a number");
+    return d;
+  }
   return v.as_number(std::numeric_limits<double>::quiet_NaN());
 }
 
@@ -59,14 +64,20 @@ Window ingest_matrix(const Json& util, const Json* prof, const Json* power, cons
         // still counts as skipped if it could not have been converted
         continue;
       }
-      if (asg.assign(s["metric"], is_power, is_prof, &p, &slot) != Assigner::Placed) continue;
-      (is_power ? pseries : useries).push_back(RawSeries{p, slot, &vals});
+      // Whose samples are read: every series that is placed or skipped (a sample that is not [time, "number"] fails
+      // the query as it fails the reference's decode, wherever it sits — in the window or not); a UTIL series shadowed
+      // by a PROF series of the same label set is not opened by any of the three ingest paths.
+      const Assigner::Result placed = asg.assign(s["metric"], is_power, is_prof, &p, &slot);
+      if (placed == Assigner::Shadowed) continue;
+      if (placed == Assigner::Placed) (is_power ? pseries : useries).push_back(RawSeries{p, slot, &vals});
       int64_t prev = kNoTs;
       for (const Json& tv : vals.items()) {
         // a sample is exactly [ <unix time>, "<value>" ]; anything else is a malformed response
-        // (both paths reject it, the tick then counts as a query failure, main.rs:310-321)
+        // (all paths reject it, the tick then counts as a query failure, main.rs:310-321)
         if (!tv.is_array() || tv.size() != 2 || !tv[0].is_number())
           throw std::runtime_error("matrix response: sample is not [time, value]");
+        (void)sample_value(tv[1]);
+        if (placed != Assigner::Placed) continue;
         const int64_t ts = ts_seconds(tv[0].as_number());
         if (ts == kBadTs) continue;
         newest = std::max(newest, ts);
@@ -120,13 +131,18 @@ Window ingest_matrix_text(const std::string& util, const std::string* prof, cons
       const char* v = skip_ws(s.values_b + 1, s.values_e);
       if (v < s.values_e && *v == ']') continue;  // no sample in range: no element
       uint32_t p, slot;
+      Assigner::Result placed;
       if (flat.parse(s.metric_b, s.metric_e)) {  // Prometheus' own shape: read in place
-        if (asg.assign(flat, is_power, is_prof, &p, &slot) != Assigner::Placed) continue;
+        placed = asg.assign(flat, is_power, is_prof, &p, &slot);
       } else {
         const Json metric = Json::parse(std::string(s.metric_b, s.metric_e));
-        if (asg.assign(metric, is_power, is_prof, &p, &slot) != Assigner::Placed) continue;
+        placed = asg.assign(metric, is_power, is_prof, &p, &slot);
       }
-      (is_power ? pseries : useries).push_back(TextSeries{p, slot, s.values_b, s.values_e, true});
+      if (placed == Assigner::Placed) {
+        (is_power ? pseries : useries).push_back(TextSeries{p, slot, s.values_b, s.values_e, true});
+      } else if (placed == Assigner::Skipped) {
+        for_each_sample(s.values_b, s.values_e, [](double, double) {});  // no row, but its samples are still vetted
+      }
     }
   };
   if (prof) scan(*prof, false, true);

@@ -137,8 +137,8 @@ Workers& label_workers() {
   return w;
 }
 
-// [[ts,"v"],[ts,"v"],...] exactly as Prometheus prints it: digits with an optional fraction, a quoted value without
-// quotes or escapes inside, no white space.  (Anything else is for the CPU parser to judge.)
+// [[ts,"v"],[ts,"v"],...] exactly as Prometheus prints it: digits with an optional fraction, a quoted number
+// (strict_sample_value), no white space.  (Anything else is for the CPU parser to judge.)
 bool samples_are_compact(const char* p, const char* e) {
   if (p >= e || *p++ != '[') return false;
   if (p < e && *p == ']') return p + 1 == e;
@@ -155,8 +155,9 @@ bool samples_are_compact(const char* p, const char* e) {
     if (e - p < 2 || p[0] != ',' || p[1] != '"') return false;
     p += 2;
     d = p;
-    while (p < e && *p != '"' && *p != '\\' && (unsigned char)*p >= 0x20) ++p;
-    if (p == d || e - p < 2 || p[0] != '"' || p[1] != ']') return false;
+    while (p < e && *p != '"') ++p;
+    double v;
+    if (e - p < 2 || p[1] != ']' || !detail::strict_sample_value(d, p, &v)) return false;
     p += 2;
     if (p >= e) return false;
     if (*p == ']') return p + 1 == e;

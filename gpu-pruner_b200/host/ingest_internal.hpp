@@ -625,6 +625,31 @@ slow : {
 }
 }
 
+// A sample value is what Rust's f64::from_str accepts (the reference decodes it that way: prometheus-http-query 0.8.3
+// behind main.rs:405-409, so a value that is not a number fails the whole query) — decimal digits with optional sign,
+// fraction and exponent, "NaN", "Inf" / "Infinity" with optional sign, nothing around it.  strtod is more generous
+// (hex floats, leading white space, "nan(...)", a valid prefix followed by garbage): those are refused here, because
+// garbage read as 0.0 is an idle GPU.
+inline bool strict_sample_value(const char* b, const char* e, double* out) {
+  const size_t n = (size_t)(e - b);
+  char buf[64];
+  if (n == 0 || n + 1 > sizeof buf) return false;
+  for (size_t i = 0; i < n; ++i) {
+    const char c = b[i];
+    const bool ok = (c >= '0' && c <= '9') || c == '+' || c == '-' || c == '.' || c == 'e' || c == 'E' ||
+                    c == 'N' || c == 'n' || c == 'a' || c == 'A' || c == 'I' || c == 'i' || c == 'f' || c == 'F' ||
+                    c == 't' || c == 'T' || c == 'y' || c == 'Y';
+    if (!ok) return false;
+    buf[i] = c;
+  }
+  buf[n] = 0;
+  char* ep = nullptr;
+  const double v = strtod(buf, &ep);
+  if (ep != buf + n) return false;
+  *out = v;
+  return true;
+}
+
 // walks [[ts,"v"],[ts,"v"],...] calling f(ts, value)
 template <typename F>
 void for_each_sample(const char* p, const char* e, F&& f) {
@@ -642,19 +667,20 @@ void for_each_sample(const char* p, const char* e, F&& f) {
     p = skip_ws(p + 1, e);
     double v;
     if (p < e && *p == '"') {
-      v = parse_number(p + 1, e, &q);
-      if (q < e && *q != '"') {  // "NaN", "+Inf", ...
-        char buf[32];
-        size_t n = 0;
-        const char* r = p + 1;
-        while (r < e && *r != '"' && n + 1 < sizeof buf) buf[n++] = *r++;
-        buf[n] = 0;
-        v = strtod(buf, nullptr);
-        q = r;
+      const char* r = p + 1;
+      bool plain = true;  // sign, digits, point: the exact fast path; everything else ("NaN", "+Inf", "5e-07") is vetted
+      for (; r < e && *r != '"'; ++r) plain = plain && ((*r >= '0' && *r <= '9') || *r == '.' || *r == '-' || *r == '+');
+      if (r >= e) bad("unterminated sample value");
+      if (plain) {
+        v = parse_number(p + 1, r, &q);
+        if (q != r || r == p + 1) bad("sample value is not a number");
+      } else if (!strict_sample_value(p + 1, r, &v)) {
+        bad("sample value is not a number");
       }
-      p = q + 1;
+      p = r + 1;
     } else {
       v = parse_number(p, e, &q);
+      if (q == p) bad("sample value is not a number");
       p = q;
     }
     p = skip_ws(p, e);

@@ -14,6 +14,7 @@ const Json kNull;
 struct Parser {
   const std::string& t;
   size_t i = 0;
+  int struct_depth = 0;
   explicit Parser(const std::string& text) : t(text) {}
 
   [[noreturn]] void err(const char* what) const {
@@ -107,6 +108,7 @@ struct Parser {
         ws();
         if (i >= t.size() || t[i] != ':') err("expected ':'");
         ++i;
+        if (depth < struct_depth && o.find(k)) err("duplicate member name");
         o.set(k, value(depth + 1));
         ws();
         if (i < t.size() && t[i] == ',') { ++i; continue; }
@@ -233,8 +235,9 @@ std::string Json::dump() const {
   return s;
 }
 
-Json Json::parse(const std::string& text) {
+Json Json::parse(const std::string& text, int struct_depth) {
   Parser p(text);
+  p.struct_depth = struct_depth;
   Json v = p.value(0);
   p.ws();
   if (p.i != text.size()) p.err("trailing characters");

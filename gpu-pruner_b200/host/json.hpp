@@ -52,7 +52,10 @@ class Json {
   Json& push(Json v);                          // array
 
   std::string dump() const;                    // compact, deterministic
-  static Json parse(const std::string& text);  // throws std::runtime_error with offset
+  // throws std::runtime_error with offset.  struct_depth: objects nested less deep than this are decoded like structs —
+  // a repeated member name is an error (a response envelope {status, data: {resultType, result}} is one in the
+  // reference's decoder: struct_depth = 2); deeper objects are maps, the last value wins.
+  static Json parse(const std::string& text, int struct_depth = 0);
   static Json parse_file(const std::string& path);
 
  private:

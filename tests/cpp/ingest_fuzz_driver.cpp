@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
       ok_text = false;
     }
     try {
-      wd = ingest_matrix(Json::parse(s), nullptr, nullptr, o);
+      wd = ingest_matrix(Json::parse(s, 2), nullptr, nullptr, o);
     } catch (const std::exception&) {
       ok_dom = false;
     }

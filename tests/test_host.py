@@ -8,6 +8,7 @@
 * the owner-walk scenarios of /root/reference/gpu-pruner/tests/e2e.rs:168-252 on JSON fixtures
 * ingest of the Prometheus matrix wire format (querytest.rs:41-53)
 """
+import ctypes as C
 import json
 import os
 import subprocess
@@ -664,3 +665,66 @@ def test_text_ingest_accepts_every_json_layout():
             assert dims == ref[0] and np.array_equal(u.view(np.uint32), ref[1].view(np.uint32)), (name, mode)
             assert m == ref[2], (name, mode)
     H.ingest_mode(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# a sample value that is not a number fails the query (the reference decodes it with f64::from_str through
+# prometheus-http-query, main.rs:405-409) — it must never be read as 0.0, which is an idle GPU
+# ---------------------------------------------------------------------------------------------
+def _one_series(value):
+    lab = {"__name__": "DCGM_FI_DEV_GPU_UTIL", "Hostname": "n", "gpu": "0", "modelName": "m", "exported_pod": "p",
+           "exported_namespace": "ns", "exported_container": "c"}
+    return {"status": "success", "data": {"resultType": "matrix", "result": [
+        {"metric": lab, "values": [[1_700_000_000 - 1, "7"], [1_700_000_000, value]]}]}}
+
+
+@pytest.mark.parametrize("value", ["abc", "", "0x10", "1e", "0.5x", " 1", "1 ", "1,5", "nan(1)", "1.2.3", "--1", "0.5e+", "٣"])
+def test_a_sample_value_that_is_not_a_number_fails_the_query(value):
+    with pytest.raises(RuntimeError) as ei:
+        H.ingest(_one_series(value), duration_min=1, step=1, t_end=1_700_000_000)
+    assert "not a number" in str(ei.value)
+
+
+@pytest.mark.parametrize("value, want", [("0", 0.0), ("-0", -0.0), ("+3", 3.0), ("12.25", 12.25), ("1e2", 100.0), ("1E1", 10.0),
+                                          ("5e-07", 5e-07), ("NaN", float("nan")), ("+Inf", float("inf")), ("-Inf", float("-inf")),
+                                          ("Inf", float("inf")), ("0.30000000000000004", 0.30000000000000004), (".5", 0.5), ("5.", 5.0)])
+def test_every_spelling_prometheus_prints_is_a_number(value, want):
+    u, _, _ = H.ingest(_one_series(value), duration_min=1, step=1, t_end=1_700_000_000)
+    got = float(u[0, 0, -1])
+    assert (got != got and want != want) or got == np.float32(want), (value, got)
+
+
+def test_garbage_is_garbage_wherever_it_sits():
+    """out of the window, or in a series that gets no row: the reference's decode reads every sample of the response"""
+    T = 1_700_000_000
+    good = _one_series("7")["data"]["result"][0]
+    orphan = {"metric": {k: v for k, v in good["metric"].items() if k != "exported_pod"}, "values": [[T, "abc"]]}
+    for series in ([{"metric": good["metric"], "values": [[T - 5000, "abc"], [T, "7"]]}], [good, orphan],
+                   [good, {"metric": orphan["metric"], "values": [[T, "7"], "x"]}]):
+        with pytest.raises(RuntimeError):
+            H.ingest({"status": "success", "data": {"resultType": "matrix", "result": series}}, duration_min=1, step=1, t_end=T)
+    orphan["values"] = [[T, "NaN"]]
+    u, _, meta = H.ingest({"status": "success", "data": {"resultType": "matrix", "result": [good, orphan]}},
+                          duration_min=1, step=1, t_end=T)
+    assert u.shape[0] == 1
+
+
+def test_repeated_envelope_field_fails_the_decode():
+    """`{"status":…,"data":…,"data":{…}}`: the envelope is a struct in the reference's decoder (a repeated field is
+    an error); found by a long run of the parser fuzz, where the DOM path took the last `data` and the text path the
+    first.  Repeated LABELS are a map there: the last value wins, in every path."""
+    T = 1_700_000_000
+    good = _one_series("7")
+    text = json.dumps(good, separators=(",", ":")).replace('"data":{', '"data":"success","data":{', 1)
+    for mode in (-1, 1, 4):
+        H.ingest_mode(mode)
+        rc = H.lib().gph_ingest(text.encode(), None, None, C.c_longlong(1), C.c_longlong(1), C.c_longlong(T),
+                                (C.c_uint * 3)(), None, None, C.create_string_buffer(1 << 16), 1 << 16)
+        assert rc != 0, mode
+    dup_label = json.dumps(good, separators=(",", ":")).replace('"gpu":"0"', '"gpu":"9","gpu":"0"', 1)
+    for mode in (-1, 1):
+        H.ingest_mode(mode)
+        dims = (C.c_uint * 3)()
+        assert H.lib().gph_ingest(dup_label.encode(), None, None, C.c_longlong(1), C.c_longlong(1), C.c_longlong(T),
+                                  dims, None, None, C.create_string_buffer(1 << 16), 1 << 16) == 0
+        assert tuple(dims) == (1, 1, 60)
