@@ -16,8 +16,21 @@
 #include <stdexcept>
 #include <string>
 
+#ifdef EMUL_PARSE_KERNEL
+// The parse pass runs the SOURCE of k_text_parse (gpu-pruner_b200/csrc/gpr_text_kernels.cuh, cut out verbatim into
+// text_kernel_extract.inc by the test) as real threads — warps compacting '[' offsets with shuffles, the two-stage
+// bulk-copy ring, one candidate per lane — instead of the tile-by-tile loop below.
+#include "cuda_shim.hpp"
+#endif
 #include "../../gpu-pruner_b200/csrc/gpr_text.cuh"
 #include "ingest_device.hpp"
+#ifdef EMUL_PARSE_KERNEL
+namespace gpr {
+namespace text {
+#include "text_kernel_extract.inc"
+}
+}
+#endif
 
 using namespace gph;
 namespace tx = gpr::text;
@@ -90,6 +103,21 @@ class EmulDevice : public TextDevice {
     const uint64_t n = n_[slot];
     const tx::Span* sp = reinterpret_cast<const tx::Span*>(spans.data());
     const uint64_t tiles = (n + tx::kTileBytes - 1) / tx::kTileBytes;
+#ifdef EMUL_PARSE_KERNEL
+    if (!spans.empty() && n) {
+      // as gpr_text_parse launches it (gpr_api.cu), on a small grid so that warps own several tiles each
+      constexpr int kWarps = 4;
+      const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, 2));
+      tx::Span* dsp = reinterpret_cast<tx::Span*>(spans.data());
+      float* dpl = reinterpret_cast<float*>(pl.data());
+      const uint32_t n_spans = (uint32_t)spans.size();
+      launch(blocks, kWarps * 32, tx::text_parse_smem<kWarps>(), [&] {
+        tx::k_text_parse<kWarps>(text.data(), n, n + tx::kTextPad, dsp, n_spans, g, dpl);
+      });
+    }
+    (void)sp, (void)sink;
+    return;
+#endif
     // what a warp sees: one tile plus the halo, nothing else (bytes beyond are poisoned); tiles in reverse
     // order and candidates from the back: nothing may depend on the order things run in
     struct Tile {

@@ -16,14 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "gpu-pruner_b200", "host")
 
 
-@pytest.fixture(scope="module")
-def driver(tmp_path_factory):
-    out = tmp_path_factory.mktemp("emul_ticks") / "text_emul"
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
-                           "-I", HOST, os.path.join(ROOT, "tests", "cpp", "text_emul.cpp"),
-                           os.path.join(HOST, "ingest.cpp"), os.path.join(HOST, "ingest_device.cpp"),
-                           os.path.join(HOST, "json.cpp"), "-o", str(out), "-lpthread"])
-    return str(out)
+@pytest.fixture(scope="module", params=["tiles", "kernel"])
+def driver(request, tmp_path_factory):
+    """both flavours of the emulated device (tests/emul_build.py): parser core tile by tile / k_text_parse's source"""
+    import emul_build
+    return emul_build.build(tmp_path_factory.mktemp("emul_ticks_" + request.param), request.param)
 
 
 def _run(driver, root, duration_min):
@@ -132,11 +129,8 @@ def test_many_series_worker_pool_under_thread_sanitizer(tmp_path):
     """More series than the worker pool's threshold (256): the label maps of a tick are parsed on several threads
     (ingest_device.cpp Workers / plan_text).  Same invariant as everywhere in this file — the ring equals a fresh
     full-range ingest at every tick — with the emulator built under ThreadSanitizer."""
-    exe = tmp_path / "text_emul_tsan"
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-fno-omit-frame-pointer",
-                           "-I", HOST, os.path.join(ROOT, "tests", "cpp", "text_emul.cpp"),
-                           os.path.join(HOST, "ingest.cpp"), os.path.join(HOST, "ingest_device.cpp"),
-                           os.path.join(HOST, "json.cpp"), "-o", str(exe), "-lpthread"])
+    import emul_build
+    exe = emul_build.build(tmp_path, "kernel", sanitize="thread")   # worker pool AND the parse kernel's threads
     rng = random.Random(77)
     N, step, interval = 60, 5, 15
     t0 = 1_700_000_000

@@ -18,15 +18,11 @@ HOST = os.path.join(ROOT, "gpu-pruner_b200", "host")
 T_END = 1_700_000_000
 
 
-@pytest.fixture(scope="module")
-def driver(tmp_path_factory):
-    out = tmp_path_factory.mktemp("emul") / "text_emul"
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
-           "-I", HOST, os.path.join(ROOT, "tests", "cpp", "text_emul.cpp"),
-           os.path.join(HOST, "ingest.cpp"), os.path.join(HOST, "ingest_device.cpp"), os.path.join(HOST, "json.cpp"),
-           "-o", str(out), "-lpthread"]
-    subprocess.check_call(cmd)
-    return str(out)
+@pytest.fixture(scope="module", params=["tiles", "kernel"])
+def driver(request, tmp_path_factory):
+    """both flavours of the emulated device (tests/emul_build.py): parser core tile by tile / k_text_parse's source"""
+    import emul_build
+    return emul_build.build(tmp_path_factory.mktemp("emul_" + request.param), request.param)
 
 
 def _run(driver, dirs, step=1, duration_min=1, t_end=T_END):

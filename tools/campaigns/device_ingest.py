@@ -1,6 +1,6 @@
 """Long differential run of the device ingest on the emulated device (tests/cpp/text_emul.cpp) against the CPU text
 parser, well-formed and mutated responses:  device_ingest.py DRIVER SEED ROUNDS   (120 responses per round)
-DRIVER = text_emul built as in tests/test_text_device_cpu.py (ASan + UBSan)."""
+DRIVER = text_emul in either flavour, built by tests/emul_build.py (ASan + UBSan): build(dir, "tiles" | "kernel")."""
 import sys, os, random, subprocess, tempfile, pathlib, shutil
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'tests'))
 import test_text_device_cpu as T
