@@ -154,6 +154,16 @@ class EmulDevice : public TextDevice {
     if (with_power) ring_[1].assign((size_t)ring_rows_ * T, tx::kFillBits);
   }
   void resident_advance(uint32_t n_new) override {
+#ifdef EMUL_PARSE_KERNEL
+    for (auto& pl : ring_) {   // the source of k_fill_columns, as gpr_resident_advance launches it
+      if (pl.empty()) continue;
+      float* p = reinterpret_cast<float*>(pl.data());
+      const uint32_t rows = ring_rows_, T = ring_T_, head = ring_head_;
+      launch(2, 256, 0, [&] { tx::k_fill_columns(p, rows, T, (uint64_t)T, head, n_new); });
+    }
+    ring_head_ = (ring_head_ + n_new) % ring_T_;
+    return;
+#endif
     for (auto& pl : ring_)
       for (size_t r = 0; r * ring_T_ < pl.size(); ++r)
         for (uint32_t i = 0; i < n_new; ++i) pl[r * ring_T_ + (ring_head_ + i) % ring_T_] = tx::kFillBits;

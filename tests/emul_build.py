@@ -12,13 +12,12 @@ HOST = os.path.join(ROOT, "gpu-pruner_b200", "host")
 
 def extract_parse_kernel():
     src = open(os.path.join(ROOT, "gpu-pruner_b200", "csrc", "gpr_text_kernels.cuh")).read()
-    body = src[src.index("// NaN-aware max into a cell that starts as kFillBits"):
-               src.index("// NaN-fill `n_cols` columns starting at ring position")]
+    body = src[src.index("// NaN-aware max into a cell that starts as kFillBits"):src.index("}  // namespace text")]
     for old, new in (('asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', ";"),
                      ("extern __shared__ __align__(128) unsigned char smem[];", "unsigned char* smem = tl_cta->smem;")):
         assert body.count(old) == 1, old
         body = body.replace(old, new)
-    assert "asm" not in body and "__shared__" not in body and "k_text_parse" in body
+    assert "asm" not in body and "__shared__" not in body and "k_text_parse" in body and "k_fill_columns" in body
     return body
 
 
